@@ -1,0 +1,504 @@
+"""Stateless NumPy restatement of the reference's OFDM modem arithmetic (TEST INFRASTRUCTURE ONLY).
+
+Every function cites the reference file:line it follows, relative to
+/root/reference/GNU-Radio-Repositories/ (abbreviated GRR/).  All arithmetic is complex128 like the
+reference (NumPy promotes the complex64 stream).  Two styles are provided where the reference's
+cost structure matters for the CPU baseline:
+
+  * ``literal=True``  keeps the reference's dense ``diag`` matmuls and Python-level loops
+    (this is what a GNU Radio thread running the reference block actually executes);
+  * ``literal=False`` is the mathematically identical element-wise form.
+
+Parity status is described in oracle/__init__.py (pinned for N=64/QPSK by the golden fixtures;
+"our definition" for everything the reference has no arithmetic for).
+"""
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+TWO_PI = 2.0 * np.pi
+
+
+# --------------------------------------------------------------------------------------------
+# parameters
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ModemParams:
+    """Numerology of one modem instance.
+
+    nfft, cp_len, num_synch_bins, synch_dat=[M0, D], num_data_bins are the reference block's ctor
+    arguments (GRR/gr-utsa_ofdm/python/SynchAndChanEst.py:17-19).  ``compat`` selects which of the
+    two live RX variants' constants are reproduced:
+
+      "utsa"   : ZC root 23, search stride 1, gate = scale_factor_gate, regulariser 10**(snr/20)
+      "rxofdm" : ZC root 37, search stride CP-1, gate 0.4, regulariser = snr taken as linear
+    """
+    nfft: int = 64
+    cp_len: int = 16
+    num_synch_bins: int = 62
+    num_data_bins: int = 60
+    m0: int = 1                      # consecutive synch symbols per frame  (synch_dat[0])
+    d: int = 3                       # data symbols per frame               (synch_dat[1])
+    bps: int = 2                     # bits per data bin: 1 BPSK, 2 QPSK, 4 16-QAM, 6 64-QAM
+    snr: float = 100.0               # the block's "snr" ctor argument, meaning depends on compat
+    gate: float = 0.7                # scale_factor_gate (utsa); rxofdm hard-codes 0.4
+    compat: str = "utsa"
+    zc_root: Optional[int] = None    # default: 23 (utsa) / 37 (rxofdm)
+    equalizer: str = "mmse"          # "mmse" (reference) or "zf" (extension: regulariser -> 0)
+    sync_advance: int = 0            # framed mode: how many samples before the CP end the window opens
+
+    def __post_init__(self):
+        if self.zc_root is None:
+            self.zc_root = 23 if self.compat == "utsa" else 37
+        if self.compat == "rxofdm":
+            self.gate = 0.4
+
+    # derived -------------------------------------------------------------------------------
+    @property
+    def sym_len(self):               # rx_b_len, GRR/gr-utsa_ofdm/python/SynchAndChanEst.py:79
+        return self.nfft + self.cp_len
+
+    @property
+    def frame_syms(self):
+        return self.m0 + self.d
+
+    @property
+    def frame_len(self):
+        return self.frame_syms * self.sym_len
+
+    @property
+    def mm(self):                    # MM, SynchAndChanEst.py:48-49
+        return self.m0 * self.num_synch_bins
+
+    @property
+    def stride(self):                # SynchAndChanEst.py:77 vs gr-RXOFDM/python/synch_and_chan_est.py:81
+        return 1 if self.compat == "utsa" else self.cp_len - 1
+
+    @property
+    def reg_chanest(self):
+        """x in  H = r*conj(zc) / (1 + 1/x).  utsa: SynchAndChanEst.py:99,180; rxofdm: :184."""
+        return 10.0 ** (self.snr / 20.0) if self.compat == "utsa" else float(self.snr)
+
+    @property
+    def reg_eq(self):
+        """x in  g = conj(H)/(|H|^2 + 1/x) for DATA symbols.  utsa :245; rxofdm :247."""
+        if self.equalizer == "zf":
+            return np.inf
+        return 10.0 ** (self.snr / 20.0) if self.compat == "utsa" else float(self.snr)
+
+    @property
+    def reg_eq_synch(self):
+        """x for the synch-symbol equaliser (raw snr in both variants: utsa :214, rxofdm :217)."""
+        return float(self.snr)
+
+
+# --------------------------------------------------------------------------------------------
+# a1  bin maps
+# --------------------------------------------------------------------------------------------
+def signed_bins(n):
+    """-n/2..-1, 1..n/2  (DC skipped).  SynchAndChanEst.py:38-39, :68-69; SDRScript.py:61."""
+    h = int(n / 2)
+    return list(range(-h, 0)) + list(range(1, h + 1))
+
+
+def bins_used(n, nfft):
+    """FFT indices of the used bins: (b + N) % N.  SynchAndChanEst.py:41,:70; MultiAntennaSystem.py:14."""
+    return (np.array(signed_bins(n), dtype=np.int64) + nfft) % nfft
+
+
+# --------------------------------------------------------------------------------------------
+# a2  Zadoff-Chu
+# --------------------------------------------------------------------------------------------
+def zadoff_chu(mm, root, parity_of=None):
+    """zc[k] = exp(-j*2pi/MM * p * k^2/2)  (even)  or  exp(-j*2pi/MM * p * k(k+1)/2)  (odd).
+
+    utsa / TX simulator test the parity of MM (SynchAndChanEst.py:54-59, SynchSignal.py:24-30);
+    gr-RXOFDM tests the parity of num_synch_bins instead (synch_and_chan_est.py:54-64): pass it as
+    ``parity_of``.
+    """
+    k = np.arange(int(mm), dtype=np.float64)
+    par = mm if parity_of is None else parity_of
+    if par % 2 == 0:
+        q = k * k / 2.0
+    else:
+        q = k * (k + 1.0) / 2.0
+    return np.exp(-1j * (TWO_PI / mm) * root * q)
+
+
+def zc_for(prm: ModemParams):
+    par = prm.mm if prm.compat == "utsa" else prm.num_synch_bins
+    return zadoff_chu(prm.mm, prm.zc_root, par)
+
+
+# --------------------------------------------------------------------------------------------
+# a3  bit -> symbol map
+# --------------------------------------------------------------------------------------------
+_QPSK_EIGHTHS = np.array([1.0, -1.0, 3.0, 5.0])       # MultiAntennaSystem.py:171-178
+
+
+def pam_levels(bits_per_axis):
+    """Gray-coded PAM amplitude for each bit pattern (MSB first), 3GPP TS 36.211 7.1 layout.
+
+    1 bit : (1-2b0)
+    2 bits: (1-2b0)*(2-(1-2b1))
+    3 bits: (1-2b0)*(4-(1-2b1)*(2-(1-2b2)))
+    Unpinned extension (the reference only has BPSK/QPSK).  Returned un-normalised.
+    """
+    n = 1 << bits_per_axis
+    lev = np.zeros(n)
+    for v in range(n):
+        b = [(v >> (bits_per_axis - 1 - i)) & 1 for i in range(bits_per_axis)]
+        if bits_per_axis == 1:
+            a = 1 - 2 * b[0]
+        elif bits_per_axis == 2:
+            a = (1 - 2 * b[0]) * (2 - (1 - 2 * b[1]))
+        else:
+            a = (1 - 2 * b[0]) * (4 - (1 - 2 * b[1]) * (2 - (1 - 2 * b[2])))
+        lev[v] = a
+    return lev
+
+
+QAM_NORM = {2: np.sqrt(2.0), 4: np.sqrt(10.0), 6: np.sqrt(42.0)}
+
+
+def constellation(bps):
+    """All 2**bps points indexed by the MSB-first decimal value of the bin's bits."""
+    if bps == 1:
+        return np.array([-1.0 + 0j, 1.0 + 0j])          # 2*b-1, MultiAntennaSystem.py:156-157
+    if bps == 2:
+        return np.exp(1j * TWO_PI / 8.0 * _QPSK_EIGHTHS)  # MultiAntennaSystem.py:171-178
+    half = bps // 2
+    lev = pam_levels(half) / QAM_NORM[bps]
+    pts = np.zeros(1 << bps, dtype=complex)
+    for v in range(1 << bps):
+        # even-position bits (b0,b2,b4) drive I, odd-position bits (b1,b3,b5) drive Q -- the same
+        # convention as the reference's QPSK (b0 -> sign of Re, b1 -> sign of Im).
+        bi = bq = 0
+        for i in range(half):
+            bi = (bi << 1) | ((v >> (bps - 1 - 2 * i)) & 1)
+            bq = (bq << 1) | ((v >> (bps - 2 - 2 * i)) & 1)
+        pts[v] = lev[bi] + 1j * lev[bq]
+    return pts
+
+
+def bits_to_symbols(bits, bps):
+    """bits: [..., n*bps] of 0/1 -> complex [..., n].  MSB first (MultiAntennaSystem.py:160-170)."""
+    bits = np.asarray(bits)
+    n = bits.shape[-1] // bps
+    b = bits.reshape(bits.shape[:-1] + (n, bps)).astype(np.int64)
+    w = 1 << np.arange(bps - 1, -1, -1)
+    dec = (b * w).sum(-1)
+    return constellation(bps)[dec]
+
+
+# --------------------------------------------------------------------------------------------
+# a3/a4  frequency-grid assembly (bit map + synch-symbol insertion)
+# --------------------------------------------------------------------------------------------
+def tx_freq_grid(bits, prm: ModemParams, n_frames):
+    """[n_frames*(M0+D), N] frequency grid.  MultiAntennaSystem.py:135-183, SDRScript.py:79-85.
+
+    ``bits`` is a flat 0/1 array of n_frames*D*ndb*bps payload bits.  The synch symbols carry the
+    first num_synch_bins entries of the ZC sequence (synch_state never advances in the reference:
+    MultiAntennaSystem.py:143-146 re-reduces it modulo M0 but never increments it).
+    """
+    N = prm.nfft
+    zc = zadoff_chu(prm.mm, prm.zc_root)            # TX side always keys parity on MM (SynchSignal.py:24)
+    sb = bins_used(prm.num_synch_bins, N)
+    db = bins_used(prm.num_data_bins, N)
+    per_sym = prm.num_data_bins * prm.bps
+    bits = np.asarray(bits).reshape(-1)
+    assert bits.size == n_frames * prm.d * per_sym
+    grid = np.zeros((n_frames * prm.frame_syms, N), dtype=complex)
+    data_i = 0
+    for f in range(n_frames):
+        for s in range(prm.frame_syms):
+            row = f * prm.frame_syms + s
+            if s < prm.m0:
+                grid[row, sb] = zc[0:prm.num_synch_bins]
+            else:
+                chunk = bits[data_i * per_sym:(data_i + 1) * per_sym]
+                grid[row, db] = bits_to_symbols(chunk, prm.bps)
+                data_i += 1
+    return grid
+
+
+# --------------------------------------------------------------------------------------------
+# a5  IFFT + CP add + power normalise
+# --------------------------------------------------------------------------------------------
+def tx_symb_gen(grid, cp_len):
+    """Per symbol: ifft -> [last CP samples, body] -> unit energy/sample -> divide by sqrt(var).
+
+    MultiAntennaSystem.py:189-219 (single antenna).  Returns the flat time waveform.
+    """
+    n_sym, N = grid.shape
+    L = N + cp_len
+    out = np.zeros(n_sym * L, dtype=complex)
+    for s in range(n_sym):
+        body = np.fft.ifft(grid[s], N)
+        t = np.concatenate((body[N - cp_len:], body))
+        energy = abs(np.dot(t, np.conj(t)))
+        scale = np.sqrt(L / energy) if energy > 1e-30 else 1.0
+        t = t * scale
+        t = t * (1.0 / np.sqrt(np.var(t)))
+        out[s * L:(s + 1) * L] = t
+    return out
+
+
+def tx_modulate(bits, prm: ModemParams, n_frames):
+    return tx_symb_gen(tx_freq_grid(bits, prm, n_frames), prm.cp_len)
+
+
+# --------------------------------------------------------------------------------------------
+# a7  channel + AWGN (test bench)
+# --------------------------------------------------------------------------------------------
+REF_TAPS = np.array([0.3977, 0.7954 - 0.3977j, -0.1988, 0.0994, -0.0398])  # MultiAntennaSystem.py:64
+
+
+def reference_channel(nfft, kind="Fading"):
+    """N-tap zero-padded impulse response.  MultiAntennaSystem.py:79-90 ('AWGN' = one-sample delay)."""
+    h = np.zeros(nfft, dtype=complex)
+    if kind == "AWGN":
+        h[1] = 1.0
+    elif kind == "Ideal":
+        h[0] = 1.0
+    else:
+        h[0:len(REF_TAPS)] = REF_TAPS / np.linalg.norm(REF_TAPS)
+    return h
+
+
+def apply_channel(tx, h):
+    """np.convolve(tx, h): MultiAntennaSystem.py:221-231."""
+    return np.convolve(tx, h)
+
+
+def noise_variance(tx, prm: ModemParams, snr_db, snr_type="Digital"):
+    """MultiAntennaSystem.py:236-246."""
+    sig_pow = np.var(tx)
+    if snr_type == "Digital":
+        return (1.0 / (prm.num_data_bins * prm.bps)) * prm.sym_len * sig_pow * 10 ** (-snr_db / 10.0)
+    return sig_pow * 10 ** (-snr_db / 10.0)
+
+
+def add_awgn(x, noise_var, rng):
+    """Complex AWGN of total variance noise_var.  MultiAntennaSystem.py:257-260 (seeded here)."""
+    s = np.sqrt(noise_var / 2.0)
+    return x + s * rng.standard_normal(x.shape) + 1j * s * rng.standard_normal(x.shape)
+
+
+# --------------------------------------------------------------------------------------------
+# a8-a10  one synchronisation trial
+# --------------------------------------------------------------------------------------------
+def delay_bank(prm: ModemParams):
+    """del_mat_exp[(CP+1) x M0*nsb] = exp(j*2pi*d*bin/N), tiled M0 times.  SynchAndChanEst.py:74-75."""
+    sb = bins_used(prm.num_synch_bins, prm.nfft)
+    e = np.exp((1j * (TWO_PI / prm.nfft)) * np.outer(np.arange(prm.cp_len + 1), sb))
+    return np.tile(e, (1, prm.m0))
+
+
+def sync_window(in0, start, prm: ModemParams):
+    """Gather the M0 FFT windows that start at ``start`` and pick the synch bins.
+
+    SynchAndChanEst.py:145-154.  Returns the un-normalised M0*nsb vector.
+    """
+    N, L = prm.nfft, prm.sym_len
+    sb = bins_used(prm.num_synch_bins, N)
+    out = np.zeros(prm.mm, dtype=complex)
+    for ll in range(prm.m0):
+        a = L * ll + start
+        spec = np.fft.fft(np.asarray(in0[a:a + N], dtype=complex), N)
+        out[ll * prm.num_synch_bins:(ll + 1) * prm.num_synch_bins] = spec[sb]
+    return out
+
+
+def sync_trial(in0, start, prm: ModemParams, zc=None, bank=None, literal=False):
+    """One trial of the sliding search at FFT-window start sample ``start``.
+
+    Returns (dmax_ind, dmax_val, synchdat) where synchdat is the unit-power synch-bin vector.
+    SynchAndChanEst.py:156-164 / synch_and_chan_est.py:158-168.
+    """
+    zc = zc_for(prm) if zc is None else zc
+    bank = delay_bank(prm) if bank is None else bank
+    sd0 = sync_window(in0, start, prm)
+    if literal:
+        p_est = np.sqrt(len(sd0) / sum(np.multiply(sd0, np.conj(sd0))))
+        sd = p_est * sd0
+        del_mat = np.matmul(np.matmul(bank, np.diag(sd)), np.conj(zc))
+    else:
+        p_est = np.sqrt(len(sd0) / np.sum(sd0 * np.conj(sd0)))
+        sd = p_est * sd0
+        del_mat = bank @ (sd * np.conj(zc))
+    mag = np.abs(del_mat)
+    return int(np.argmax(mag)), float(np.max(mag)), sd
+
+
+# --------------------------------------------------------------------------------------------
+# a12/a13  LS channel estimate on the preamble
+# --------------------------------------------------------------------------------------------
+def chan_est(sd, dmax_ind, prm: ModemParams, zc=None, bank=None, literal=False):
+    """De-rotate by the detected delay, divide out the ZC, average over the M0 repeats.
+
+    Returns (chan_est[nsb], chan_est1[N], data_recov[MM]).  SynchAndChanEst.py:177-188.
+    """
+    zc = zc_for(prm) if zc is None else zc
+    bank = delay_bank(prm) if bank is None else bank
+    del_vec = bank[dmax_ind]
+    if literal:
+        data_recov = np.matmul(np.diag(del_vec), sd)
+        tmp = np.divide(np.matmul(np.diag(data_recov), np.conj(zc)), (1.0 / prm.reg_chanest) + np.ones(len(zc)))
+    else:
+        data_recov = del_vec * sd
+        tmp = data_recov * np.conj(zc) / (1.0 / prm.reg_chanest + 1.0)
+    ce = tmp.reshape(prm.m0, prm.num_synch_bins).sum(axis=0) / float(prm.m0)
+    ce1 = np.zeros(prm.nfft, dtype=complex)
+    ce1[bins_used(prm.num_synch_bins, prm.nfft)] = ce
+    return ce, ce1, data_recov
+
+
+def chan_est_aux(ce, ce1, data_recov, prm: ModemParams):
+    """Time-domain channel and equalised synch symbol.  SynchAndChanEst.py:202,:212-218.
+
+    Returns (chan_est_tim[N], est_synch_freq[MM]).
+    """
+    tim = np.fft.ifft(ce1, prm.nfft)
+    g = np.conj(ce) / (1.0 / prm.reg_eq_synch + ce * np.conj(ce))
+    return tim, np.tile(g, prm.m0) * data_recov
+
+
+# --------------------------------------------------------------------------------------------
+# a14-a16  one data symbol
+# --------------------------------------------------------------------------------------------
+def demod_symbol(in0, ptr, delay, h_full, prm: ModemParams, literal=False):
+    """FFT (CP skipped by the start pointer) -> data bins -> unit power -> de-rotate -> one-tap MMSE.
+
+    SynchAndChanEst.py:226-248 / synch_and_chan_est.py:230-250.  A window that runs past the end
+    of ``in0`` is zero-padded by np.fft.fft exactly like the reference.
+    """
+    N = prm.nfft
+    db = bins_used(prm.num_data_bins, N)
+    spec = np.fft.fft(np.asarray(in0[ptr:ptr + N], dtype=complex), N)
+    fd = spec[db]
+    p0 = np.sqrt(len(fd) / np.dot(fd, np.conj(fd)))
+    fd = fd * p0
+    hd = h_full[db]
+    inv_reg = 0.0 if np.isinf(prm.reg_eq) else 1.0 / prm.reg_eq
+    if literal:
+        arg = [((1j * (TWO_PI / N)) * delay) * kk for kk in db]
+        z = np.matmul(np.diag(fd), np.exp(arg))
+        mag = np.matmul(np.diag(hd), np.conj(hd))
+        g = np.divide(np.conj(hd), [inv_reg + v for v in mag])
+        return np.matmul(np.diag(g), z)
+    z = fd * np.exp(((1j * (TWO_PI / N)) * delay) * db)
+    g = np.conj(hd) / (inv_reg + hd * np.conj(hd))
+    return g * z
+
+
+# --------------------------------------------------------------------------------------------
+# framed receiver: one trial per frame at the nominal position (throughput mode)
+# --------------------------------------------------------------------------------------------
+def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, literal=False):
+    """Loop-A body once per frame + loop-B body for all D data symbols of that frame.
+
+    Frame f's synch FFT window opens at  first + f*frame_stride + CP - sync_advance ; data symbol n
+    opens at that position + M0*L + n*L.  This is the reference's per-lock arithmetic
+    (SynchAndChanEst.py:143-219 then :221-248) applied with one candidate per frame, which is how
+    a receiver with known framing runs it.  Returns dict(delay, peak, locked, h[N], eq[D,ndb]) per
+    frame stacked on axis 0.
+    """
+    fs = prm.frame_len if frame_stride is None else frame_stride
+    zc, bank = zc_for(prm), delay_bank(prm)
+    L = prm.sym_len
+    delay = np.zeros(n_frames, dtype=np.int32)
+    peak = np.zeros(n_frames)
+    locked = np.zeros(n_frames, dtype=np.uint8)
+    h = np.zeros((n_frames, prm.nfft), dtype=complex)
+    eq = np.zeros((n_frames, prm.d, prm.num_data_bins), dtype=complex)
+    for f in range(n_frames):
+        pos = first + f * fs + prm.cp_len - prm.sync_advance
+        d_i, d_v, sd = sync_trial(rx, pos, prm, zc, bank, literal)
+        delay[f], peak[f] = d_i, d_v
+        locked[f] = 1 if d_v > prm.gate * prm.mm else 0
+        _, h[f], _ = chan_est(sd, d_i, prm, zc, bank, literal)
+        for n in range(prm.d):
+            eq[f, n] = demod_symbol(rx, pos + prm.m0 * L + n * L, d_i, h[f], prm, literal)
+    return dict(delay=delay, peak=peak, locked=locked, h=h, eq=eq)
+
+
+# --------------------------------------------------------------------------------------------
+# a18  demapping
+# --------------------------------------------------------------------------------------------
+def bit_recovery(data_in):
+    """The legacy QPSK soft/hard demapper.  GRR/LEGACY/gr-ofdm-rx/python/BitRecovery.py:77-157.
+
+    Returns (llrp0[2n], llrp1[2n], hardbit[2n]).  sigma is estimated over the WHOLE buffer (:102).
+    """
+    x = np.asarray(data_in, dtype=complex).reshape(-1)
+    pts = np.exp((1j * (TWO_PI / 8.0)) * _QPSK_EIGHTHS)            # :45-52
+    dist = np.abs(x[:, None] - pts[None, :])                       # :86-88
+    near = np.argmin(dist, axis=1)
+    dmin = dist[np.arange(len(x)), near]
+    ez = x - pts[near]                                             # :93-98
+    sigma = 0.7071067811865476 * np.mean(np.abs(dmin))            # :102
+    dfact = 1.0 / (sigma * sigma)
+    K = 1.414213562373095                                          # :57
+    n = len(x)
+    llr0 = np.zeros(2 * n)
+    llr1 = np.zeros(2 * n)
+    same_r = -0.5 * dfact * np.abs(ez.real)
+    other_r = -0.5 * dfact * (K - np.abs(ez.real))
+    same_i = -0.5 * dfact * np.abs(ez.imag)
+    other_i = -0.5 * dfact * (K - np.abs(ez.imag))
+    re, im = x.real, x.imag
+    # quadrant tests in the reference's order, first match wins (:106-125)
+    q1 = (re >= 0) & (im >= 0)
+    q2 = ~q1 & (re <= 0) & (im >= 0)
+    q3 = ~q1 & ~q2 & (re <= 0) & (im <= 0)
+    q4 = ~q1 & ~q2 & ~q3 & (re >= 0) & (im <= 0)
+    re_pos = q1 | q4          # Re bit is 0 -> llrp0 gets the "same" metric
+    im_pos = q1 | q2
+    any_q = q1 | q2 | q3 | q4  # (NaN inputs match nothing and stay 0)
+    llr0[0::2] = np.where(any_q, np.where(re_pos, same_r, other_r), 0.0)
+    llr1[0::2] = np.where(any_q, np.where(re_pos, other_r, same_r), 0.0)
+    llr0[1::2] = np.where(any_q, np.where(im_pos, same_i, other_i), 0.0)
+    llr1[1::2] = np.where(any_q, np.where(im_pos, other_i, same_i), 0.0)
+    hard = (0.5 * (np.sign(llr1 - llr0) + 1.0)).astype(int)        # :155-156
+    return llr0, llr1, hard
+
+
+def maxlog_llr(x, bps, scale=1.0):
+    """Exact max-log LLR per bit, brute force over the whole constellation (OUR DEFINITION).
+
+    L_b = scale * ( min_{s: b=0} |x-s|^2 - min_{s: b=1} |x-s|^2 ),  L_b > 0  <=>  bit 1.
+    ``scale`` = 1/noise_variance.  Bit order is the mapper's (MSB first).  Returns [..., n*bps].
+    """
+    x = np.asarray(x, dtype=complex)
+    pts = constellation(bps)
+    d2 = np.abs(x[..., None] - pts) ** 2
+    out = np.zeros(x.shape + (bps,))
+    idx = np.arange(1 << bps)
+    for b in range(bps):
+        one = ((idx >> (bps - 1 - b)) & 1).astype(bool)
+        out[..., b] = scale * (d2[..., ~one].min(-1) - d2[..., one].min(-1))
+    return out.reshape(x.shape[:-1] + (x.shape[-1] * bps,))
+
+
+def hard_bits(x, bps):
+    """Bits of the nearest constellation point (== sign of the max-log LLR).  [..., n*bps] uint8."""
+    x = np.asarray(x, dtype=complex)
+    pts = constellation(bps)
+    near = np.argmin(np.abs(x[..., None] - pts), axis=-1)
+    sh = np.arange(bps - 1, -1, -1)
+    b = ((near[..., None] >> sh) & 1).astype(np.uint8)
+    return b.reshape(x.shape[:-1] + (x.shape[-1] * bps,))
+
+
+# --------------------------------------------------------------------------------------------
+# counters (BER / EVM) -- the only quantity that is reduced across GPUs
+# --------------------------------------------------------------------------------------------
+def counters(bits_rx, bits_tx, eq, ref_syms):
+    """[bit_errors, bits, sum|e|^2, sum|ref|^2] as float64."""
+    bits_rx = np.asarray(bits_rx).reshape(-1)
+    bits_tx = np.asarray(bits_tx).reshape(-1)
+    e = np.asarray(eq).reshape(-1) - np.asarray(ref_syms).reshape(-1)
+    return np.array([float(np.count_nonzero(bits_rx != bits_tx)), float(bits_tx.size),
+                     float(np.sum(np.abs(e) ** 2)), float(np.sum(np.abs(ref_syms) ** 2))])
