@@ -1,0 +1,155 @@
+/*
+ * ofdm_b200.h -- C ABI of libofdm_b200.so, the B200 (sm_100a) implementation of the OFDM modem
+ * hot path of tayloreisman16/LTE-GNU-Radio-Code.
+ *
+ * The reference has no native interface for this path: its blocks are pure-Python
+ * gr.sync_block subclasses whose work() bodies call NumPy (the pybind11 modules are empty stubs,
+ * GNU-Radio-Repositories/gr-RXOFDM/python/bindings/python_bindings.cc:37-53).  The entry points
+ * below are therefore the functions a maintainer would bind from those work() bodies with ctypes
+ * (see INTEGRATION.md); each one names the reference statements it replaces.  Paths are relative
+ * to GNU-Radio-Repositories/ (GRR/).
+ *
+ * Conventions
+ *   - plain C types only; complex samples are interleaved float pairs (numpy complex64 / float2);
+ *   - every function returns 0 on success or a negative OFDM_E* code and never throws;
+ *     ofdm_last_error() returns a thread-local description of the last failure;
+ *   - pointers named d_* are DEVICE pointers owned by the caller, h_* are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all d_* entry
+ *     points are asynchronous on it and never synchronise or allocate;
+ *   - the library owns only the plan (twiddles, Zadoff-Chu, bin tables, optional staging buffers
+ *     used by the h_* convenience entry points).
+ *   - bits are packed MSB-first (numpy.packbits order); each OFDM data symbol owns
+ *     ofdm_plan_hard_stride() bytes (= ceil(num_data_bins*bps/8)).
+ */
+#ifndef OFDM_B200_H
+#define OFDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDM_B200_ABI_VERSION 1
+
+enum {
+    OFDM_OK = 0,
+    OFDM_EINVAL = -1,      /* bad argument / unsupported numerology */
+    OFDM_ECUDA = -2,       /* a CUDA runtime call failed; see ofdm_last_error() */
+    OFDM_ENOMEM = -3
+};
+
+enum { OFDM_EQ_MMSE = 0, OFDM_EQ_ZF = 1 };
+
+/* Numerology + constants of one modem instance.  The first six fields are the reference block's
+ * constructor arguments (GRR/gr-utsa_ofdm/python/SynchAndChanEst.py:17-19,
+ * GRR/gr-RXOFDM/python/synch_and_chan_est.py:17-18). */
+typedef struct ofdm_params {
+    int32_t nfft;            /* power of two, 64..4096 */
+    int32_t cp_len;          /* 0 <= cp_len < nfft */
+    int32_t num_synch_bins;  /* even, <= nfft (== nfft reproduces the +-N/2 alias of ofdm_chain.py:83) */
+    int32_t num_data_bins;   /* even, < nfft */
+    int32_t m0;              /* synch symbols per frame, synch_dat[0] */
+    int32_t d;               /* data symbols per frame,  synch_dat[1] */
+    int32_t bps;             /* bits per data bin: 1 BPSK, 2 QPSK, 4 16-QAM, 6 64-QAM */
+    int32_t zc_root;         /* 23 (gr-utsa_ofdm, TX simulator) or 37 (gr-RXOFDM) */
+    int32_t zc_parity_of;    /* value whose parity picks the ZC formula: M0*nsb (utsa) or nsb (rxofdm); 0 = M0*nsb */
+    int32_t equalizer;       /* OFDM_EQ_MMSE | OFDM_EQ_ZF */
+    int32_t sync_advance;    /* framed mode: samples before the CP end at which the synch window opens */
+    float gate;              /* lock when peak > gate * M0*nsb  (SynchAndChanEst.py:166; 0.4 in gr-RXOFDM :170) */
+    float inv_reg_chanest;   /* 1/x in H = r*conj(zc)/(1 + 1/x)          (SynchAndChanEst.py:180-181) */
+    float inv_reg_eq;        /* 1/x in g = conj(H)/(|H|^2 + 1/x), data   (SynchAndChanEst.py:244-246) */
+    float inv_reg_eq_synch;  /* same for the synch-symbol equaliser       (SynchAndChanEst.py:213-218) */
+    float llr_scale;         /* 1/noise variance multiplying the max-log LLRs */
+    int32_t reserved[8];     /* must be zero */
+} ofdm_params;
+
+typedef struct ofdm_plan ofdm_plan;
+
+int ofdm_abi_version(void);
+const char *ofdm_last_error(void);
+
+/* Builds the device tables on the CURRENT CUDA device.  Replaces the constructor-time precompute
+ * of the blocks: bin maps, Zadoff-Chu, delay bank (SynchAndChanEst.py:36-99). */
+int ofdm_plan_create(const ofdm_params *params, ofdm_plan **plan_out);
+int ofdm_plan_destroy(ofdm_plan *plan);
+int ofdm_plan_hard_stride(const ofdm_plan *plan);          /* bytes of packed bits per data symbol */
+int ofdm_plan_frame_len(const ofdm_plan *plan);            /* (M0+D)*(nfft+cp_len) samples */
+
+/* TX: bits -> QAM + Zadoff-Chu/resource-element insertion -> IFFT -> CP add -> power normalise.
+ * Replaces MultiAntennaSystem.multi_ant_binary_map + multi_ant_symb_gen
+ * (GRR/LEGACY/gr-ofdm-rx/python/txrx_mod/MultiAntennaSystem.py:113-219).
+ * d_bits: n_frames*D*hard_stride bytes.  d_time: n_frames*frame_len complex64. */
+int ofdm_tx_modulate(ofdm_plan *plan, const uint8_t *d_bits, float *d_time, int64_t n_frames, void *stream);
+
+/* RX sliding search: trial t opens its FFT window at sample first_start + t*stride.  For each
+ * trial: M0 FFTs, synch-bin pick, unit-power normalise, (CP+1)-delay correlation with the ZC,
+ * max / argmax.  Replaces the body of loop A up to the gate test (SynchAndChanEst.py:145-164,
+ * synch_and_chan_est.py:148-168).  d_peak[t] = max|c|, d_delay[t] = argmax. */
+int ofdm_rx_sync_search(ofdm_plan *plan, const float *d_time, int64_t n_samples, int64_t first_start,
+                        int64_t stride, int64_t n_trials, float *d_peak, int32_t *d_delay, void *stream);
+
+/* RX LS channel estimate for n_locks accepted locks (window start d_pos[i], delay d_delay[i]).
+ * Replaces SynchAndChanEst.py:177-188 (d_H, nfft per lock) and, when the pointers are non-NULL,
+ * :202-218 (d_htime = ifft(H), nfft per lock; d_synch_eq = equalised synch symbols, M0*nsb per lock). */
+int ofdm_rx_chanest(ofdm_plan *plan, const float *d_time, int64_t n_samples, const int64_t *d_pos,
+                    const int32_t *d_delay, int64_t n_locks, float *d_H, float *d_htime,
+                    float *d_synch_eq, void *stream);
+
+/* RX data symbols: FFT with the CP skipped by the start pointer, data-bin pick, unit-power
+ * normalise, delay de-rotation, one-tap MMSE/ZF, optional max-log LLR + packed hard bits.
+ * Symbol i opens at d_start[i], uses delay d_delay[i] and channel row d_hrow[i] of d_H.
+ * Windows past n_samples are zero-padded (np.fft.fft semantics).  Replaces loop B
+ * (SynchAndChanEst.py:225-248, synch_and_chan_est.py:230-250).
+ * d_eq: n_sym*ndb complex64.  d_llr (nullable): n_sym*ndb*bps float.  d_hard (nullable):
+ * n_sym*hard_stride bytes. */
+int ofdm_rx_demod(ofdm_plan *plan, const float *d_time, int64_t n_samples, const int64_t *d_start,
+                  const int32_t *d_delay, const int32_t *d_hrow, const float *d_H, int64_t n_sym,
+                  float *d_eq, float *d_llr, uint8_t *d_hard, void *stream);
+
+/* RX framed mode (throughput path): loop A body once per frame at the nominal position plus
+ * loop B for the frame's D data symbols, fused in one kernel -- the channel estimate never
+ * leaves the SM.  Frame f's synch window opens at first + f*frame_stride + cp_len - sync_advance.
+ * Outputs per frame: d_delay, d_peak, d_locked (peak > gate*M0*nsb); d_H nullable (nfft per frame).
+ * Per data symbol (n_frames*D rows): d_eq, d_llr (nullable), d_hard (nullable). */
+int ofdm_rx_frames(ofdm_plan *plan, const float *d_time, int64_t n_samples, int64_t first,
+                   int64_t frame_stride, int64_t n_frames, int32_t *d_delay, float *d_peak,
+                   uint8_t *d_locked, float *d_H, float *d_eq, float *d_llr, uint8_t *d_hard,
+                   void *stream);
+
+/* Legacy QPSK soft/hard demapper with a buffer-wide noise estimate.  Replaces BitRecovery.work
+ * (GRR/LEGACY/gr-ofdm-rx/python/BitRecovery.py:77-157).  Two launches: the first reduces
+ * sum(dmin) into d_ws[0] (double, zeroed by the call), the second writes d_llr0/d_llr1 (2n float
+ * each) and d_hard (2n bytes, one 0/1 per byte like the reference's int array). */
+int ofdm_bit_recovery(ofdm_plan *plan, const float *d_in, int64_t n, float *d_llr0, float *d_llr1,
+                      uint8_t *d_hard, double *d_ws, void *stream);
+
+/* BER/EVM counters, ACCUMULATED into d_cnt[8] (double): [0] bit errors, [1] bits compared,
+ * [2] sum|eq-ref|^2, [3] sum|ref|^2, [4] frames locked, [5] frames; [6],[7] spare.
+ * ref symbols are rebuilt from d_bits_tx.  d_locked nullable.  This vector is the only thing
+ * ever reduced across GPUs (NCCL all-reduce on the host side). */
+int ofdm_counters(ofdm_plan *plan, const uint8_t *d_bits_rx, const uint8_t *d_bits_tx, const float *d_eq,
+                  const uint8_t *d_locked, int64_t n_frames, double *d_cnt, void *stream);
+
+/* Test-bench channel (NOT on the modem path): per-frame n_taps-tap FIR + AWGN, counter-based
+ * Philox noise.  d_taps: n_frames*n_taps complex64 (or one set when taps_per_frame == 0).
+ * Replaces MultiAntennaSystem.rx_signal_gen / additive_noise (:221-260) for synthetic inputs.
+ * Frames are filtered independently (no inter-frame tail). */
+int ofdm_channel_awgn(ofdm_plan *plan, const float *d_tx, float *d_rx, int64_t n_frames, const float *d_taps,
+                      int32_t n_taps, int32_t taps_per_frame, float noise_sigma, uint64_t seed, void *stream);
+
+/* Host-buffer convenience entry points (what a GNU Radio work() sees): stage through plan-owned
+ * device buffers, copies inside the call, chunked and double-buffered on internal streams.
+ * They synchronise before returning.  Pinned host memory makes the copies asynchronous. */
+int ofdm_rx_frames_host(ofdm_plan *plan, const float *h_time, int64_t n_samples, int64_t first,
+                        int64_t frame_stride, int64_t n_frames, int32_t *h_delay, float *h_peak,
+                        uint8_t *h_locked, float *h_eq, float *h_llr, uint8_t *h_hard);
+int ofdm_tx_modulate_host(ofdm_plan *plan, const uint8_t *h_bits, float *h_time, int64_t n_frames);
+
+/* Introspection for benchmarks: kernels launched by this library since load. */
+uint64_t ofdm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFDM_B200_H */

@@ -1,0 +1,584 @@
+// api.cu -- the C ABI of libofdm_b200.so (include/ofdm_b200.h), the plan, and the small
+// non-FFT kernels (legacy demapper, BER/EVM counters, test-bench channel).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/ofdm_b200.h"
+#include "launch.cuh"
+
+namespace ofdm {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, const char *a = "", long long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return OFDM_ECUDA;
+}
+#define CU(call, where)                                   \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// misc kernels
+// ------------------------------------------------------------------------------------------------
+// Legacy QPSK demapper, phase 1: sum over the buffer of the distance to the nearest point.
+// BitRecovery.py:86-88,:102
+__global__ void bitrec_sum_kernel(const float2 *__restrict__ x, long long n, double *__restrict__ ws) {
+    const float a = 0.70710678118654752440f;
+    float acc = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 z = __ldg(x + i);
+        const float ex = z.x - (z.x >= 0.f ? a : -a), ey = z.y - (z.y >= 0.f ? a : -a);
+        acc += sqrtf(ex * ex + ey * ey);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ float part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += (double)part[w];
+        atomicAdd(ws, s);
+    }
+}
+
+// phase 2: llrp0 / llrp1 / hard bit per axis.  BitRecovery.py:102-125,:155-156
+__global__ void bitrec_llr_kernel(const float2 *__restrict__ x, long long n, const double *__restrict__ ws,
+                                  float *__restrict__ llr0, float *__restrict__ llr1, uint8_t *__restrict__ hard) {
+    const float a = 0.70710678118654752440f, K = 1.414213562373095f;
+    const double sigma = 0.7071067811865476 * (ws[0] / (double)n);
+    const float hd = (float)(-0.5 / (sigma * sigma));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 z = __ldg(x + i);
+        const float er = fabsf(z.x - (z.x >= 0.f ? a : -a)), ei = fabsf(z.y - (z.y >= 0.f ? a : -a));
+        // quadrant tests in the reference's first-match order reduce to these two predicates
+        const bool re_pos = (z.x > 0.f) || (z.x == 0.f && z.y >= 0.f);
+        const bool im_pos = (z.y >= 0.f);
+        const float sr = hd * er, orr = hd * (K - er), si = hd * ei, oi = hd * (K - ei);
+        const float l0r = re_pos ? sr : orr, l1r = re_pos ? orr : sr;
+        const float l0i = im_pos ? si : oi, l1i = im_pos ? oi : si;
+        reinterpret_cast<float2 *>(llr0)[i] = make_float2(l0r, l0i);
+        reinterpret_cast<float2 *>(llr1)[i] = make_float2(l1r, l1i);
+        uchar2 h;
+        h.x = (l1r - l0r) > 0.f;
+        h.y = (l1i - l0i) > 0.f;
+        reinterpret_cast<uchar2 *>(hard)[i] = h;
+    }
+}
+
+template <int BPS>
+__device__ __forceinline__ void cnt_symbol(const DevParams &P, const uint8_t *tx, const float2 *eq, int ndb, float &e2,
+                                           float &r2, int lane0, int step) {
+    for (int b = lane0; b < ndb; b += step) {
+        const float2 r = map_bits<BPS>(read_bits<BPS>(tx, b * BPS, P.hard_stride));
+        const float2 z = __ldg(eq + b);
+        e2 += (z.x - r.x) * (z.x - r.x) + (z.y - r.y) * (z.y - r.y);
+        r2 += r.x * r.x + r.y * r.y;
+    }
+}
+
+// BER / EVM counters: one warp per data symbol.
+__global__ void counters_kernel(const DevParams P, const uint8_t *__restrict__ rx, const uint8_t *__restrict__ tx,
+                                const float2 *__restrict__ eq, const uint8_t *__restrict__ locked, long long n_frames,
+                                double *__restrict__ cnt) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const long long n_sym = n_frames * P.d;
+    float e2 = 0.f, r2 = 0.f;
+    unsigned long long errs = 0;
+    for (long long s = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); s < n_sym; s += (long long)gridDim.x * wpb) {
+        const uint8_t *t = tx + s * P.hard_stride;
+        if (rx != nullptr) {
+            const uint8_t *r = rx + s * P.hard_stride;
+            for (int b = lane; b < P.hard_stride; b += 32) errs += __popc((unsigned)(__ldg(r + b) ^ __ldg(t + b)));
+        }
+        if (eq != nullptr) {
+            const float2 *q = eq + s * P.ndb;
+            switch (P.bps) {
+                case 1: cnt_symbol<1>(P, t, q, P.ndb, e2, r2, lane, 32); break;
+                case 2: cnt_symbol<2>(P, t, q, P.ndb, e2, r2, lane, 32); break;
+                case 4: cnt_symbol<4>(P, t, q, P.ndb, e2, r2, lane, 32); break;
+                default: cnt_symbol<6>(P, t, q, P.ndb, e2, r2, lane, 32); break;
+            }
+        }
+    }
+    double de = (double)e2, dr = (double)r2, dq = (double)errs;
+    for (int o = 16; o > 0; o >>= 1) {
+        de += __shfl_xor_sync(0xffffffffu, de, o);
+        dr += __shfl_xor_sync(0xffffffffu, dr, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    __shared__ double part[3][32];
+    if (lane == 0) {
+        part[0][threadIdx.x >> 5] = dq;
+        part[1][threadIdx.x >> 5] = de;
+        part[2][threadIdx.x >> 5] = dr;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < wpb; ++w) {
+            a += part[0][w];
+            b += part[1][w];
+            c += part[2][w];
+        }
+        if (rx != nullptr) atomicAdd(cnt + 0, a);
+        if (eq != nullptr) {
+            atomicAdd(cnt + 2, b);
+            atomicAdd(cnt + 3, c);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // frames / locked frames / bits compared: counted once by the first warp
+        double lk = 0;
+        if (locked != nullptr)
+            for (long long f = lane; f < n_frames; f += 32) lk += locked[f] ? 1.0 : 0.0;
+        for (int o = 16; o > 0; o >>= 1) lk += __shfl_xor_sync(0xffffffffu, lk, o);
+        if (lane == 0) {
+            if (rx != nullptr) atomicAdd(cnt + 1, (double)n_sym * (double)(P.ndb * P.bps));
+            atomicAdd(cnt + 4, lk);
+            atomicAdd(cnt + 5, (double)n_frames);
+        }
+    }
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11), one call = 4 x 32 random bits.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// test-bench channel: y[f,n] = sum_t h[f,t] x[f,n-t] + sigma*(g1 + j g2), frames independent
+__global__ void channel_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, long long n_frames, int frame_len,
+                               const float2 *__restrict__ taps, int n_taps, int taps_per_frame, float sigma,
+                               unsigned long long seed) {
+    const long long total = n_frames * frame_len;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / frame_len;
+        const int n = (int)(i - f * frame_len);
+        const float2 *h = taps + (taps_per_frame ? f * n_taps : 0);
+        float2 acc = make_float2(0.f, 0.f);
+        for (int t = 0; t < n_taps && t <= n; ++t) acc = cadd(acc, cmul(__ldg(h + t), __ldg(x + i - t)));
+        if (sigma > 0.f) {
+            const uint4 r = philox4x32_10(make_uint4((unsigned)i, (unsigned)(i >> 32), 0u, 0u),
+                                          make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+            const float u1 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f;
+            const float u2 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
+            const float rad = sigma * sqrtf(-2.f * __logf(u1));
+            float sn, cs;
+            __sincosf(6.283185307179586f * u2, &sn, &cs);
+            acc.x += rad * cs;
+            acc.y += rad * sn;
+        }
+        y[i] = acc;
+    }
+}
+
+}  // namespace ofdm
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+using namespace ofdm;
+
+struct ofdm_plan {
+    ofdm_params prm;
+    DevParams dev;
+    const KernelSet *ks;
+    int device, sms, log2n;
+    void *d_tables;                // one allocation holding every table
+    // staging for the host-buffer entry points (grown on demand, freed with the plan)
+    static const int NSLOT = 2;
+    cudaStream_t st[NSLOT];
+    cudaEvent_t ev[NSLOT];
+    bool streams_made;
+    void *stage[NSLOT];
+    size_t stage_bytes[NSLOT];
+};
+
+static const KernelSet *kset_for(int log2n) {
+    switch (log2n) {
+        case 6: return &kset_6;
+        case 7: return &kset_7;
+        case 8: return &kset_8;
+        case 9: return &kset_9;
+        case 10: return &kset_10;
+        case 11: return &kset_11;
+        case 12: return &kset_12;
+    }
+    return nullptr;
+}
+
+extern "C" {
+
+int ofdm_abi_version(void) { return OFDM_B200_ABI_VERSION; }
+const char *ofdm_last_error(void) { return g_err; }
+uint64_t ofdm_launch_count(void) { return g_launches.load(); }
+
+int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
+    if (!p || !out) return fail(OFDM_EINVAL, "null argument%s");
+    *out = nullptr;
+    int log2n = 0;
+    while ((1 << log2n) < p->nfft) ++log2n;
+    if ((1 << log2n) != p->nfft || log2n < 6 || log2n > 12) return fail(OFDM_EINVAL, "nfft must be a power of two in 64..4096%s");
+    const int N = p->nfft;
+    if (p->cp_len < 0 || p->cp_len >= N) return fail(OFDM_EINVAL, "cp_len out of range%s");
+    if (p->num_synch_bins < 2 || p->num_synch_bins > N || (p->num_synch_bins & 1))
+        return fail(OFDM_EINVAL, "num_synch_bins must be even and <= nfft%s");
+    if (p->num_data_bins < 2 || p->num_data_bins >= N || (p->num_data_bins & 1))
+        return fail(OFDM_EINVAL, "num_data_bins must be even and < nfft%s");
+    if (p->m0 < 1 || p->m0 > 16 || p->d < 0) return fail(OFDM_EINVAL, "synch_dat out of range%s");
+    if (p->bps != 1 && p->bps != 2 && p->bps != 4 && p->bps != 6) return fail(OFDM_EINVAL, "bps must be 1, 2, 4 or 6%s");
+    if (p->sync_advance < 0 || p->sync_advance > p->cp_len) return fail(OFDM_EINVAL, "sync_advance must be in 0..cp_len%s");
+    for (int i = 0; i < 8; ++i)
+        if (p->reserved[i] != 0) return fail(OFDM_EINVAL, "reserved fields must be zero%s");
+
+    ofdm_plan *pl = new (std::nothrow) ofdm_plan();
+    if (!pl) return fail(OFDM_ENOMEM, "out of host memory%s");
+    memset(pl, 0, sizeof(*pl));
+    pl->prm = *p;
+    pl->log2n = log2n;
+    pl->ks = kset_for(log2n);
+    cudaError_t e = cudaGetDevice(&pl->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->sms, cudaDevAttrMultiProcessorCount, pl->device);
+    if (e != cudaSuccess) {
+        delete pl;
+        return cuda_fail(e, "ofdm_plan_create(device query)");
+    }
+
+    const int nsb = p->num_synch_bins, m0 = p->m0, mm = m0 * nsb;
+    // host tables in double precision, rounded once to fp32
+    std::vector<float2> tw(N), zc_bin((size_t)m0 * N, make_float2(0.f, 0.f)), zc_dup((size_t)m0 * 2), zc_tx(N, make_float2(0.f, 0.f));
+    std::vector<float> w_bin(N, 0.f);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 0; k < N; ++k) {
+        const double a = -two_pi * (double)k / (double)N;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    // Zadoff-Chu: SynchAndChanEst.py:54-59 / synch_and_chan_est.py:54-64 / SynchSignal.py:21-30
+    std::vector<double> zr(mm), zi(mm);
+    const int par = p->zc_parity_of > 0 ? p->zc_parity_of : mm;
+    for (int k = 0; k < mm; ++k) {
+        const double kk = (double)k;
+        const double q = (par % 2 == 0) ? kk * kk / 2.0 : kk * (kk + 1.0) / 2.0;
+        const double a = -(two_pi / (double)mm) * (double)p->zc_root * q;
+        zr[k] = cos(a);
+        zi[k] = sin(a);
+    }
+    // TX side keys the parity on MM (SynchSignal.py:24); only differs from `par` for gr-RXOFDM with even M0, odd nsb
+    std::vector<double> tzr(nsb), tzi(nsb);
+    for (int k = 0; k < nsb; ++k) {
+        const double kk = (double)k;
+        const double q = (mm % 2 == 0) ? kk * kk / 2.0 : kk * (kk + 1.0) / 2.0;
+        const double a = -(two_pi / (double)mm) * (double)p->zc_root * q;
+        tzr[k] = cos(a);
+        tzi[k] = sin(a);
+    }
+    int dup_bin = -1;
+    const int h = nsb / 2;
+    for (int idx = 0; idx < nsb; ++idx) {
+        const int sb = idx < h ? idx - h : idx - h + 1;              // signed bin
+        const int k = ((sb % N) + N) % N;
+        if (w_bin[k] > 0.f) dup_bin = k;
+        w_bin[k] += 1.f;
+        for (int s = 0; s < m0; ++s) {
+            zc_bin[(size_t)s * N + k].x += (float)zr[s * nsb + idx];
+            zc_bin[(size_t)s * N + k].y += (float)(-zi[s * nsb + idx]);
+        }
+        zc_tx[k] = make_float2((float)tzr[idx], (float)tzi[idx]);   // fancy assignment: last index wins
+    }
+    for (int s = 0; s < m0; ++s) {
+        zc_dup[2 * s + 0] = make_float2((float)zr[s * nsb + 0], (float)(-zi[s * nsb + 0]));
+        zc_dup[2 * s + 1] = make_float2((float)zr[s * nsb + nsb - 1], (float)(-zi[s * nsb + nsb - 1]));
+    }
+
+    const size_t b_tw = sizeof(float2) * N, b_zb = sizeof(float2) * m0 * N, b_w = sizeof(float) * N,
+                 b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * N;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt);
+    e = cudaMalloc(&pl->d_tables, total);
+    if (e != cudaSuccess) {
+        delete pl;
+        return cuda_fail(e, "ofdm_plan_create(cudaMalloc)");
+    }
+    char *base = (char *)pl->d_tables;
+    size_t o = 0;
+    auto put = [&](const void *src, size_t n) -> void * {
+        void *dst = base + o;
+        if (e == cudaSuccess) e = cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+        o += al(n);
+        return dst;
+    };
+    DevParams &D = pl->dev;
+    D.tw = (const float2 *)put(tw.data(), b_tw);
+    D.zc_bin = (const float2 *)put(zc_bin.data(), b_zb);
+    D.w_bin = (const float *)put(w_bin.data(), b_w);
+    D.zc_dup = (const float2 *)put(zc_dup.data(), b_zd);
+    D.zc_tx = (const float2 *)put(zc_tx.data(), b_zt);
+    if (e != cudaSuccess) {
+        cudaFree(pl->d_tables);
+        delete pl;
+        return cuda_fail(e, "ofdm_plan_create(cudaMemcpy)");
+    }
+    D.nfft = N;
+    D.cp = p->cp_len;
+    D.nsb = nsb;
+    D.ndb = p->num_data_bins;
+    D.m0 = m0;
+    D.d = p->d;
+    D.bps = p->bps;
+    D.mm = mm;
+    D.sync_advance = p->sync_advance;
+    D.hard_stride = (p->num_data_bins * p->bps + 7) / 8;
+    D.dup_bin = dup_bin;
+    D.equalizer = p->equalizer;
+    D.gate_thresh = p->gate * (float)mm;
+    D.chanest_scale = (float)(1.0 / ((1.0 + (double)p->inv_reg_chanest) * (double)m0));
+    D.inv_reg_eq = p->equalizer == OFDM_EQ_ZF ? 0.f : p->inv_reg_eq;
+    D.inv_reg_eq_synch = p->inv_reg_eq_synch;
+    D.llr_scale = p->llr_scale;
+    *out = pl;
+    return OFDM_OK;
+}
+
+int ofdm_plan_destroy(ofdm_plan *pl) {
+    if (!pl) return OFDM_OK;
+    cudaFree(pl->d_tables);
+    for (int i = 0; i < ofdm_plan::NSLOT; ++i) {
+        if (pl->stage[i]) cudaFree(pl->stage[i]);
+        if (pl->streams_made) {
+            cudaStreamDestroy(pl->st[i]);
+            cudaEventDestroy(pl->ev[i]);
+        }
+    }
+    delete pl;
+    return OFDM_OK;
+}
+
+int ofdm_plan_hard_stride(const ofdm_plan *pl) { return pl ? pl->dev.hard_stride : OFDM_EINVAL; }
+int ofdm_plan_frame_len(const ofdm_plan *pl) {
+    return pl ? (pl->prm.m0 + pl->prm.d) * (pl->prm.nfft + pl->prm.cp_len) : OFDM_EINVAL;
+}
+
+int ofdm_tx_modulate(ofdm_plan *pl, const uint8_t *d_bits, float *d_time, int64_t n_frames, void *stream) {
+    if (!pl || !d_time || (!d_bits && pl->prm.d > 0) || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_tx_modulate: bad argument%s");
+    CU(pl->ks->tx(pl->dev, d_bits, (float2 *)d_time, n_frames * (pl->prm.m0 + pl->prm.d), (cudaStream_t)stream, pl->sms),
+       "ofdm_tx_modulate");
+    return OFDM_OK;
+}
+
+int ofdm_rx_sync_search(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first_start, int64_t stride,
+                        int64_t n_trials, float *d_peak, int32_t *d_delay, void *stream) {
+    if (!pl || !d_time || !d_peak || !d_delay || n_trials < 0 || stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_sync_search: bad argument%s");
+    CU(pl->ks->sync_search(pl->dev, (const float2 *)d_time, n_samples, first_start, stride, n_trials, d_peak, d_delay,
+                           (cudaStream_t)stream, pl->sms),
+       "ofdm_rx_sync_search");
+    return OFDM_OK;
+}
+
+int ofdm_rx_chanest(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_pos, const int32_t *d_delay,
+                    int64_t n_locks, float *d_H, float *d_htime, float *d_synch_eq, void *stream) {
+    if (!pl || !d_time || !d_pos || !d_delay || !d_H || n_locks < 0) return fail(OFDM_EINVAL, "ofdm_rx_chanest: bad argument%s");
+    CU(pl->ks->chanest(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_pos, d_delay, n_locks,
+                       (float2 *)d_H, (float2 *)d_htime, (float2 *)d_synch_eq, (cudaStream_t)stream, pl->sms),
+       "ofdm_rx_chanest");
+    return OFDM_OK;
+}
+
+int ofdm_rx_demod(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_start, const int32_t *d_delay,
+                  const int32_t *d_hrow, const float *d_H, int64_t n_sym, float *d_eq, float *d_llr, uint8_t *d_hard,
+                  void *stream) {
+    if (!pl || !d_time || !d_start || !d_delay || !d_hrow || !d_H || !d_eq || n_sym < 0)
+        return fail(OFDM_EINVAL, "ofdm_rx_demod: bad argument%s");
+    CU(pl->ks->rx_demod(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_start, d_delay, d_hrow,
+                        (const float2 *)d_H, n_sym, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms),
+       "ofdm_rx_demod");
+    return OFDM_OK;
+}
+
+int ofdm_rx_frames(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first, int64_t frame_stride,
+                   int64_t n_frames, int32_t *d_delay, float *d_peak, uint8_t *d_locked, float *d_H, float *d_eq,
+                   float *d_llr, uint8_t *d_hard, void *stream) {
+    if (!pl || !d_time || !d_delay || !d_peak || !d_locked || !d_eq || n_frames < 0)
+        return fail(OFDM_EINVAL, "ofdm_rx_frames: bad argument%s");
+    CU(pl->ks->rx_frames(pl->dev, (const float2 *)d_time, n_samples, first, frame_stride, n_frames, d_delay, d_peak,
+                         d_locked, (float2 *)d_H, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms),
+       "ofdm_rx_frames");
+    return OFDM_OK;
+}
+
+int ofdm_bit_recovery(ofdm_plan *pl, const float *d_in, int64_t n, float *d_llr0, float *d_llr1, uint8_t *d_hard,
+                      double *d_ws, void *stream) {
+    if (!pl || !d_in || !d_llr0 || !d_llr1 || !d_hard || !d_ws || n < 0) return fail(OFDM_EINVAL, "ofdm_bit_recovery: bad argument%s");
+    if (n == 0) return OFDM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_ws, 0, sizeof(double), st), "ofdm_bit_recovery(memset)");
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)pl->sms * 8;
+    if (blocks > cap) blocks = cap;
+    bitrec_sum_kernel<<<(int)blocks, 256, 0, st>>>((const float2 *)d_in, n, d_ws);
+    count_launch();
+    bitrec_llr_kernel<<<(int)blocks, 256, 0, st>>>((const float2 *)d_in, n, d_ws, d_llr0, d_llr1, d_hard);
+    count_launch();
+    CU(cudaGetLastError(), "ofdm_bit_recovery");
+    return OFDM_OK;
+}
+
+int ofdm_counters(ofdm_plan *pl, const uint8_t *d_bits_rx, const uint8_t *d_bits_tx, const float *d_eq,
+                  const uint8_t *d_locked, int64_t n_frames, double *d_cnt, void *stream) {
+    if (!pl || !d_bits_tx || !d_cnt || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_counters: bad argument%s");
+    if (n_frames == 0) return OFDM_OK;
+    long long blocks = (n_frames * pl->prm.d + 7) / 8;
+    const long long cap = (long long)pl->sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    counters_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pl->dev, d_bits_rx, d_bits_tx, (const float2 *)d_eq,
+                                                                   d_locked, n_frames, d_cnt);
+    count_launch();
+    CU(cudaGetLastError(), "ofdm_counters");
+    return OFDM_OK;
+}
+
+int ofdm_channel_awgn(ofdm_plan *pl, const float *d_tx, float *d_rx, int64_t n_frames, const float *d_taps,
+                      int32_t n_taps, int32_t taps_per_frame, float noise_sigma, uint64_t seed, void *stream) {
+    if (!pl || !d_tx || !d_rx || !d_taps || n_taps < 1 || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_channel_awgn: bad argument%s");
+    if (n_frames == 0) return OFDM_OK;
+    const int fl = ofdm_plan_frame_len(pl);
+    long long blocks = (n_frames * fl + 255) / 256;
+    const long long cap = (long long)pl->sms * 16;
+    if (blocks > cap) blocks = cap;
+    channel_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)d_tx, (float2 *)d_rx, n_frames, fl,
+                                                                  (const float2 *)d_taps, n_taps, taps_per_frame,
+                                                                  noise_sigma, seed);
+    count_launch();
+    CU(cudaGetLastError(), "ofdm_channel_awgn");
+    return OFDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points: chunked, double-buffered H2D -> kernel -> D2H on two internal streams
+// ------------------------------------------------------------------------------------------------
+static int ensure_streams(ofdm_plan *pl) {
+    if (pl->streams_made) return OFDM_OK;
+    for (int i = 0; i < ofdm_plan::NSLOT; ++i) {
+        CU(cudaStreamCreateWithFlags(&pl->st[i], cudaStreamNonBlocking), "cudaStreamCreate");
+        CU(cudaEventCreateWithFlags(&pl->ev[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    pl->streams_made = true;
+    return OFDM_OK;
+}
+static int ensure_stage(ofdm_plan *pl, int slot, size_t bytes) {
+    if (pl->stage_bytes[slot] >= bytes) return OFDM_OK;
+    if (pl->stage[slot]) cudaFree(pl->stage[slot]);
+    pl->stage[slot] = nullptr;
+    pl->stage_bytes[slot] = 0;
+    CU(cudaMalloc(&pl->stage[slot], bytes), "staging cudaMalloc");
+    pl->stage_bytes[slot] = bytes;
+    return OFDM_OK;
+}
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, int64_t first, int64_t frame_stride,
+                        int64_t n_frames, int32_t *h_delay, float *h_peak, uint8_t *h_locked, float *h_eq, float *h_llr,
+                        uint8_t *h_hard) {
+    if (!pl || !h_time || !h_eq || n_frames < 0 || frame_stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_frames_host: bad argument%s");
+    if (n_frames == 0) return OFDM_OK;
+    int rc = ensure_streams(pl);
+    if (rc) return rc;
+    const ofdm_params &p = pl->prm;
+    const int64_t L = p.nfft + p.cp_len, fl = (int64_t)(p.m0 + p.d) * L;
+    const int64_t ndb = p.num_data_bins, hs = pl->dev.hard_stride;
+    // chunk size: ~32 MiB of input per slot so copies and kernels of adjacent chunks overlap
+    int64_t per = (32ll << 20) / (frame_stride * 8);
+    if (per < 1) per = 1;
+    if (per > n_frames) per = n_frames;
+    const size_t b_in = al256((size_t)((per - 1) * frame_stride + fl + 2 * p.cp_len) * 8);
+    const size_t b_dl = al256(per * 4), b_pk = al256(per * 4), b_lk = al256(per);
+    const size_t b_eq = al256(per * p.d * ndb * 8), b_ll = al256(per * p.d * ndb * p.bps * 4), b_hd = al256(per * p.d * hs);
+    const size_t tot = b_in + b_dl + b_pk + b_lk + b_eq + b_ll + b_hd;
+    for (int s = 0; s < ofdm_plan::NSLOT; ++s) {
+        rc = ensure_stage(pl, s, tot);
+        if (rc) return rc;
+    }
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += per, slot ^= 1) {
+        const int64_t nf = (n_frames - f0 < per) ? (n_frames - f0) : per;
+        cudaStream_t st = pl->st[slot];
+        char *b = (char *)pl->stage[slot];
+        float *din = (float *)b;
+        int32_t *ddl = (int32_t *)(b + b_in);
+        float *dpk = (float *)(b + b_in + b_dl);
+        uint8_t *dlk = (uint8_t *)(b + b_in + b_dl + b_pk);
+        float *deq = (float *)(b + b_in + b_dl + b_pk + b_lk);
+        float *dll = (float *)(b + b_in + b_dl + b_pk + b_lk + b_eq);
+        uint8_t *dhd = (uint8_t *)(b + b_in + b_dl + b_pk + b_lk + b_eq + b_ll);
+        // samples needed by this chunk: [lo, hi)
+        int64_t lo = first + f0 * frame_stride - p.sync_advance;
+        if (lo < 0) lo = 0;
+        int64_t hi = first + (f0 + nf - 1) * frame_stride + fl + p.cp_len;
+        if (hi > n_samples) hi = n_samples;
+        if (hi < lo) hi = lo;
+        CU(cudaMemcpyAsync(din, h_time + 2 * lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, st), "H2D");
+        CU(pl->ks->rx_frames(pl->dev, (const float2 *)din, hi - lo, first + f0 * frame_stride - lo, frame_stride, nf, ddl,
+                             dpk, dlk, nullptr, (float2 *)deq, h_llr ? dll : nullptr, h_hard ? dhd : nullptr, st, pl->sms),
+           "ofdm_rx_frames_host(kernel)");
+        if (h_delay) CU(cudaMemcpyAsync(h_delay + f0, ddl, nf * 4, cudaMemcpyDeviceToHost, st), "D2H");
+        if (h_peak) CU(cudaMemcpyAsync(h_peak + f0, dpk, nf * 4, cudaMemcpyDeviceToHost, st), "D2H");
+        if (h_locked) CU(cudaMemcpyAsync(h_locked + f0, dlk, nf, cudaMemcpyDeviceToHost, st), "D2H");
+        CU(cudaMemcpyAsync(h_eq + 2 * f0 * p.d * ndb, deq, (size_t)nf * p.d * ndb * 8, cudaMemcpyDeviceToHost, st), "D2H");
+        if (h_llr)
+            CU(cudaMemcpyAsync(h_llr + f0 * p.d * ndb * p.bps, dll, (size_t)nf * p.d * ndb * p.bps * 4, cudaMemcpyDeviceToHost, st), "D2H");
+        if (h_hard) CU(cudaMemcpyAsync(h_hard + f0 * p.d * hs, dhd, (size_t)nf * p.d * hs, cudaMemcpyDeviceToHost, st), "D2H");
+    }
+    for (int s = 0; s < ofdm_plan::NSLOT; ++s) CU(cudaStreamSynchronize(pl->st[s]), "ofdm_rx_frames_host(sync)");
+    return OFDM_OK;
+}
+
+int ofdm_tx_modulate_host(ofdm_plan *pl, const uint8_t *h_bits, float *h_time, int64_t n_frames) {
+    if (!pl || !h_time || (!h_bits && pl->prm.d > 0) || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_tx_modulate_host: bad argument%s");
+    if (n_frames == 0) return OFDM_OK;
+    int rc = ensure_streams(pl);
+    if (rc) return rc;
+    const ofdm_params &p = pl->prm;
+    const int64_t fl = ofdm_plan_frame_len(pl), hs = pl->dev.hard_stride;
+    int64_t per = (32ll << 20) / (fl * 8);
+    if (per < 1) per = 1;
+    if (per > n_frames) per = n_frames;
+    const size_t b_bits = al256((size_t)per * p.d * hs + 16), b_out = al256((size_t)per * fl * 8);
+    for (int s = 0; s < ofdm_plan::NSLOT; ++s) {
+        rc = ensure_stage(pl, s, b_bits + b_out);
+        if (rc) return rc;
+    }
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += per, slot ^= 1) {
+        const int64_t nf = (n_frames - f0 < per) ? (n_frames - f0) : per;
+        cudaStream_t st = pl->st[slot];
+        char *b = (char *)pl->stage[slot];
+        if (p.d > 0) CU(cudaMemcpyAsync(b, h_bits + f0 * p.d * hs, (size_t)nf * p.d * hs, cudaMemcpyHostToDevice, st), "H2D");
+        CU(pl->ks->tx(pl->dev, (const uint8_t *)b, (float2 *)(b + b_bits), nf * (p.m0 + p.d), st, pl->sms), "ofdm_tx_modulate_host(kernel)");
+        CU(cudaMemcpyAsync(h_time + 2 * f0 * fl, b + b_bits, (size_t)nf * fl * 8, cudaMemcpyDeviceToHost, st), "D2H");
+    }
+    for (int s = 0; s < ofdm_plan::NSLOT; ++s) CU(cudaStreamSynchronize(pl->st[s]), "ofdm_tx_modulate_host(sync)");
+    return OFDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,4 @@
+#include "launch.cuh"
+namespace ofdm {
+OFDM_DEFINE_KERNELSET(11)
+}

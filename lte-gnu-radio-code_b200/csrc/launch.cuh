@@ -1,0 +1,153 @@
+// launch.cuh -- host-side launchers, instantiated once per log2(NFFT) in inst_n*.cu so the
+// translation units compile in parallel.
+#pragma once
+#include "kernels.cuh"
+
+namespace ofdm {
+
+template <int LOG2N> struct GroupsFor {
+    // threads per CTA = max(T, 128): several small symbols share a CTA
+    static constexpr int value = (LOG2N >= 10) ? 1 : (128 / FftCfg<LOG2N>::T);
+};
+
+struct LaunchDims {
+    int grid, iters;
+};
+
+void count_launch();
+
+// grid = min(#CTAs needed, resident CTAs on the whole device): persistent groups stride over the work
+template <auto kernel>
+static inline cudaError_t plan_launch(int threads, int smem, int groups, long long work, int sms, LaunchDims &dims) {
+    static int cached_dev = -1, cached_bps = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != cached_dev) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_bps, kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (cached_bps < 1) cached_bps = 1;
+        cached_dev = dev;
+    }
+    const long long need = (work + groups - 1) / groups;
+    const long long cap = (long long)sms * cached_bps;
+    long long grid = need < cap ? need : cap;
+    if (grid < 1) grid = 1;
+    dims.grid = (int)grid;
+    dims.iters = (int)((work + grid * groups - 1) / (grid * groups));
+    return cudaSuccess;
+}
+
+#define OFDM_BPS_SWITCH(bps, ...)         \
+    switch (bps) {                        \
+        case 1: { constexpr int BPS = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int BPS = 2; __VA_ARGS__; } break; \
+        case 4: { constexpr int BPS = 4; __VA_ARGS__; } break; \
+        case 6: { constexpr int BPS = 6; __VA_ARGS__; } break; \
+        default: return cudaErrorInvalidValue; \
+    }
+
+template <int LOG2N>
+cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_samples, long long first,
+                             long long frame_stride, long long n_frames, int *delay, float *peak, uint8_t *locked,
+                             float2 *H, float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    if (n_frames <= 0) return cudaSuccess;
+    OFDM_BPS_SWITCH(P.bps, {
+        constexpr auto k = rx_frames_kernel<LOG2N, BPS, G>;
+        LaunchDims d;
+        cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
+        if (e != cudaSuccess) return e;
+        k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H, eq,
+                                  llr, hard);
+        count_launch();
+    })
+    return cudaGetLastError();
+}
+
+template <int LOG2N>
+cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_samples, const long long *start,
+                            const int *delay, const int *hrow, const float2 *H, long long n_sym, float2 *eq,
+                            float *llr, uint8_t *hard, cudaStream_t st, int sms) {
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    if (n_sym <= 0) return cudaSuccess;
+    OFDM_BPS_SWITCH(P.bps, {
+        constexpr auto k = rx_demod_kernel<LOG2N, BPS, G>;
+        LaunchDims d;
+        cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
+        if (e != cudaSuccess) return e;
+        k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
+        count_launch();
+    })
+    return cudaGetLastError();
+}
+
+template <int LOG2N>
+cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long long n_sym_total, cudaStream_t st,
+                      int sms) {
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    if (n_sym_total <= 0) return cudaSuccess;
+    OFDM_BPS_SWITCH(P.bps, {
+        constexpr auto k = tx_kernel<LOG2N, BPS, G>;
+        LaunchDims d;
+        cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
+        if (e != cudaSuccess) return e;
+        k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);
+        count_launch();
+    })
+    return cudaGetLastError();
+}
+
+template <int LOG2N>
+cudaError_t launch_sync_search(const DevParams &P, const float2 *x, long long n_samples, long long first_start,
+                               long long stride, long long n_trials, float *peak, int *delay, cudaStream_t st,
+                               int sms) {
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    if (n_trials <= 0) return cudaSuccess;
+    constexpr auto k = rx_sync_search_kernel<LOG2N, G>;
+    LaunchDims d;
+    cudaError_t e = plan_launch<k>(TH, SM, G, n_trials, sms, d);
+    if (e != cudaSuccess) return e;
+    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first_start, stride, n_trials, d.iters, peak, delay);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int LOG2N>
+cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samples, const long long *pos,
+                           const int *delay, long long n_locks, float2 *H, float2 *htime, float2 *synch_eq,
+                           cudaStream_t st, int sms) {
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    if (n_locks <= 0) return cudaSuccess;
+    constexpr auto k = rx_chanest_kernel<LOG2N, G>;
+    LaunchDims d;
+    cudaError_t e = plan_launch<k>(TH, SM, G, n_locks, sms, d);
+    if (e != cudaSuccess) return e;
+    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, pos, delay, n_locks, d.iters, H, htime, synch_eq);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// one table of launchers per transform size
+struct KernelSet {
+    cudaError_t (*rx_frames)(const DevParams &, const float2 *, long long, long long, long long, long long, int *,
+                             float *, uint8_t *, float2 *, float2 *, float *, uint8_t *, cudaStream_t, int);
+    cudaError_t (*rx_demod)(const DevParams &, const float2 *, long long, const long long *, const int *, const int *,
+                            const float2 *, long long, float2 *, float *, uint8_t *, cudaStream_t, int);
+    cudaError_t (*tx)(const DevParams &, const uint8_t *, float2 *, long long, cudaStream_t, int);
+    cudaError_t (*sync_search)(const DevParams &, const float2 *, long long, long long, long long, long long, float *,
+                               int *, cudaStream_t, int);
+    cudaError_t (*chanest)(const DevParams &, const float2 *, long long, const long long *, const int *, long long,
+                           float2 *, float2 *, float2 *, cudaStream_t, int);
+};
+
+#define OFDM_DEFINE_KERNELSET(LOG2N)                                                               \
+    extern const KernelSet kset_##LOG2N = {launch_rx_frames<LOG2N>, launch_rx_demod<LOG2N>,        \
+                                           launch_tx<LOG2N>, launch_sync_search<LOG2N>,            \
+                                           launch_chanest<LOG2N>};
+
+extern const KernelSet kset_6, kset_7, kset_8, kset_9, kset_10, kset_11, kset_12;
+
+}  // namespace ofdm

@@ -1,0 +1,108 @@
+"""GPU parity: CUDA path (through the C ABI) vs the NumPy oracle on identical inputs.
+
+Bar (BASELINE.json north_star): recovered bits bit-exact; constellation points / equalised
+symbols / LLRs within 1e-4 relative error in fp32 -- relative to the RMS of the compared
+quantity (SURVEY.md section 7 "hard parts").
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import ofdm_oracle as oo  # noqa: E402
+
+RTOL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return float(np.max(np.abs(a - b)) / (np.sqrt(np.mean(np.abs(b) ** 2)) + 1e-30))
+
+
+def make(cfgkw):
+    from ofdm_b200 import Modem, ModemConfig
+    return Modem(ModemConfig(**cfgkw))
+
+
+def oracle_prm(cfg):
+    return oo.ModemParams(nfft=cfg.nfft, cp_len=cfg.cp_len, num_synch_bins=cfg.num_synch_bins,
+                          num_data_bins=cfg.num_data_bins, m0=cfg.m0, d=cfg.d, bps=cfg.bps, snr=cfg.snr,
+                          gate=cfg.gate, compat=cfg.compat, zc_root=cfg.zc_root, equalizer=cfg.equalizer,
+                          sync_advance=cfg.sync_advance)
+
+
+def pack_symbols(bits, n_sym, per_sym, hard_stride):
+    """flat 0/1 -> [n_sym, hard_stride] packed MSB-first, each symbol padded to whole bytes."""
+    b = np.asarray(bits, dtype=np.uint8).reshape(n_sym, per_sym)
+    return np.packbits(b, axis=1)[:, :hard_stride].copy()
+
+
+def unpack_symbols(packed, per_sym):
+    return np.unpackbits(np.asarray(packed), axis=1)[:, :per_sym].reshape(-1)
+
+
+CASES = [
+    dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2),
+    dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4),
+    dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=2, d=2, bps=6),
+    dict(nfft=64, cp_len=16, num_synch_bins=64, num_data_bins=60, m0=1, d=3, bps=2),   # +-N/2 alias (D9)
+    dict(nfft=128, cp_len=32, num_synch_bins=126, num_data_bins=120, m0=1, d=3, bps=1),
+    dict(nfft=256, cp_len=64, num_synch_bins=254, num_data_bins=240, m0=1, d=2, bps=4),
+    dict(nfft=512, cp_len=36, num_synch_bins=510, num_data_bins=480, m0=1, d=3, bps=6),
+    dict(nfft=1024, cp_len=72, num_synch_bins=1022, num_data_bins=600, m0=1, d=2, bps=4),
+    dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=3, bps=6),
+    dict(nfft=4096, cp_len=288, num_synch_bins=4094, num_data_bins=3840, m0=1, d=2, bps=2),
+]
+
+
+@pytest.mark.parametrize("kw", CASES, ids=lambda k: "N%d_b%d_m%d" % (k["nfft"], k["bps"], k["m0"]))
+def test_tx_matches_oracle(kw):
+    m = make(dict(kw, snr=100))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    n_frames = 5
+    rng = np.random.default_rng(1234)
+    per_sym = cfg.num_data_bins * cfg.bps
+    bits = rng.integers(0, 2, n_frames * cfg.d * per_sym)
+    ref = oo.tx_modulate(bits, prm, n_frames)
+    packed = pack_symbols(bits, n_frames * cfg.d, per_sym, cfg.hard_stride)
+    out = m.tx_modulate(torch.from_numpy(packed).cuda(), n_frames).cpu().numpy()
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < RTOL
+
+
+@pytest.mark.parametrize("kw", CASES, ids=lambda k: "N%d_b%d_m%d" % (k["nfft"], k["bps"], k["m0"]))
+def test_rx_frames_matches_oracle(kw):
+    m = make(dict(kw, snr=100, gate=0.5, noise_var=0.01, sync_advance=min(3, kw["cp_len"])))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    n_frames = 6
+    rng = np.random.default_rng(99)
+    per_sym = cfg.num_data_bins * cfg.bps
+    bits = rng.integers(0, 2, n_frames * cfg.d * per_sym)
+    tx = oo.tx_modulate(bits, prm, n_frames)
+    h = oo.reference_channel(cfg.nfft, "Fading")
+    rx = oo.apply_channel(tx, h)[:len(tx)]
+    rx = oo.add_awgn(rx, 1e-4, rng).astype(np.complex64)
+    ref = oo.rx_frames(rx, n_frames, prm)
+    got = m.rx_frames(torch.from_numpy(rx).cuda(), n_frames, want_h=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(got["delay"].cpu().numpy(), ref["delay"])
+    assert np.array_equal(got["locked"].cpu().numpy(), ref["locked"])
+    assert rel_err(got["peak"].cpu().numpy(), ref["peak"]) < RTOL
+    assert rel_err(got["h"].cpu().numpy(), ref["h"]) < RTOL
+    eq = got["eq"].cpu().numpy().reshape(ref["eq"].shape)
+    assert rel_err(eq, ref["eq"]) < RTOL
+    # hard bits: bit-exact vs the oracle's decisions on ITS equalised symbols, and vs the payload
+    ref_bits = oo.hard_bits(ref["eq"].reshape(-1), cfg.bps)
+    got_bits = unpack_symbols(got["hard"].cpu().numpy(), per_sym)
+    assert np.array_equal(got_bits, ref_bits)
+    if cfg.bps <= 2:
+        assert np.array_equal(got_bits, bits)      # constant-modulus payloads survive the per-symbol power normalisation
+    else:
+        assert np.mean(got_bits != bits) < 2e-2    # the reference's unit-power step is biased for QAM
+    # LLR
+    ref_llr = oo.maxlog_llr(ref["eq"].reshape(n_frames * cfg.d, -1), cfg.bps, 1.0 / cfg.noise_var)
+    assert rel_err(got["llr"].cpu().numpy(), ref_llr) < RTOL
