@@ -267,7 +267,7 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
 
     const int nsb = p->num_synch_bins, m0 = p->m0, mm = m0 * nsb;
     // host tables in double precision, rounded once to fp32
-    std::vector<float2> tw(N), zc_bin((size_t)m0 * N, make_float2(0.f, 0.f)), zc_dup((size_t)m0 * 2), zc_tx(N, make_float2(0.f, 0.f));
+    std::vector<float2> tw(N), zc_bin((size_t)m0 * N, make_float2(0.f, 0.f)), zc_dup((size_t)m0 * 2), zc_tx((size_t)m0 * N, make_float2(0.f, 0.f));
     std::vector<float> w_bin(N, 0.f);
     const double two_pi = 6.283185307179586476925286766559;
     for (int k = 0; k < N; ++k) {
@@ -284,9 +284,12 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
         zr[k] = cos(a);
         zi[k] = sin(a);
     }
-    // TX side keys the parity on MM (SynchSignal.py:24); only differs from `par` for gr-RXOFDM with even M0, odd nsb
-    std::vector<double> tzr(nsb), tzi(nsb);
-    for (int k = 0; k < nsb; ++k) {
+    // TX side keys the parity on MM (SynchSignal.py:24); only differs from `par` for gr-RXOFDM with even M0, odd nsb.
+    // Synch symbol m of a frame carries chunk m of the length-MM sequence.  (The reference never advances
+    // synch_state, MultiAntennaSystem.py:143-146, so with M0 > 1 its transmitter repeats chunk 0 while its
+    // receiver correlates against chunk m; M0 = 1, the only pinned case, is unaffected.  DESIGN.md D14.)
+    std::vector<double> tzr(mm), tzi(mm);
+    for (int k = 0; k < mm; ++k) {
         const double kk = (double)k;
         const double q = (mm % 2 == 0) ? kk * kk / 2.0 : kk * (kk + 1.0) / 2.0;
         const double a = -(two_pi / (double)mm) * (double)p->zc_root * q;
@@ -304,7 +307,8 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
             zc_bin[(size_t)s * N + k].x += (float)zr[s * nsb + idx];
             zc_bin[(size_t)s * N + k].y += (float)(-zi[s * nsb + idx]);
         }
-        zc_tx[k] = make_float2((float)tzr[idx], (float)tzi[idx]);   // fancy assignment: last index wins
+        for (int s = 0; s < m0; ++s)   // fancy assignment: last index wins
+            zc_tx[(size_t)s * N + k] = make_float2((float)tzr[s * nsb + idx], (float)tzi[s * nsb + idx]);
     }
     for (int s = 0; s < m0; ++s) {
         zc_dup[2 * s + 0] = make_float2((float)zr[s * nsb + 0], (float)(-zi[s * nsb + 0]));
@@ -312,7 +316,7 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     }
 
     const size_t b_tw = sizeof(float2) * N, b_zb = sizeof(float2) * m0 * N, b_w = sizeof(float) * N,
-                 b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * N;
+                 b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * m0 * N;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt);
     e = cudaMalloc(&pl->d_tables, total);

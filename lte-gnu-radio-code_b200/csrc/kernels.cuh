@@ -19,7 +19,7 @@ struct DevParams {
     const float2 *zc_bin;     // [M0][N]  sum of conj(zc[m*nsb+idx]) over the synch indices that map to FFT bin k
     const float *w_bin;       // [N]      how many synch indices map to bin k (0, 1, or 2 for the +-N/2 alias)
     const float2 *zc_dup;     // [M0][2]  conj(zc) of the first / last synch index (alias handling)
-    const float2 *zc_tx;      // [N]      ZC value the transmitter puts in bin k (0 if unused)
+    const float2 *zc_tx;      // [M0][N]  ZC value the transmitter puts in bin k of synch symbol m (0 if unused)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -513,7 +513,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
         } else if (s < P.m0) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = __ldg(P.zc_tx + j + m * T);
+            for (int m = 0; m < 8; ++m) v[m] = __ldg(P.zc_tx + s * N + j + m * T);
         } else {
             const uint8_t *bp = bits + (f * P.d + (s - P.m0)) * P.hard_stride;
 #pragma unroll

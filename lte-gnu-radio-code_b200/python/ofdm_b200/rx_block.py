@@ -1,0 +1,105 @@
+"""Shared machinery of the two receiver blocks (RXOFDM.synch_and_chan_est and
+utsa_ofdm.SynchAndChanEst): host<->device staging for one work() call and the lock bookkeeping,
+which stays on the host because it is a handful of scalar decisions per call
+(GRR/gr-utsa_ofdm/python/SynchAndChanEst.py:166-175, GRR/gr-RXOFDM/python/synch_and_chan_est.py:170-179).
+All arithmetic on samples runs in the CUDA kernels."""
+import pickle
+
+import numpy as np
+
+from .gr_compat import gr
+from .modem import Modem, ModemConfig
+
+
+class RxBlockBase(gr.sync_block):
+    compat = "utsa"
+
+    def _setup(self, num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr, gate,
+               directory_name, file_name_cest, diagnostics, genie, modulation, zc_root, rows, device):
+        import torch
+        self._torch = torch
+        self.num_ofdm_symb = int(num_ofdm_symb)
+        self.nfft = int(nfft)
+        self.cp_len = int(cp_len)
+        self.num_synch_bins = int(num_synch_bins)
+        self.synch_dat = list(synch_dat)
+        self.num_data_bins = int(num_data_bins)
+        self.SNR = snr
+        self.genie = genie
+        self.directory_name = directory_name
+        self.file_name_cest = file_name_cest
+        self.cfg = ModemConfig(nfft=self.nfft, cp_len=self.cp_len, num_synch_bins=self.num_synch_bins,
+                               num_data_bins=self.num_data_bins, m0=int(synch_dat[0]), d=int(synch_dat[1]),
+                               bps=modulation, snr=float(snr), gate=float(gate), compat=self.compat, zc_root=zc_root)
+        self.modem = Modem(self.cfg, device=device)
+        c = self.cfg
+        self.M = [c.m0, c.num_synch_bins]
+        self.MM = c.mm
+        self.L_synch = c.num_synch_bins
+        self.stride_val = c.stride
+        self.start_samp = c.cp_len
+        self.rx_b_len = c.sym_len
+        self.max_num_corr = 100
+        self.rows = rows
+        self._d_H = torch.zeros((rows, c.nfft), dtype=torch.complex64, device=self.modem.device)
+        self.est_chan_time = np.zeros((rows, c.nfft), dtype=complex)
+        self.est_synch_freq = np.zeros((rows, c.mm), dtype=complex)
+        self.est_data_freq = np.zeros((rows, c.num_data_bins), dtype=complex)
+        self.count = 0
+        self.last_written = 0
+
+    # state the reference keeps as a NumPy array; here it lives on the device and is read on demand
+    @property
+    def est_chan_freq_P(self):
+        return self._d_H.cpu().numpy().astype(complex)
+
+    def _upload(self, in0):
+        torch = self._torch
+        a = np.ascontiguousarray(in0, dtype=np.complex64)
+        return torch.from_numpy(a).to(self.modem.device, non_blocking=False)
+
+    def _n_valid_trials(self, n):
+        """Trials P = 0.. that pass the window guard M0*L + P*stride + N + CP < len(in0)
+        (SynchAndChanEst.py:139,144)."""
+        c = self.cfg
+        n_trials = int(np.around(n / c.stride))
+        room = n - c.m0 * c.sym_len - c.nfft - c.cp_len      # need P*stride < room
+        if room <= 0:
+            return 0
+        return min(n_trials, (room - 1) // c.stride + 1)
+
+    def _search(self, rx, n):
+        nv = self._n_valid_trials(n)
+        if nv == 0:
+            return np.zeros(0, np.float32), np.zeros(0, np.int32)
+        peak, delay = self.modem.sync_search(rx, self.cfg.cp_len, self.cfg.stride, nv)
+        return peak.cpu().numpy(), delay.cpu().numpy()
+
+    def _estimate_into(self, rx, rows, pos, delay):
+        """Channel estimates for new locks -> state rows; aux outputs only when diagnostics ask."""
+        torch = self._torch
+        dev = self.modem.device
+        want_aux = True
+        h, ht, se = self.modem.chanest(rx, torch.tensor(pos, dtype=torch.int64, device=dev),
+                                       torch.tensor(delay, dtype=torch.int32, device=dev), want_aux=want_aux)
+        idx = torch.tensor(rows, dtype=torch.int64, device=dev)
+        self._d_H.index_copy_(0, idx, h)
+        ht_h, se_h = ht.cpu().numpy(), se.cpu().numpy()
+        for i, r in enumerate(rows):
+            self.est_chan_time[r] = ht_h[i]
+            self.est_synch_freq[r] = se_h[i]
+        return ht_h
+
+    def _dump_chan(self, chan_est_tim, path):
+        with open(path, "wb") as f:
+            pickle.dump(np.asarray(chan_est_tim, dtype=complex).reshape(1, -1), f, protocol=2)
+
+    def _demod_into(self, rx, rows, start, delay, hrow):
+        if not rows:
+            return
+        torch = self._torch
+        dev = self.modem.device
+        eq, _, _ = self.modem.demod(rx, torch.tensor(start, dtype=torch.int64, device=dev),
+                                    torch.tensor(delay, dtype=torch.int32, device=dev),
+                                    torch.tensor(hrow, dtype=torch.int32, device=dev), self._d_H)
+        self.est_data_freq[np.asarray(rows)] = eq.cpu().numpy()

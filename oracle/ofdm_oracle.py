@@ -198,9 +198,11 @@ def bits_to_symbols(bits, bps):
 def tx_freq_grid(bits, prm: ModemParams, n_frames):
     """[n_frames*(M0+D), N] frequency grid.  MultiAntennaSystem.py:135-183, SDRScript.py:79-85.
 
-    ``bits`` is a flat 0/1 array of n_frames*D*ndb*bps payload bits.  The synch symbols carry the
-    first num_synch_bins entries of the ZC sequence (synch_state never advances in the reference:
-    MultiAntennaSystem.py:143-146 re-reduces it modulo M0 but never increments it).
+    ``bits`` is a flat 0/1 array of n_frames*D*ndb*bps payload bits.  Synch symbol m of a frame
+    carries chunk m of the length-MM ZC sequence.  DEVIATION: the reference computes
+    the chunk from synch_state but never advances it (MultiAntennaSystem.py:143-146), so with
+    M0 > 1 it would repeat chunk 0 while its own receiver correlates against chunk m; for M0 = 1,
+    the only case any fixture pins, both readings coincide.
     """
     N = prm.nfft
     zc = zadoff_chu(prm.mm, prm.zc_root)            # TX side always keys parity on MM (SynchSignal.py:24)
@@ -215,7 +217,7 @@ def tx_freq_grid(bits, prm: ModemParams, n_frames):
         for s in range(prm.frame_syms):
             row = f * prm.frame_syms + s
             if s < prm.m0:
-                grid[row, sb] = zc[0:prm.num_synch_bins]
+                grid[row, sb] = zc[s * prm.num_synch_bins:(s + 1) * prm.num_synch_bins]
             else:
                 chunk = bits[data_i * per_sym:(data_i + 1) * per_sym]
                 grid[row, db] = bits_to_symbols(chunk, prm.bps)
