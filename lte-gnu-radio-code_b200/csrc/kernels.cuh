@@ -4,6 +4,15 @@
 // stride over the work list.  All per-bin work (ZC correlation, channel estimate, equaliser gain,
 // de-rotation, demapping) is done on the registers the FFT leaves behind, so a received sample is
 // read from HBM exactly once and every output is written exactly once.
+//
+// Instruction-count rules followed throughout (the N=64 case is issue-bound before it is HBM-bound):
+//   * per-thread bin bookkeeping (which of my 8 bins are used, where they land) is computed once;
+//     thread j's bins are j + m*T, so within each spectrum half its outputs sit at a fixed stride
+//     and every store is `base + compile-time offset`;
+//   * groups past the end of the work list redo the last item (identical duplicate writes) instead
+//     of carrying a `valid` predicate through every load and store;
+//   * the next symbol's samples are requested (registers) before the current one is transformed,
+//     so DRAM latency overlaps the arithmetic instead of stalling it.
 #pragma once
 #include "fft_core.cuh"
 
@@ -33,8 +42,55 @@ __device__ __forceinline__ int used_index(int k, int N, int n) {
     return -1;
 }
 
-__device__ __forceinline__ float2 ldg_sample(const float2 *__restrict__ x, long long i, long long n) {
-    return (i >= 0 && i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+// Where thread j's eight bins (j + m*T) land in a used-bin list of length n.  m < 4 is the positive
+// half of the spectrum (incl. DC), m >= 4 the negative half; inside a half consecutive m are T apart
+// in the output as well, so a store is  half_base + m*T  with m*T a compile-time constant.
+struct BinMap {
+    int base_p;        // output index of bin j (m = 0) if it were used:      j - 1 + n/2
+    int base_n;        // output index of bin j + 4T (m = 4) if it were used: j + 4T - (N - n/2)
+    unsigned mask;     // bit m set <=> bin j + m*T is in the list
+};
+template <int T> __device__ __forceinline__ BinMap make_bin_map(int n, int j) {
+    constexpr int N = 8 * T;
+    const int h = n >> 1;
+    BinMap b;
+    b.base_p = j - 1 + h;
+    b.base_n = j + 4 * T - (N - h);
+    b.mask = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int k = j + m * T;
+        const bool used = (m < 4) ? (k >= 1 && k <= h) : (k >= N - h);
+        b.mask |= used ? (1u << m) : 0u;
+    }
+    return b;
+}
+template <int T> __device__ __forceinline__ int bin_out(const BinMap &b, int m) {
+    return (m < 4 ? b.base_p : b.base_n - 4 * T) + m * T;
+}
+
+__device__ __forceinline__ float2 ld_stream(const float2 *p) {      // read-once data: do not allocate in L1
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
+// this thread's 8 samples of the N-sample window that opens at `start` (zero beyond the buffer)
+template <int T>
+__device__ __forceinline__ void load8(float2 (&v)[8], const float2 *__restrict__ x, long long start, long long n,
+                                      int j) {
+    constexpr int N = 8 * T;
+    if (start >= 0 && start + N <= n) {
+        const float2 *p = x + start + j;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = ld_stream(p + m * T);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const long long i = start + j + m * T;
+            v[m] = (i >= 0 && i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
+        }
+    }
 }
 
 template <int T, int GROUPS>
@@ -68,42 +124,56 @@ __device__ __forceinline__ float3 group_sum3(float3 x, float *red, int j, int gi
 // ------------------------------------------------------------------------------------------------
 // demapping: exact max-log LLR per bit for Gray PAM per axis (closed forms; the oracle brute-forces
 // the same definition).  L > 0 <=> bit 1.  Bit order MSB first: I0 Q0 I1 Q1 I2 Q2.
+//   L_b = scale * ( min_{s:b=0} (x-s)^2 - min_{s:b=1} (x-s)^2 ),  c = 4*a*scale, t = |x|
+//   sign bit  : -sgn(x) * c * (t + max(t-2a,0) [+ max(t-4a,0) + max(t-6a,0)])
+//   16-QAM b1 : c * (t - 2a)
+//   64-QAM b1 : c * ((t-4a) + min(t-2a,0) + max(t-6a,0));   b2 : c * (|t-4a| - 2a)
 // ------------------------------------------------------------------------------------------------
-template <int BPA> __device__ __forceinline__ void pam_llr(float x, float a, float (&A)[3]) {
-    const float t = fabsf(x);
-    if (BPA == 1) {
-        A[0] = -4.f * a * x;
-    } else if (BPA == 2) {
-        A[0] = -copysignf(4.f * a * (t + fmaxf(0.f, t - 2.f * a)), x);
-        A[1] = 4.f * a * (t - 2.f * a);
-    } else {
-        A[0] = -copysignf(4.f * a * (t + fmaxf(0.f, t - 2.f * a) + fmaxf(0.f, t - 4.f * a) + fmaxf(0.f, t - 6.f * a)), x);
-        A[1] = 4.f * a * ((t - 4.f * a) + fminf(0.f, t - 2.f * a) + fmaxf(0.f, t - 6.f * a));
-        A[2] = 4.f * a * fabsf(t - 4.f * a) - 8.f * a * a;
-    }
+__device__ __forceinline__ float flip_sign_of(float mag, float x) {       // mag >= 0 -> -sgn(x)*mag
+    return __uint_as_float(__float_as_uint(mag) | (~__float_as_uint(x) & 0x80000000u));
 }
+__device__ __forceinline__ unsigned neg_bit(float x) { return __float_as_uint(x) >> 31; }
 
-template <int BPS> __device__ __forceinline__ void demap(float2 z, float scale, float (&L)[BPS], unsigned &bits) {
-    if (BPS == 1) {
-        L[0] = 4.f * z.x * scale;                       // levels 2b-1: bit 1 -> +1
-        bits = L[0] > 0.f;
-        return;
-    }
-    constexpr int BPA = BPS / 2 > 0 ? BPS / 2 : 1;
-    const float a = BPS == 2 ? 0.70710678118654752440f : (BPS == 4 ? 0.31622776601683793320f : 0.15430334996209191026f);
-    float AI[3], AQ[3];
-    pam_llr<BPA>(z.x, a, AI);
-    pam_llr<BPA>(z.y, a, AQ);
-    bits = 0;
+template <int BPS> struct Demapper {
+    static constexpr float A = BPS == 2 ? 0.70710678118654752440f
+                                        : (BPS == 4 ? 0.31622776601683793320f : 0.15430334996209191026f);
+    float c;
+    __device__ __forceinline__ explicit Demapper(float scale) : c(BPS == 1 ? 4.f * scale : 4.f * A * scale) {}
+
+    __device__ __forceinline__ void run(float2 z, float (&L)[BPS], unsigned &bits) const {
+        if (BPS == 1) {
+            L[0] = c * z.x;                              // levels 2b-1: bit 1 -> +1
+            bits = neg_bit(z.x) ^ 1u;
+        } else if (BPS == 2) {
+            L[0] = -c * z.x;
+            L[1] = -c * z.y;
+            bits = (neg_bit(z.x) << 1) | neg_bit(z.y);
+        } else if (BPS == 4) {
+            const float ux = fabsf(z.x) - 2.f * A, uy = fabsf(z.y) - 2.f * A;
+            L[0] = flip_sign_of(c * (fabsf(z.x) + fmaxf(ux, 0.f)), z.x);
+            L[1] = flip_sign_of(c * (fabsf(z.y) + fmaxf(uy, 0.f)), z.y);
+            L[2] = c * ux;
+            L[3] = c * uy;
+            bits = (neg_bit(z.x) << 3) | (neg_bit(z.y) << 2) | ((neg_bit(ux) ^ 1u) << 1) | (neg_bit(uy) ^ 1u);
+        } else {
+            float a0[2], a1[2], a2[2];
+            const float xs[2] = {z.x, z.y};
 #pragma unroll
-    for (int i = 0; i < BPA; ++i) {
-        L[2 * i] = AI[i] * scale;
-        L[2 * i + 1] = AQ[i] * scale;
-        bits = (bits << 2) | ((AI[i] > 0.f) << 1) | (AQ[i] > 0.f);
+            for (int i = 0; i < 2; ++i) {
+                const float t = fabsf(xs[i]);
+                const float u2 = t - 2.f * A, u4 = t - 4.f * A, u6 = t - 6.f * A;
+                a0[i] = flip_sign_of(c * (t + fmaxf(u2, 0.f) + fmaxf(u4, 0.f) + fmaxf(u6, 0.f)), xs[i]);
+                a1[i] = c * (u4 + fminf(u2, 0.f) + fmaxf(u6, 0.f));
+                a2[i] = c * (fabsf(u4) - 2.f * A);
+            }
+            L[0] = a0[0]; L[1] = a0[1]; L[2] = a1[0]; L[3] = a1[1]; L[4] = a2[0]; L[5] = a2[1];
+            bits = (neg_bit(z.x) << 5) | (neg_bit(z.y) << 4) | ((unsigned)(a1[0] > 0.f) << 3) |
+                   ((unsigned)(a1[1] > 0.f) << 2) | ((unsigned)(a2[0] > 0.f) << 1) | (unsigned)(a2[1] > 0.f);
+        }
     }
-}
+};
 
-// bits (MSB-first value of one bin) -> constellation point; inverse of demap's hard decision.
+// bits (MSB-first value of one bin) -> constellation point; inverse of the demapper's hard decision.
 // QPSK points follow MultiAntennaSystem.py:171-178, BPSK :156-157, 16/64-QAM TS 36.211 7.1.
 template <int BPS> __device__ __forceinline__ float2 map_bits(unsigned v) {
     if (BPS == 1) return make_float2(v ? 1.f : -1.f, 0.f);
@@ -113,40 +183,53 @@ template <int BPS> __device__ __forceinline__ float2 map_bits(unsigned v) {
     }
     if (BPS == 4) {
         const float a = 0.31622776601683793320f;
-        const float i = ((v & 8) ? -1.f : 1.f) * ((v & 2) ? 3.f : 1.f);
-        const float q = ((v & 4) ? -1.f : 1.f) * ((v & 1) ? 3.f : 1.f);
-        return make_float2(i * a, q * a);
+        const float i = ((v & 8) ? -a : a) * ((v & 2) ? 3.f : 1.f);
+        const float q = ((v & 4) ? -a : a) * ((v & 1) ? 3.f : 1.f);
+        return make_float2(i, q);
     }
     const float a = 0.15430334996209191026f;
-    // magnitude by (b1,b2): 00->3 01->1 10->5 11->7
-    const int mi = ((v >> 3) & 1) * 2 + ((v >> 1) & 1), mq = ((v >> 2) & 1) * 2 + (v & 1);
-    const float tab[4] = {3.f, 1.f, 5.f, 7.f};
-    const float i = ((v & 32) ? -1.f : 1.f) * tab[mi];
-    const float q = ((v & 16) ? -1.f : 1.f) * tab[mq];
-    return make_float2(i * a, q * a);
+    // magnitude by (b1,b2): 00->3 01->1 10->5 11->7   ==  4 + (2*b1-1)*(2 + (2*b2-1)) ... as a 4-entry nibble table
+    const unsigned mi = ((v >> 2) & 2) | ((v >> 1) & 1), mq = ((v >> 1) & 2) | (v & 1);
+    const float i = (float)((0x7513u >> (4 * mi)) & 15u), q = (float)((0x7513u >> (4 * mq)) & 15u);
+    return make_float2((v & 32) ? -a * i : a * i, (v & 16) ? -a * q : a * q);
 }
 
 // read BPS bits starting at bit offset `bo` of a packed MSB-first byte string
 template <int BPS> __device__ __forceinline__ unsigned read_bits(const uint8_t *__restrict__ p, int bo, int nbytes) {
     const int by = bo >> 3, sh = bo & 7;
     unsigned w = (unsigned)__ldg(p + by) << 8;
-    if (BPS + sh > 8 && by + 1 < nbytes) w |= (unsigned)__ldg(p + by + 1);
+    if (BPS == 6 && by + 1 < nbytes) w |= (unsigned)__ldg(p + by + 1);
     return (w >> (16 - sh - BPS)) & ((1u << BPS) - 1u);
 }
 
-// pack the per-bin values staged in hb[0..ndb) into MSB-first bytes; thread i makes bytes i, i+T, ...
+// Pack the per-bin values staged in hb[] (one byte per data bin, zero-padded past ndb) into
+// MSB-first bytes with word-wide shared-memory reads; thread i produces bytes i, i+T, ...
 template <int BPS, int T>
-__device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict__ out, int ndb, int nbytes, int j) {
-    for (int b = j; b < nbytes; b += T) {
-        unsigned acc = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int p = 8 * b + i;
-            const int bin = p / BPS, bit = p - bin * BPS;
-            const unsigned v = bin < ndb ? hb[bin] : 0u;
-            acc = (acc << 1) | ((v >> (BPS - 1 - bit)) & 1u);
+__device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict__ out, int nbytes, int j) {
+    if (BPS == 4) {
+        for (int b = j; b < nbytes; b += T) {
+            const unsigned w = *reinterpret_cast<const uint16_t *>(hb + 2 * b);
+            out[b] = (uint8_t)(((w & 15u) << 4) | (w >> 8));
         }
-        out[b] = (uint8_t)acc;
+    } else if (BPS == 2) {
+        for (int b = j; b < nbytes; b += T) {
+            const unsigned w = *reinterpret_cast<const uint32_t *>(hb + 4 * b);
+            out[b] = (uint8_t)(((w & 3u) << 6) | ((w >> 4) & 0x30u) | ((w >> 14) & 0x0cu) | (w >> 24));
+        }
+    } else if (BPS == 1) {
+        for (int b = j; b < nbytes; b += T) {
+            const uint2 w = *reinterpret_cast<const uint2 *>(hb + 8 * b);
+            out[b] = (uint8_t)((((w.x * 0x08040201u) >> 24) << 4) | ((w.y * 0x08040201u) >> 24));
+        }
+    } else {
+        const int quads = (nbytes + 2) / 3;
+        for (int q = j; q < quads; q += T) {
+            const unsigned w = *reinterpret_cast<const uint32_t *>(hb + 4 * q);
+            const unsigned v = ((w & 63u) << 18) | (((w >> 8) & 63u) << 12) | (((w >> 16) & 63u) << 6) | (w >> 24);
+            if (3 * q + 0 < nbytes) out[3 * q + 0] = (uint8_t)(v >> 16);
+            if (3 * q + 1 < nbytes) out[3 * q + 1] = (uint8_t)(v >> 8);
+            if (3 * q + 2 < nbytes) out[3 * q + 2] = (uint8_t)v;
+        }
     }
 }
 
@@ -156,7 +239,8 @@ template <int LOG2N, int GROUPS> struct Smem {
     static constexpr int GSTRIDE = (LOG2N == 6) ? (2 * C::BUF + 8) : 2 * C::BUF;   // complex slots per group
     static constexpr int FFT_BYTES = GROUPS * GSTRIDE * 8;
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
-    static constexpr int HB_BYTES = GROUPS * C::N;
+    static constexpr int HB_STRIDE = C::N + 8;                                      // +8: zero pad, staggers banks
+    static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
     static constexpr int BYTES = FFT_BYTES + RED_BYTES + HB_BYTES;
     __device__ static float2 *buf0(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s) + gid * GSTRIDE; }
     __device__ static float *redf(unsigned char *s, int gid) {
@@ -165,46 +249,47 @@ template <int LOG2N, int GROUPS> struct Smem {
     __device__ static unsigned long long *redu(unsigned char *s, int gid) {
         return reinterpret_cast<unsigned long long *>(s + FFT_BYTES) + gid * 16;
     }
-    __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + FFT_BYTES + RED_BYTES + gid * C::N; }
+    __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + FFT_BYTES + RED_BYTES + gid * HB_STRIDE; }
 };
 
 // ------------------------------------------------------------------------------------------------
-// synchronisation on one preamble: M0 FFTs -> ZC correlation in the frequency domain -> the
-// (CP+1)-delay bank evaluated as ONE inverse FFT (c[d] = sum_k y_k e^{+j2pi dk/N} is an N-point
-// inverse DFT sampled at d = 0..CP), instead of the reference's dense (CP+1) x MM matmul.
-// SynchAndChanEst.py:145-164.  On return ys[m] holds sum_m0 X[k]*conj(zc) for k = j+m*T,
-// p_est the unit-power factor; key encodes (max |c|^2, lowest d).
+// Preamble handling, split in two so the framed kernel can prefetch between the pieces.
+//
+// sync_accumulate: after the forward FFT of synch symbol s, add this thread's bins into the
+//   correlation sums  ys_k += X_k * conj(zc_k)  and the power sum (SynchAndChanEst.py:153-157).
+// sync_finish: unit-power factor, then the (CP+1)-delay bank evaluated as ONE inverse FFT
+//   (c[d] = sum_k ys_k e^{+j2pi dk/N} is an N-point inverse DFT sampled at d = 0..CP) instead of
+//   the reference's dense (CP+1) x MM matmul, then max / first argmax over d (:160-164).
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N, int GROUPS>
-__device__ __forceinline__ void sync_core(const DevParams &P, const float2 *__restrict__ x, long long n_samples,
-                                          long long pos, bool valid, const float2 *twr, float2 *b0, float2 *b1,
-                                          float *redf, unsigned long long *redu, int j, int gid, int &pp,
-                                          float2 (&ys)[8], float2 (&ydup)[2], float &p_est, float &peak, int &delay) {
-    using C = FftCfg<LOG2N>;
-    constexpr int T = C::T, N = C::N;
-    const int L = N + P.cp;
-    float pw = 0.f;
+template <int LOG2N>
+__device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2 (&v)[8], int s, int j,
+                                                float2 (&ys)[8], float2 (&ydup)[2], float &pw) {
+    constexpr int T = FftCfg<LOG2N>::T, N = FftCfg<LOG2N>::N;
+    const float2 *zb = P.zc_bin + s * N + j;
+    const float *wb = P.w_bin + j;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
-    ydup[0] = ydup[1] = make_float2(0.f, 0.f);
-    for (int s = 0; s < P.m0; ++s) {
-        float2 v[8];
-        const long long base = pos + (long long)s * L + j;
+    for (int m = 0; m < 8; ++m) {
+        pw = fmaf(__ldg(wb + m * T), cabs2(v[m]), pw);
+        const float2 z = __ldg(zb + m * T);
+        ys[m].x = fmaf(v[m].x, z.x, fmaf(-v[m].y, z.y, ys[m].x));
+        ys[m].y = fmaf(v[m].x, z.y, fmaf(v[m].y, z.x, ys[m].y));
+    }
+    if (P.dup_bin >= 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = valid ? ldg_sample(x, base + m * T, n_samples) : make_float2(0.f, 0.f);
-        fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int k = j + m * T;
-            pw = fmaf(__ldg(P.w_bin + k), cabs2(v[m]), pw);
-            const float2 z = __ldg(P.zc_bin + s * N + k);
-            ys[m] = cadd(ys[m], cmul(v[m], z));
-            if (k == P.dup_bin) {
+        for (int m = 0; m < 8; ++m)
+            if (j + m * T == P.dup_bin) {
                 ydup[0] = cadd(ydup[0], cmul(v[m], __ldg(P.zc_dup + 2 * s)));
                 ydup[1] = cadd(ydup[1], cmul(v[m], __ldg(P.zc_dup + 2 * s + 1)));
             }
-        }
     }
+}
+
+template <int LOG2N, int GROUPS>
+__device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&ys)[8], float pw, const float2 *twr,
+                                            float2 *b0, float2 *b1, float *redf, unsigned long long *redu, int j,
+                                            int gid, int &pp, float &p_est, float &peak, int &delay) {
+    using C = FftCfg<LOG2N>;
+    constexpr int T = C::T;
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     p_est = pw > 0.f ? sqrtf((float)P.mm / pw) : 0.f;
     float2 c[8];
@@ -245,58 +330,69 @@ __device__ __forceinline__ void chan_core(const DevParams &P, const float2 (&ys)
         const float2 h = cscale(cmulc(y, w), sc);
         H[m] = h;
         const float den = cabs2(h) + inv_reg;
-        const float inv = den > 0.f ? 1.f / den : 0.f;
+        const float inv = den > 0.f ? __fdividef(1.f, den) : 0.f;
         G[m] = cscale(cmulc(make_float2(h.x, -h.y), w), inv);
     }
 }
 
+// Everything a data symbol's epilogue needs that does not change from symbol to symbol.
+template <int LOG2N, int BPS> struct DataCtx {
+    BinMap map;
+    Demapper<BPS> dem;
+    float sqrt_ndb;
+    __device__ __forceinline__ DataCtx(const DevParams &P, int j)
+        : map(make_bin_map<FftCfg<LOG2N>::T>(P.ndb, j)), dem(P.llr_scale), sqrt_ndb(sqrtf((float)P.ndb)) {}
+};
+
 // equalise + demap + store one data symbol held in v[] (FFT output).  SynchAndChanEst.py:232-248.
 template <int LOG2N, int BPS, int GROUPS>
-__device__ __forceinline__ void data_epilogue(const DevParams &P, const float2 (&v)[8], const float2 (&G)[8],
-                                              long long row, bool valid, float *redf, uint8_t *hb, int j, int gid,
-                                              float2 *__restrict__ eq_out, float *__restrict__ llr_out,
+__device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<LOG2N, BPS> &D, const float2 (&v)[8],
+                                              const float2 (&G)[8], long long row, float *redf, uint8_t *hb, int j,
+                                              int gid, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                                               uint8_t *__restrict__ hard_out) {
     using C = FftCfg<LOG2N>;
-    constexpr int T = C::T, N = C::N;
-    int jo[8];
+    constexpr int T = C::T;
+    const unsigned mask = D.map.mask;
     float pw = 0.f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        jo[m] = used_index(j + m * T, N, P.ndb);
-        pw += jo[m] >= 0 ? cabs2(v[m]) : 0.f;
-    }
+    for (int m = 0; m < 8; ++m)
+        if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
-    const float p0 = pw > 0.f ? sqrtf((float)P.ndb / pw) : 0.f;
+    const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
+    float2 *eqp = eq_out + row * P.ndb + D.map.base_p;
+    float2 *eqn = eq_out + row * P.ndb + (D.map.base_n - 4 * T);
+    float *lp = llr_out + (row * P.ndb + D.map.base_p) * BPS;
+    float *ln = llr_out + (row * P.ndb + (D.map.base_n - 4 * T)) * BPS;
+    uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - 4 * T);
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-        if (jo[m] >= 0) {
+        if (mask & (1u << m)) {
             const float2 z = cscale(cmul(G[m], v[m]), p0);
-            const long long o = row * P.ndb + jo[m];
-            if (valid) eq_out[o] = z;
+            __stcs((m < 4 ? eqp : eqn) + m * T, z);
             if (soft || hard) {
                 float Lb[BPS];
                 unsigned bits;
-                demap<BPS>(z, P.llr_scale, Lb, bits);
-                if (soft && valid) {
-                    float *lp = llr_out + o * BPS;
+                D.dem.run(z, Lb, bits);
+                if (soft) {
+                    float *q = (m < 4 ? lp : ln) + m * T * BPS;
                     if (BPS == 1) {
-                        lp[0] = Lb[0];
+                        __stcs(q, Lb[0]);
                     } else if (BPS == 4) {
-                        *reinterpret_cast<float4 *>(lp) = make_float4(Lb[0], Lb[1], Lb[2], Lb[3]);
+                        __stcs(reinterpret_cast<float4 *>(q), make_float4(Lb[0], Lb[1], Lb[2], Lb[3]));
                     } else {
 #pragma unroll
-                        for (int b = 0; b < BPS; b += 2)
-                            *reinterpret_cast<float2 *>(lp + b) = make_float2(Lb[b], Lb[b + 1 < BPS ? b + 1 : b]);
+                        for (int b = 0; b + 1 < BPS; b += 2)
+                            __stcs(reinterpret_cast<float2 *>(q + b), make_float2(Lb[b], Lb[b + 1]));
                     }
                 }
-                if (hard) hb[jo[m]] = (uint8_t)bits;
+                if (hard) (m < 4 ? hp : hn)[m * T] = (uint8_t)bits;
             }
         }
     }
     if (hard) {
         group_sync<T, GROUPS>(gid);
-        if (valid) pack_bits<BPS, T>(hb, hard_out + row * P.hard_stride, P.ndb, P.hard_stride, j);
+        pack_bits<BPS, T>(hb, hard_out + row * P.hard_stride, P.hard_stride, j);
     }
 }
 
@@ -310,56 +406,80 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const float2 (
     float *redf = S::redf(smem_raw, gid);                                              \
     unsigned long long *redu = S::redu(smem_raw, gid);                                 \
     uint8_t *hb = S::hb(smem_raw, gid);                                                \
-    (void)redu; (void)hb; (void)redf;                                                  \
+    (void)redu; (void)redf;                                                            \
+    for (int i = j; i < S::HB_STRIDE; i += T) hb[i] = 0;                               \
     float2 twr[C::NTW > 0 ? C::NTW : 1];                                               \
     load_twiddles<LOG2N>(twr, P.tw, j);                                                \
     const long long total_groups = (long long)gridDim.x * GROUPS;                      \
     const long long gg = (long long)blockIdx.x * GROUPS + gid;                         \
     int pp = 0;
 
+template <int LOG2N> struct MinBlocks {
+    // resident CTAs per SM the register allocator should aim for (threads per CTA = max(T,128))
+    static constexpr int value = LOG2N <= 9 ? 4 : (LOG2N == 10 ? 4 : (LOG2N == 11 ? 2 : 1));
+};
+
 // ------------------------------------------------------------------------------------------------
 // K1  framed receiver: sync + channel estimate + D data symbols per frame, fused.
+//     The group walks its frames symbol by symbol; while symbol q is transformed the samples of
+//     symbol q+1 (next symbol of the frame, or the preamble of the group's next frame) are in flight.
 // ------------------------------------------------------------------------------------------------
 template <int LOG2N, int BPS, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS)
+__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
                  float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, float2 *__restrict__ H_out,
                  float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
     OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
     constexpr int N = C::N;
-    const int L = N + P.cp;
+    const int L = N + P.cp, fs = P.m0 + P.d;
+    const DataCtx<LOG2N, BPS> D(P, j);
+    const long long last_frame = n_frames - 1;
+    const long long off0 = first + P.cp - P.sync_advance;
+    long long f = gg < last_frame ? gg : last_frame;
+    long long pos = off0 + f * frame_stride;
+    float2 cur[8], nxt[8];
+    load8<T>(cur, x, pos, n_samples, j);
     for (int it = 0; it < iters; ++it) {
-        const long long f = gg + (long long)it * total_groups;
-        const bool valid = f < n_frames;
-        const long long pos = first + f * frame_stride + P.cp - P.sync_advance;
-        float2 ys[8], ydup[2], H[8], G[8];
-        float p_est, peak;
-        int delay;
-        sync_core<LOG2N, GROUPS>(P, x, n_samples, pos, valid, twr, b0, b1, redf, redu, j, gid, pp, ys, ydup, p_est,
-                                 peak, delay);
-        chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq, j, H, G);
-        if (valid) {
-            if (j == 0) {
-                delay_out[f] = delay;
-                peak_out[f] = peak;
-                locked_out[f] = peak > P.gate_thresh ? 1 : 0;
-            }
-            if (H_out != nullptr) {
+        long long fn = gg + (long long)(it + 1) * total_groups;
+        fn = fn < last_frame ? fn : last_frame;
+        const long long npos = off0 + fn * frame_stride;
+        float2 ys[8], ydup[2], G[8];
+        float pw = 0.f;
 #pragma unroll
-                for (int m = 0; m < 8; ++m) H_out[f * N + j + m * T] = H[m];
-            }
-        }
-        const long long dbase = pos + (long long)P.m0 * L + j;
-        for (int n = 0; n < P.d; ++n) {
-            float2 v[8];
-            const long long sb = dbase + (long long)n * L;
+        for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
+        ydup[0] = ydup[1] = make_float2(0.f, 0.f);
+        for (int s = 0; s < fs; ++s) {
+            const long long nstart = (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos;
+            load8<T>(nxt, x, nstart, n_samples, j);          // (the very last prefetch re-reads a valid window)
+            fft_group<LOG2N, false, GROUPS>(cur, twr, b0, b1, j, gid, pp);
+            if (s < P.m0) {
+                sync_accumulate<LOG2N>(P, cur, s, j, ys, ydup, pw);
+                if (s == P.m0 - 1) {
+                    float p_est, peak;
+                    int delay;
+                    float2 H[8];
+                    sync_finish<LOG2N, GROUPS>(P, ys, pw, twr, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+                    chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq, j, H, G);
+                    if (j == 0) {
+                        delay_out[f] = delay;
+                        peak_out[f] = peak;
+                        locked_out[f] = peak > P.gate_thresh ? 1 : 0;
+                    }
+                    if (H_out != nullptr) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = valid ? ldg_sample(x, sb + m * T, n_samples) : make_float2(0.f, 0.f);
-            fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
-            data_epilogue<LOG2N, BPS, GROUPS>(P, v, G, f * P.d + n, valid, redf, hb, j, gid, eq_out, llr_out,
-                                              hard_out);
+                        for (int m = 0; m < 8; ++m) H_out[f * N + j + m * T] = H[m];
+                    }
+                }
+            } else {
+                data_epilogue<LOG2N, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, j, gid, eq_out, llr_out,
+                                                  hard_out);
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) cur[m] = nxt[m];
         }
+        f = fn;
+        pos = npos;
     }
 }
 
@@ -367,20 +487,31 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
 // K2  sliding search: one trial per group iteration.  Outputs max|c| and argmax per trial.
 // ------------------------------------------------------------------------------------------------
 template <int LOG2N, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS)
+__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
                       long long stride, long long n_trials, int iters, float *__restrict__ peak_out,
                       int *__restrict__ delay_out) {
     OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
+    constexpr int N = C::N;
+    const int L = N + P.cp;
     for (int it = 0; it < iters; ++it) {
-        const long long t = gg + (long long)it * total_groups;
-        const bool valid = t < n_trials;
+        long long t = gg + (long long)it * total_groups;
+        t = t < n_trials - 1 ? t : n_trials - 1;
+        const long long pos = first_start + t * stride;
         float2 ys[8], ydup[2];
-        float p_est, peak;
+        float pw = 0.f, p_est, peak;
         int delay;
-        sync_core<LOG2N, GROUPS>(P, x, n_samples, first_start + t * stride, valid, twr, b0, b1, redf, redu, j, gid,
-                                 pp, ys, ydup, p_est, peak, delay);
-        if (valid && j == 0) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
+        ydup[0] = ydup[1] = make_float2(0.f, 0.f);
+        for (int s = 0; s < P.m0; ++s) {
+            float2 v[8];
+            load8<T>(v, x, pos + (long long)s * L, n_samples, j);
+            fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
+            sync_accumulate<LOG2N>(P, v, s, j, ys, ydup, pw);
+        }
+        sync_finish<LOG2N, GROUPS>(P, ys, pw, twr, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+        if (j == 0) {
             peak_out[t] = peak;
             delay_out[t] = delay;
         }
@@ -391,7 +522,7 @@ rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long
 // K3  channel estimate for accepted locks (+ optional time-domain channel and equalised preamble).
 // ------------------------------------------------------------------------------------------------
 template <int LOG2N, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS)
+__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
                   const long long *__restrict__ pos_in, const int *__restrict__ delay_in, long long n_locks, int iters,
                   float2 *__restrict__ H_out, float2 *__restrict__ htime_out, float2 *__restrict__ synch_eq_out) {
@@ -399,55 +530,54 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
     constexpr int N = C::N;
     const int L = N + P.cp;
     for (int it = 0; it < iters; ++it) {
-        const long long i = gg + (long long)it * total_groups;
-        const bool valid = i < n_locks;
-        const long long pos = valid ? pos_in[i] : 0;
-        const int delay = valid ? delay_in[i] : 0;
+        long long i = gg + (long long)it * total_groups;
+        i = i < n_locks - 1 ? i : n_locks - 1;
+        const long long pos = pos_in[i];
+        const int delay = delay_in[i];
         float2 ys[8], ydup[2], H[8], G[8];
-        float p_est, peak;
+        float pw = 0.f, p_est, peak;
         int dfound;
-        sync_core<LOG2N, GROUPS>(P, x, n_samples, pos, valid, twr, b0, b1, redf, redu, j, gid, pp, ys, ydup, p_est,
-                                 peak, dfound);
-        chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq_synch, j, H, G);
-        if (valid) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) H_out[i * N + j + m * T] = H[m];
+        for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
+        ydup[0] = ydup[1] = make_float2(0.f, 0.f);
+        for (int s = 0; s < P.m0; ++s) {
+            float2 v[8];
+            load8<T>(v, x, pos + (long long)s * L, n_samples, j);
+            fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
+            sync_accumulate<LOG2N>(P, v, s, j, ys, ydup, pw);
         }
+        sync_finish<LOG2N, GROUPS>(P, ys, pw, twr, b0, b1, redf, redu, j, gid, pp, p_est, peak, dfound);
+        chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq_synch, j, H, G);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) H_out[i * N + j + m * T] = H[m];
         if (htime_out != nullptr) {                              // ifft(chan_est1): SynchAndChanEst.py:202
             float2 c[8];
 #pragma unroll
             for (int m = 0; m < 8; ++m) c[m] = H[m];
             fft_group<LOG2N, true, GROUPS>(c, twr, b0, b1, j, gid, pp);
-            if (valid) {
 #pragma unroll
-                for (int m = 0; m < 8; ++m) htime_out[i * N + j + m * T] = cscale(c[m], 1.f / (float)N);
-            }
+            for (int m = 0; m < 8; ++m) htime_out[i * N + j + m * T] = cscale(c[m], 1.f / (float)N);
         }
         if (synch_eq_out != nullptr) {                           // eq_gain_ext * data_recov: :213-218
             for (int s = 0; s < P.m0; ++s) {
                 float2 v[8];
-                const long long base = pos + (long long)s * L + j;
-#pragma unroll
-                for (int m = 0; m < 8; ++m)
-                    v[m] = valid ? ldg_sample(x, base + m * T, n_samples) : make_float2(0.f, 0.f);
+                load8<T>(v, x, pos + (long long)s * L, n_samples, j);
                 fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
-                if (valid) {
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const int k = j + m * T;
-                        const int idx = used_index(k, N, P.nsb);
-                        if (idx >= 0) {
-                            // G already carries conj(H)/(|H|^2+1/snr) * rot ; data_recov = rot*p_est*X
-                            const float2 z = cscale(cmul(G[m], v[m]), p_est);
-                            synch_eq_out[i * P.mm + s * P.nsb + idx] = z;
-                            if (k == P.dup_bin) {
-                                // the aliased bin also appears as synch index 0, with the gain of index 0
-                                const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));
-                                const float2 h0 = cscale(cmulc(ydup[0], w), p_est * P.chanest_scale);
-                                const float den = cabs2(h0) + P.inv_reg_eq_synch;
-                                const float2 g0 = cscale(cmulc(make_float2(h0.x, -h0.y), w), den > 0.f ? 1.f / den : 0.f);
-                                synch_eq_out[i * P.mm + s * P.nsb + 0] = cscale(cmul(g0, v[m]), p_est);
-                            }
+                for (int m = 0; m < 8; ++m) {
+                    const int k = j + m * T;
+                    const int idx = used_index(k, N, P.nsb);
+                    if (idx >= 0) {
+                        // G already carries conj(H)/(|H|^2+1/snr) * rot ; data_recov = rot*p_est*X
+                        const float2 z = cscale(cmul(G[m], v[m]), p_est);
+                        synch_eq_out[i * P.mm + s * P.nsb + idx] = z;
+                        if (k == P.dup_bin) {
+                            // the aliased bin also appears as synch index 0, with the gain of index 0
+                            const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));
+                            const float2 h0 = cscale(cmulc(ydup[0], w), p_est * P.chanest_scale);
+                            const float den = cabs2(h0) + P.inv_reg_eq_synch;
+                            const float2 g0 = cscale(cmulc(make_float2(h0.x, -h0.y), w), den > 0.f ? 1.f / den : 0.f);
+                            synch_eq_out[i * P.mm + s * P.nsb + 0] = cscale(cmul(g0, v[m]), p_est);
                         }
                     }
                 }
@@ -460,31 +590,31 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
 // K4  data symbols from an explicit symbol list (used by the stream blocks' work()).
 // ------------------------------------------------------------------------------------------------
 template <int LOG2N, int BPS, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS)
+__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
                 const long long *__restrict__ start_in, const int *__restrict__ delay_in,
                 const int *__restrict__ hrow_in, const float2 *__restrict__ Hmat, long long n_sym, int iters,
                 float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
     OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
     constexpr int N = C::N;
+    const DataCtx<LOG2N, BPS> D(P, j);
     for (int it = 0; it < iters; ++it) {
-        const long long i = gg + (long long)it * total_groups;
-        const bool valid = i < n_sym;
-        const long long start = valid ? start_in[i] : 0;
-        const int delay = valid ? delay_in[i] : 0;
-        const long long hrow = valid ? hrow_in[i] : 0;
+        long long i = gg + (long long)it * total_groups;
+        i = i < n_sym - 1 ? i : n_sym - 1;
+        const int delay = delay_in[i];
+        const long long hrow = hrow_in[i];
         float2 v[8], G[8];
+        load8<T>(v, x, start_in[i], n_samples, j);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int k = j + m * T;
-            v[m] = valid ? ldg_sample(x, start + k, n_samples) : make_float2(0.f, 0.f);
-            const float2 h = valid ? __ldg(Hmat + hrow * N + k) : make_float2(0.f, 0.f);
+            const float2 h = __ldg(Hmat + hrow * N + k);
             const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));
             const float den = cabs2(h) + P.inv_reg_eq;
-            G[m] = cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? 1.f / den : 0.f);
+            G[m] = cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? __fdividef(1.f, den) : 0.f);
         }
         fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
-        data_epilogue<LOG2N, BPS, GROUPS>(P, v, G, i, valid, redf, hb, j, gid, eq_out, llr_out, hard_out);
+        data_epilogue<LOG2N, BPS, GROUPS>(P, D, v, G, i, redf, hb, j, gid, eq_out, llr_out, hard_out);
     }
 }
 
@@ -496,58 +626,59 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
 // (CP samples count twice), so the symbol is written to HBM once, already normalised.
 // ------------------------------------------------------------------------------------------------
 template <int LOG2N, int BPS, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS)
+__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
     OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
     constexpr int N = C::N;
     const int L = N + P.cp, fs = P.m0 + P.d;
+    const BinMap map = make_bin_map<T>(P.ndb, j);
+    // this thread's samples n = j + m*T that also go into the cyclic prefix (n >= N - CP)
+    unsigned cpmask = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) cpmask |= (j + m * T >= N - P.cp) ? (1u << m) : 0u;
+    const float invN = 1.f / (float)N, fL = (float)L;
     for (int it = 0; it < iters; ++it) {
-        const long long si = gg + (long long)it * total_groups;
-        const bool valid = si < n_sym_total;
+        long long si = gg + (long long)it * total_groups;
+        si = si < n_sym_total - 1 ? si : n_sym_total - 1;
         const long long f = si / fs;
         const int s = (int)(si - f * fs);
         float2 v[8];
-        if (!valid) {
+        if (s < P.m0) {
+            const float2 *z = P.zc_tx + s * N + j;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = make_float2(0.f, 0.f);
-        } else if (s < P.m0) {
-#pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = __ldg(P.zc_tx + s * N + j + m * T);
+            for (int m = 0; m < 8; ++m) v[m] = __ldg(z + m * T);
         } else {
             const uint8_t *bp = bits + (f * P.d + (s - P.m0)) * P.hard_stride;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const int jo = used_index(j + m * T, N, P.ndb);
-                v[m] = jo >= 0 ? map_bits<BPS>(read_bits<BPS>(bp, jo * BPS, P.hard_stride)) : make_float2(0.f, 0.f);
+                const int jo = bin_out<T>(map, m);
+                v[m] = (map.mask & (1u << m)) ? map_bits<BPS>(read_bits<BPS>(bp, jo * BPS, P.hard_stride))
+                                              : make_float2(0.f, 0.f);
             }
         }
         fft_group<LOG2N, true, GROUPS>(v, twr, b0, b1, j, gid, pp);
         float3 acc = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const float w = (j + m * T >= N - P.cp) ? 2.f : 1.f;
+            const float w = (cpmask & (1u << m)) ? 2.f : 1.f;
             acc.x = fmaf(w, cabs2(v[m]), acc.x);
             acc.y = fmaf(w, v[m].x, acc.y);
             acc.z = fmaf(w, v[m].y, acc.z);
         }
         acc = group_sum3<T, GROUPS>(acc, redf, j, gid);
         // v holds N * ifft(X).  Reference: t/N -> *sqrt(L/E) -> /sqrt(var)
-        const float invN = 1.f / (float)N;
         const float E = acc.x * invN * invN;
-        const float s1 = E > 1e-30f ? sqrtf((float)L / E) * invN : invN;
-        const float mx = s1 * acc.y / (float)L, my = s1 * acc.z / (float)L;
-        const float var = s1 * s1 * acc.x / (float)L - (mx * mx + my * my);
-        const float g = var > 0.f ? s1 * rsqrtf(var) : 0.f;
-        if (valid) {
-            float2 *o = out + si * L;
+        const float s1 = E > 1e-30f ? sqrtf(fL / E) * invN : invN;
+        const float mx = s1 * acc.y / fL, my = s1 * acc.z / fL;
+        const float var = s1 * s1 * acc.x / fL - (mx * mx + my * my);
+        const float g = var > 0.f ? s1 / sqrtf(var) : 0.f;
+        float2 *o = out + si * L + j;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int n = j + m * T;
-                const float2 z = cscale(v[m], g);
-                o[P.cp + n] = z;
-                if (n >= N - P.cp) o[n - (N - P.cp)] = z;
-            }
+        for (int m = 0; m < 8; ++m) {
+            const float2 z = cscale(v[m], g);
+            __stcs(o + P.cp + m * T, z);
+            if (cpmask & (1u << m)) __stcs(o + (m * T - (N - P.cp)), z);
         }
     }
 }
