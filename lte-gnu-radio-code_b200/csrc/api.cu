@@ -384,6 +384,7 @@ int ofdm_plan_frame_len(const ofdm_plan *pl) {
 }
 
 int ofdm_tx_modulate(ofdm_plan *pl, const uint8_t *d_bits, float *d_time, int64_t n_frames, void *stream) {
+    if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_time || (!d_bits && pl->prm.d > 0) || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_tx_modulate: bad argument%s");
     CU(pl->ks->tx(pl->dev, d_bits, (float2 *)d_time, n_frames * (pl->prm.m0 + pl->prm.d), (cudaStream_t)stream, pl->sms),
        "ofdm_tx_modulate");
@@ -392,6 +393,7 @@ int ofdm_tx_modulate(ofdm_plan *pl, const uint8_t *d_bits, float *d_time, int64_
 
 int ofdm_rx_sync_search(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first_start, int64_t stride,
                         int64_t n_trials, float *d_peak, int32_t *d_delay, void *stream) {
+    if (pl && n_trials == 0) return OFDM_OK;
     if (!pl || !d_time || !d_peak || !d_delay || n_trials < 0 || stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_sync_search: bad argument%s");
     CU(pl->ks->sync_search(pl->dev, (const float2 *)d_time, n_samples, first_start, stride, n_trials, d_peak, d_delay,
                            (cudaStream_t)stream, pl->sms),
@@ -401,6 +403,7 @@ int ofdm_rx_sync_search(ofdm_plan *pl, const float *d_time, int64_t n_samples, i
 
 int ofdm_rx_chanest(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_pos, const int32_t *d_delay,
                     int64_t n_locks, float *d_H, float *d_htime, float *d_synch_eq, void *stream) {
+    if (pl && n_locks == 0) return OFDM_OK;
     if (!pl || !d_time || !d_pos || !d_delay || !d_H || n_locks < 0) return fail(OFDM_EINVAL, "ofdm_rx_chanest: bad argument%s");
     CU(pl->ks->chanest(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_pos, d_delay, n_locks,
                        (float2 *)d_H, (float2 *)d_htime, (float2 *)d_synch_eq, (cudaStream_t)stream, pl->sms),
@@ -411,6 +414,7 @@ int ofdm_rx_chanest(ofdm_plan *pl, const float *d_time, int64_t n_samples, const
 int ofdm_rx_demod(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_start, const int32_t *d_delay,
                   const int32_t *d_hrow, const float *d_H, int64_t n_sym, float *d_eq, float *d_llr, uint8_t *d_hard,
                   void *stream) {
+    if (pl && n_sym == 0) return OFDM_OK;
     if (!pl || !d_time || !d_start || !d_delay || !d_hrow || !d_H || !d_eq || n_sym < 0)
         return fail(OFDM_EINVAL, "ofdm_rx_demod: bad argument%s");
     CU(pl->ks->rx_demod(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_start, d_delay, d_hrow,
@@ -422,6 +426,7 @@ int ofdm_rx_demod(ofdm_plan *pl, const float *d_time, int64_t n_samples, const i
 int ofdm_rx_frames(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first, int64_t frame_stride,
                    int64_t n_frames, int32_t *d_delay, float *d_peak, uint8_t *d_locked, float *d_H, float *d_eq,
                    float *d_llr, uint8_t *d_hard, void *stream) {
+    if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_time || !d_delay || !d_peak || !d_locked || !d_eq || n_frames < 0)
         return fail(OFDM_EINVAL, "ofdm_rx_frames: bad argument%s");
     CU(pl->ks->rx_frames(pl->dev, (const float2 *)d_time, n_samples, first, frame_stride, n_frames, d_delay, d_peak,
@@ -432,6 +437,7 @@ int ofdm_rx_frames(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_
 
 int ofdm_bit_recovery(ofdm_plan *pl, const float *d_in, int64_t n, float *d_llr0, float *d_llr1, uint8_t *d_hard,
                       double *d_ws, void *stream) {
+    if (pl && n == 0) return OFDM_OK;
     if (!pl || !d_in || !d_llr0 || !d_llr1 || !d_hard || !d_ws || n < 0) return fail(OFDM_EINVAL, "ofdm_bit_recovery: bad argument%s");
     if (n == 0) return OFDM_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -449,6 +455,7 @@ int ofdm_bit_recovery(ofdm_plan *pl, const float *d_in, int64_t n, float *d_llr0
 
 int ofdm_counters(ofdm_plan *pl, const uint8_t *d_bits_rx, const uint8_t *d_bits_tx, const float *d_eq,
                   const uint8_t *d_locked, int64_t n_frames, double *d_cnt, void *stream) {
+    if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_bits_tx || !d_cnt || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_counters: bad argument%s");
     if (n_frames == 0) return OFDM_OK;
     long long blocks = (n_frames * pl->prm.d + 7) / 8;
@@ -464,6 +471,7 @@ int ofdm_counters(ofdm_plan *pl, const uint8_t *d_bits_rx, const uint8_t *d_bits
 
 int ofdm_channel_awgn(ofdm_plan *pl, const float *d_tx, float *d_rx, int64_t n_frames, const float *d_taps,
                       int32_t n_taps, int32_t taps_per_frame, float noise_sigma, uint64_t seed, void *stream) {
+    if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_tx || !d_rx || !d_taps || n_taps < 1 || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_channel_awgn: bad argument%s");
     if (n_frames == 0) return OFDM_OK;
     const int fl = ofdm_plan_frame_len(pl);
@@ -504,6 +512,7 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, int64_t first, int64_t frame_stride,
                         int64_t n_frames, int32_t *h_delay, float *h_peak, uint8_t *h_locked, float *h_eq, float *h_llr,
                         uint8_t *h_hard) {
+    if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !h_time || !h_eq || n_frames < 0 || frame_stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_frames_host: bad argument%s");
     if (n_frames == 0) return OFDM_OK;
     int rc = ensure_streams(pl);
@@ -558,6 +567,7 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
 }
 
 int ofdm_tx_modulate_host(ofdm_plan *pl, const uint8_t *h_bits, float *h_time, int64_t n_frames) {
+    if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !h_time || (!h_bits && pl->prm.d > 0) || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_tx_modulate_host: bad argument%s");
     if (n_frames == 0) return OFDM_OK;
     int rc = ensure_streams(pl);

