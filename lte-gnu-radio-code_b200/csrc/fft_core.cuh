@@ -8,8 +8,8 @@
 //   * before each pass and after the last one, thread j holds element  j + m*T  in v[m], m=0..7.
 //     Inputs can therefore be loaded straight from HBM with warp-contiguous 8-byte accesses and
 //     the output bins come out warp-contiguous too -- no staging pass on either side;
-//   * pass twiddles depend only on (j, pass) and are hoisted into registers once per thread
-//     (persistent kernels re-use them for every symbol);
+//   * pass twiddles live in a per-CTA shared-memory table laid out [pass][q][j mod Ns], so lanes
+//     read consecutive (or broadcast) entries and no registers are pinned between symbols;
 //   * the exchange layouts are chosen per pass so that both the scattered write and the
 //     contiguous read are shared-memory bank-conflict free for 8-byte accesses.
 //
@@ -37,6 +37,16 @@ template <bool INV> __device__ __forceinline__ float2 mul_mi(float2 a) {
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 
+// pass structure: N8 radix-8 passes, then one radix-4 (LOG2N%3==2) or radix-2 (LOG2N%3==1) pass
+__host__ __device__ constexpr int fft_radix(int log2n, int p) { return p < log2n / 3 ? 8 : (1 << (log2n % 3)); }
+__host__ __device__ constexpr int fft_ns(int log2n, int p) { return 1 << (3 * (p < log2n / 3 ? p : log2n / 3)); }
+// shared twiddle table: pass p >= 1 holds (R-1) rows of Ns entries, row q-1 entry r = W_N^(q*r*N/(Ns*R))
+__host__ __device__ constexpr int fft_tw_off(int log2n, int p) {
+    int o = 0;
+    for (int i = 1; i < p; ++i) o += (fft_radix(log2n, i) - 1) * fft_ns(log2n, i);
+    return o;
+}
+
 template <int LOG2N> struct FftCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int T = N / 8;                       // threads per symbol group
@@ -44,12 +54,12 @@ template <int LOG2N> struct FftCfg {
     static constexpr int REM = LOG2N % 3;                 // 0: none, 1: radix-2, 2: radix-4 last pass
     static constexpr int NPASS = N8 + (REM ? 1 : 0);
     static constexpr int NEXCH = NPASS - 1;               // shared-memory exchanges per transform
-    // twiddle registers (complex) per thread: 7 per twiddled radix-8 pass, 6 (radix-4) / 4 (radix-2)
-    static constexpr int NTW = 7 * (N8 - 1) + (REM == 2 ? 6 : (REM == 1 ? 4 : 0));
+    static constexpr int TW_ENTRIES = fft_tw_off(LOG2N, NPASS);
     // padded buffer length in complex slots; N == 64 uses a pad-per-8 layout (see lay())
     static constexpr int BUF = (LOG2N == 6) ? 72 : N;
-    __host__ __device__ static constexpr int radix(int p) { return p < N8 ? 8 : (1 << REM); }
-    __host__ __device__ static constexpr int ns(int p) { return 1 << (3 * (p < N8 ? p : N8)); }
+    __host__ __device__ static constexpr int radix(int p) { return fft_radix(LOG2N, p); }
+    __host__ __device__ static constexpr int ns(int p) { return fft_ns(LOG2N, p); }
+    __host__ __device__ static constexpr int tw_off(int p) { return fft_tw_off(LOG2N, p); }
 };
 
 // Exchange layout for the buffer written by pass P (Ns = 8^P):
@@ -117,32 +127,17 @@ template <int T, int GROUPS> __device__ __forceinline__ void group_sync(int gid)
     }
 }
 
-// Load this thread's pass twiddles from the global table tw[k] = exp(-2*pi*i*k/N).
-// Layout of twr[]: passes 1..NPASS-1 in order; radix-8: q=1..7; radix-4: b=0,1 x q=1..3; radix-2: b=0..3.
-template <int LOG2N> __device__ __forceinline__ void load_twiddles(float2 *twr, const float2 *__restrict__ tw, int j) {
+// Fill the CTA's shared twiddle table from the global table tw[k] = exp(-2*pi*i*k/N).
+template <int LOG2N>
+__device__ __forceinline__ void fill_twiddles(float2 *tws, const float2 *__restrict__ tw, int tid, int nthreads) {
     using C = FftCfg<LOG2N>;
-    int o = 0;
 #pragma unroll
     for (int p = 1; p < C::NPASS; ++p) {
-        const int R = C::radix(p), Ns = C::ns(p);
+        const int R = C::radix(p), Ns = C::ns(p), off = C::tw_off(p);
         const int step = C::N / (Ns * R);
-        if (R == 8) {
-            const int r = j & (Ns - 1);
-#pragma unroll
-            for (int q = 1; q < 8; ++q) twr[o++] = __ldg(&tw[q * r * step]);
-        } else if (R == 4) {
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int r = (j + b * C::T) & (Ns - 1);
-#pragma unroll
-                for (int q = 1; q < 4; ++q) twr[o++] = __ldg(&tw[q * r * step]);
-            }
-        } else {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int r = (j + b * C::T) & (Ns - 1);
-                twr[o++] = __ldg(&tw[r * step]);
-            }
+        for (int i = tid; i < (R - 1) * Ns; i += nthreads) {
+            const int q = i / Ns + 1, r = i & (Ns - 1);
+            tws[off + i] = __ldg(&tw[(q * r * step) & (C::N - 1)]);
         }
     }
 }
@@ -154,23 +149,25 @@ template <bool INV> __device__ __forceinline__ float2 twmul(float2 a, float2 w) 
 // One pass P of the transform, fully unrolled by the caller through template recursion.
 template <int LOG2N, bool INV, int GROUPS, int P> struct Pass {
     using C = FftCfg<LOG2N>;
-    static __device__ __forceinline__ void run(float2 (&v)[8], const float2 *twr, float2 *buf0, float2 *buf1,
+    static __device__ __forceinline__ void run(float2 (&v)[8], const float2 *tws, float2 *buf0, float2 *buf1,
                                                int j, int gid, int &pp) {
         constexpr int R = C::radix(P), Ns = C::ns(P);
-        // twiddle offset of this pass inside twr[]
-        constexpr int off = (P == 0) ? 0 : 7 * (P - 1);
         if (P > 0) {
+            constexpr int off = C::tw_off(P);
             if (R == 8) {
+                const float2 *t = tws + off + (j & (Ns - 1));
 #pragma unroll
-                for (int q = 1; q < 8; ++q) v[q] = twmul<INV>(v[q], twr[off + q - 1]);
+                for (int q = 1; q < 8; ++q) v[q] = twmul<INV>(v[q], t[(q - 1) * Ns]);
             } else if (R == 4) {
 #pragma unroll
-                for (int b = 0; b < 2; ++b)
+                for (int b = 0; b < 2; ++b) {
+                    const float2 *t = tws + off + ((j + b * C::T) & (Ns - 1));
 #pragma unroll
-                    for (int q = 1; q < 4; ++q) v[b + 2 * q] = twmul<INV>(v[b + 2 * q], twr[off + b * 3 + q - 1]);
+                    for (int q = 1; q < 4; ++q) v[b + 2 * q] = twmul<INV>(v[b + 2 * q], t[(q - 1) * Ns]);
+                }
             } else {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) v[b + 4] = twmul<INV>(v[b + 4], twr[off + b]);
+                for (int b = 0; b < 4; ++b) v[b + 4] = twmul<INV>(v[b + 4], tws[off + ((j + b * C::T) & (Ns - 1))]);
             }
         }
         if (R == 8) {
@@ -192,7 +189,7 @@ template <int LOG2N, bool INV, int GROUPS, int P> struct Pass {
             group_sync<C::T, GROUPS>(gid);
 #pragma unroll
             for (int m = 0; m < 8; ++m) v[m] = buf[lay<LOG2N, P>(j + m * C::T)];
-            Pass<LOG2N, INV, GROUPS, P + 1>::run(v, twr, buf0, buf1, j, gid, pp);
+            Pass<LOG2N, INV, GROUPS, P + 1>::run(v, tws, buf0, buf1, j, gid, pp);
         }
     }
 };
@@ -203,9 +200,9 @@ template <int LOG2N, bool INV, int GROUPS> struct Pass<LOG2N, INV, GROUPS, 4> {
 // In-place transform of the group's symbol.  pp is the running ping-pong selector (kept across
 // calls so that consecutive transforms never need a second barrier per exchange).
 template <int LOG2N, bool INV, int GROUPS>
-__device__ __forceinline__ void fft_group(float2 (&v)[8], const float2 *twr, float2 *buf0, float2 *buf1, int j,
+__device__ __forceinline__ void fft_group(float2 (&v)[8], const float2 *tws, float2 *buf0, float2 *buf1, int j,
                                           int gid, int &pp) {
-    Pass<LOG2N, INV, GROUPS, 0>::run(v, twr, buf0, buf1, j, gid, pp);
+    Pass<LOG2N, INV, GROUPS, 0>::run(v, tws, buf0, buf1, j, gid, pp);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -11,8 +11,9 @@
 //     and every store is `base + compile-time offset`;
 //   * groups past the end of the work list redo the last item (identical duplicate writes) instead
 //     of carrying a `valid` predicate through every load and store;
-//   * the next symbol's samples are requested (registers) before the current one is transformed,
-//     so DRAM latency overlaps the arithmetic instead of stalling it.
+//   * the next symbol's samples are requested with cp.async into per-thread shared-memory slots
+//     before the current one is transformed, so DRAM latency overlaps the arithmetic without
+//     holding registers.
 #pragma once
 #include "fft_core.cuh"
 
@@ -236,21 +237,62 @@ __device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict
 // shared-memory carve-up per CTA
 template <int LOG2N, int GROUPS> struct Smem {
     using C = FftCfg<LOG2N>;
+    static constexpr int THREADS = C::T * GROUPS;
     static constexpr int GSTRIDE = (LOG2N == 6) ? (2 * C::BUF + 8) : 2 * C::BUF;   // complex slots per group
     static constexpr int FFT_BYTES = GROUPS * GSTRIDE * 8;
+    static constexpr int TW_BYTES = C::TW_ENTRIES * 8;                              // pass twiddles, shared by the CTA
+    static constexpr int STAGE_BYTES = THREADS * 8 * 8;                             // next symbol: 8 samples per thread
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
     static constexpr int HB_STRIDE = C::N + 8;                                      // +8: zero pad, staggers banks
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
-    static constexpr int BYTES = FFT_BYTES + RED_BYTES + HB_BYTES;
+    static constexpr int OFF_TW = FFT_BYTES;
+    static constexpr int OFF_STAGE = OFF_TW + TW_BYTES;
+    static constexpr int OFF_RED = OFF_STAGE + STAGE_BYTES;
+    static constexpr int OFF_HB = OFF_RED + RED_BYTES;
+    static constexpr int BYTES = OFF_HB + HB_BYTES;
     __device__ static float2 *buf0(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s) + gid * GSTRIDE; }
-    __device__ static float *redf(unsigned char *s, int gid) {
-        return reinterpret_cast<float *>(s + FFT_BYTES + GROUPS * 16 * 8) + gid * 64;
-    }
+    __device__ static float2 *tws(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_TW); }
+    // slot m of thread t: stage[m * THREADS + t] -> lanes hit consecutive 8-byte words
+    __device__ static float2 *stage(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_STAGE); }
     __device__ static unsigned long long *redu(unsigned char *s, int gid) {
-        return reinterpret_cast<unsigned long long *>(s + FFT_BYTES) + gid * 16;
+        return reinterpret_cast<unsigned long long *>(s + OFF_RED) + gid * 16;
     }
-    __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + FFT_BYTES + RED_BYTES + gid * HB_STRIDE; }
+    __device__ static float *redf(unsigned char *s, int gid) {
+        return reinterpret_cast<float *>(s + OFF_RED + GROUPS * 16 * 8) + gid * 64;
+    }
+    __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + OFF_HB + gid * HB_STRIDE; }
 };
+
+// Asynchronous prefetch of this thread's 8 samples of the window that opens at `start` into its
+// private shared-memory slots (LDGSTS, no registers held while the data is in flight).  Samples
+// outside [0, n) are zero-filled by the hardware (src-size 0).  The thread that issued the copies
+// is the only one that reads them back, so cp.async.wait_group is the only synchronisation needed.
+template <int T, int THREADS>
+__device__ __forceinline__ void prefetch8(float2 *stage, const float2 *__restrict__ x, long long start, long long n,
+                                          int j, int tid) {
+    constexpr int N = 8 * T;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + tid);
+    if (start >= 0 && start + N <= n) {
+        const float2 *p = x + start + j;
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + m * THREADS * 8), "l"(p + m * T) : "memory");
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const long long i = start + j + m * T;
+            const bool ok = (i >= 0 && i < n);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + m * THREADS * 8),
+                         "l"(x + (ok ? i : 0)), "r"(ok ? 8 : 0) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int THREADS> __device__ __forceinline__ void take8(float2 (&v)[8], const float2 *stage, int tid) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = stage[m * THREADS + tid];
+}
 
 // ------------------------------------------------------------------------------------------------
 // Preamble handling, split in two so the framed kernel can prefetch between the pieces.
@@ -285,7 +327,7 @@ __device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2
 }
 
 template <int LOG2N, int GROUPS>
-__device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&ys)[8], float pw, const float2 *twr,
+__device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&ys)[8], float pw, const float2 *tws,
                                             float2 *b0, float2 *b1, float *redf, unsigned long long *redu, int j,
                                             int gid, int &pp, float &p_est, float &peak, int &delay) {
     using C = FftCfg<LOG2N>;
@@ -295,7 +337,7 @@ __device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&y
     float2 c[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) c[m] = ys[m];
-    fft_group<LOG2N, true, GROUPS>(c, twr, b0, b1, j, gid, pp);
+    fft_group<LOG2N, true, GROUPS>(c, tws, b0, b1, j, gid, pp);
     unsigned long long key = 0ull;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -401,22 +443,38 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     using S = Smem<LOG2N, GROUPS>;                                                     \
     constexpr int T = C::T;                                                            \
     extern __shared__ __align__(16) unsigned char smem_raw[];                          \
-    const int gid = threadIdx.x / T, j = threadIdx.x % T;                              \
+    const int tid = threadIdx.x, gid = tid / T, j = tid % T;                           \
     float2 *b0 = S::buf0(smem_raw, gid), *b1 = b0 + C::BUF;                            \
+    const float2 *tws = S::tws(smem_raw);                                              \
+    float2 *stage = S::stage(smem_raw);                                                \
     float *redf = S::redf(smem_raw, gid);                                              \
     unsigned long long *redu = S::redu(smem_raw, gid);                                 \
     uint8_t *hb = S::hb(smem_raw, gid);                                                \
-    (void)redu; (void)redf;                                                            \
+    (void)redu; (void)redf; (void)stage;                                               \
     for (int i = j; i < S::HB_STRIDE; i += T) hb[i] = 0;                               \
-    float2 twr[C::NTW > 0 ? C::NTW : 1];                                               \
-    load_twiddles<LOG2N>(twr, P.tw, j);                                                \
+    fill_twiddles<LOG2N>(S::tws(smem_raw), P.tw, tid, S::THREADS);                     \
+    __syncthreads();                                                                   \
     const long long total_groups = (long long)gridDim.x * GROUPS;                      \
     const long long gg = (long long)blockIdx.x * GROUPS + gid;                         \
     int pp = 0;
 
+// resident CTAs per SM the register allocator should aim for (threads per CTA = max(T,128));
+// overridable at build time for tuning sweeps:  make EXTRA="-DOFDM_MINB_SMALL=6 -DOFDM_MINB_2048=3"
+#ifndef OFDM_MINB_SMALL
+#define OFDM_MINB_SMALL 4
+#endif
+#ifndef OFDM_MINB_1024
+#define OFDM_MINB_1024 4
+#endif
+#ifndef OFDM_MINB_2048
+#define OFDM_MINB_2048 2
+#endif
+#ifndef OFDM_MINB_4096
+#define OFDM_MINB_4096 1
+#endif
 template <int LOG2N> struct MinBlocks {
-    // resident CTAs per SM the register allocator should aim for (threads per CTA = max(T,128))
-    static constexpr int value = LOG2N <= 9 ? 4 : (LOG2N == 10 ? 4 : (LOG2N == 11 ? 2 : 1));
+    static constexpr int value =
+        LOG2N <= 9 ? OFDM_MINB_SMALL : (LOG2N == 10 ? OFDM_MINB_1024 : (LOG2N == 11 ? OFDM_MINB_2048 : OFDM_MINB_4096));
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -438,8 +496,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
     const long long off0 = first + P.cp - P.sync_advance;
     long long f = gg < last_frame ? gg : last_frame;
     long long pos = off0 + f * frame_stride;
-    float2 cur[8], nxt[8];
-    load8<T>(cur, x, pos, n_samples, j);
+    prefetch8<T, S::THREADS>(stage, x, pos, n_samples, j, tid);
     for (int it = 0; it < iters; ++it) {
         long long fn = gg + (long long)(it + 1) * total_groups;
         fn = fn < last_frame ? fn : last_frame;
@@ -450,16 +507,18 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
         for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
         ydup[0] = ydup[1] = make_float2(0.f, 0.f);
         for (int s = 0; s < fs; ++s) {
-            const long long nstart = (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos;
-            load8<T>(nxt, x, nstart, n_samples, j);          // (the very last prefetch re-reads a valid window)
-            fft_group<LOG2N, false, GROUPS>(cur, twr, b0, b1, j, gid, pp);
+            float2 cur[8];
+            take8<S::THREADS>(cur, stage, tid);
+            // request the next symbol (the last request of the kernel re-reads a valid window)
+            prefetch8<T, S::THREADS>(stage, x, (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos, n_samples, j, tid);
+            fft_group<LOG2N, false, GROUPS>(cur, tws, b0, b1, j, gid, pp);
             if (s < P.m0) {
                 sync_accumulate<LOG2N>(P, cur, s, j, ys, ydup, pw);
                 if (s == P.m0 - 1) {
                     float p_est, peak;
                     int delay;
                     float2 H[8];
-                    sync_finish<LOG2N, GROUPS>(P, ys, pw, twr, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+                    sync_finish<LOG2N, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
                     chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq, j, H, G);
                     if (j == 0) {
                         delay_out[f] = delay;
@@ -475,12 +534,11 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                 data_epilogue<LOG2N, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, j, gid, eq_out, llr_out,
                                                   hard_out);
             }
-#pragma unroll
-            for (int m = 0; m < 8; ++m) cur[m] = nxt[m];
         }
         f = fn;
         pos = npos;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -507,10 +565,10 @@ rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long
         for (int s = 0; s < P.m0; ++s) {
             float2 v[8];
             load8<T>(v, x, pos + (long long)s * L, n_samples, j);
-            fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
+            fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
             sync_accumulate<LOG2N>(P, v, s, j, ys, ydup, pw);
         }
-        sync_finish<LOG2N, GROUPS>(P, ys, pw, twr, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+        sync_finish<LOG2N, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
         if (j == 0) {
             peak_out[t] = peak;
             delay_out[t] = delay;
@@ -543,10 +601,10 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
         for (int s = 0; s < P.m0; ++s) {
             float2 v[8];
             load8<T>(v, x, pos + (long long)s * L, n_samples, j);
-            fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
+            fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
             sync_accumulate<LOG2N>(P, v, s, j, ys, ydup, pw);
         }
-        sync_finish<LOG2N, GROUPS>(P, ys, pw, twr, b0, b1, redf, redu, j, gid, pp, p_est, peak, dfound);
+        sync_finish<LOG2N, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, dfound);
         chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq_synch, j, H, G);
 #pragma unroll
         for (int m = 0; m < 8; ++m) H_out[i * N + j + m * T] = H[m];
@@ -554,7 +612,7 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
             float2 c[8];
 #pragma unroll
             for (int m = 0; m < 8; ++m) c[m] = H[m];
-            fft_group<LOG2N, true, GROUPS>(c, twr, b0, b1, j, gid, pp);
+            fft_group<LOG2N, true, GROUPS>(c, tws, b0, b1, j, gid, pp);
 #pragma unroll
             for (int m = 0; m < 8; ++m) htime_out[i * N + j + m * T] = cscale(c[m], 1.f / (float)N);
         }
@@ -562,7 +620,7 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
             for (int s = 0; s < P.m0; ++s) {
                 float2 v[8];
                 load8<T>(v, x, pos + (long long)s * L, n_samples, j);
-                fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
+                fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     const int k = j + m * T;
@@ -613,7 +671,7 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
             const float den = cabs2(h) + P.inv_reg_eq;
             G[m] = cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? __fdividef(1.f, den) : 0.f);
         }
-        fft_group<LOG2N, false, GROUPS>(v, twr, b0, b1, j, gid, pp);
+        fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
         data_epilogue<LOG2N, BPS, GROUPS>(P, D, v, G, i, redf, hb, j, gid, eq_out, llr_out, hard_out);
     }
 }
@@ -625,39 +683,96 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
 // Both normalisations are scale factors derived from two sums over the L = N+CP output samples
 // (CP samples count twice), so the symbol is written to HBM once, already normalised.
 // ------------------------------------------------------------------------------------------------
+// aligned 32-bit word `w` of the byte string that starts at p (p 4-byte aligned); bytes at or past
+// `limit` (relative to p) read as zero so nothing outside the caller's buffer is touched
+__device__ __forceinline__ unsigned ld_word_guarded(const uint8_t *__restrict__ p, long long off, long long limit) {
+    if (off + 4 <= limit) return __ldg(reinterpret_cast<const unsigned *>(p + off));
+    unsigned w = 0;
+    for (int i = 0; i < 4; ++i)
+        if (off + i < limit) w |= (unsigned)__ldg(p + off + i) << (8 * i);
+    return w;
+}
+
 template <int LOG2N, int BPS, int GROUPS>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
     OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
     constexpr int N = C::N;
+    constexpr int WPT = 2;                                   // ceil(ceil(N*6/8/4 + 1) / T) <= 2 packed words per thread
     const int L = N + P.cp, fs = P.m0 + P.d;
     const BinMap map = make_bin_map<T>(P.ndb, j);
     // this thread's samples n = j + m*T that also go into the cyclic prefix (n >= N - CP)
     unsigned cpmask = 0;
 #pragma unroll
     for (int m = 0; m < 8; ++m) cpmask |= (j + m * T >= N - P.cp) ? (1u << m) : 0u;
-    const float invN = 1.f / (float)N, fL = (float)L;
-    for (int it = 0; it < iters; ++it) {
-        long long si = gg + (long long)it * total_groups;
-        si = si < n_sym_total - 1 ? si : n_sym_total - 1;
-        const long long f = si / fs;
-        const int s = (int)(si - f * fs);
-        float2 v[8];
-        if (s < P.m0) {
-            const float2 *z = P.zc_tx + s * N + j;
+    const float sqrtL = sqrtf((float)L), invL = 1.f / (float)L;
+    const float emin = 1e-30f * (float)N * (float)N;
+    // the payload buffer, viewed from its 4-byte-aligned base
+    const long long mis = (long long)(reinterpret_cast<unsigned long long>(bits) & 3ull);
+    const uint8_t *abits = bits - mis;
+    const long long limit = mis + (n_sym_total / fs) * P.d * (long long)P.hard_stride;
+    const int nwords = (P.hard_stride + 3 + 3) / 4;          // words that can hold a row at any byte phase
+    // (frame, symbol-in-frame) of the group's work item, advanced without 64-bit divisions
+    const long long step_f = total_groups / fs;
+    const int step_s = (int)(total_groups - step_f * fs);
+    long long f = gg / fs;
+    int s = (int)(gg - f * fs);
+    const long long last = n_sym_total - 1, last_f = last / fs;
+    const int last_s = (int)(last - last_f * fs);
+    auto row_start = [&](long long ff, int ss) -> long long {   // byte offset of the symbol's payload row, or -1
+        return ss >= P.m0 ? mis + (ff * P.d + (ss - P.m0)) * (long long)P.hard_stride : -1;
+    };
+    auto clampfs = [&](long long &ff, int &ss) {
+        if (ff > last_f || (ff == last_f && ss > last_s)) { ff = last_f; ss = last_s; }
+    };
+    clampfs(f, s);
+    unsigned wcur[WPT], wnxt[WPT];
+    {
+        const long long r = row_start(f, s);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = __ldg(z + m * T);
-        } else {
-            const uint8_t *bp = bits + (f * P.d + (s - P.m0)) * P.hard_stride;
+        for (int i = 0; i < WPT; ++i)
+            wcur[i] = (r >= 0 && j + i * T < nwords) ? ld_word_guarded(abits, (r & ~3ll) + 4 * (j + i * T), limit) : 0u;
+    }
+    for (int it = 0; it < iters; ++it) {
+        // next work item and its payload words (in flight while this symbol is built)
+        long long fn = f + step_f;
+        int sn = s + step_s;
+        if (sn >= fs) { sn -= fs; ++fn; }
+        clampfs(fn, sn);
+        {
+            const long long r = row_start(fn, sn);
+#pragma unroll
+            for (int i = 0; i < WPT; ++i)
+                wnxt[i] = (r >= 0 && j + i * T < nwords) ? ld_word_guarded(abits, (r & ~3ll) + 4 * (j + i * T), limit) : 0u;
+        }
+        float2 v[8];
+        {
+            // Stage the row's packed words, then every thread picks the bits of its own bins.  Groups that
+            // share a warp can be on different symbol types, so the barrier is executed unconditionally
+            // and synch symbols simply overwrite the (all-zero) result with their Zadoff-Chu bins.
+            unsigned *hw = reinterpret_cast<unsigned *>(hb);
+#pragma unroll
+            for (int i = 0; i < WPT; ++i)
+                if (j + i * T < nwords) hw[j + i * T] = wcur[i];
+            group_sync<T, GROUPS>(gid);
+            const int phase = (int)(row_start(f, s) & 3);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const int jo = bin_out<T>(map, m);
-                v[m] = (map.mask & (1u << m)) ? map_bits<BPS>(read_bits<BPS>(bp, jo * BPS, P.hard_stride))
-                                              : make_float2(0.f, 0.f);
+                const int bo = (map.mask & (1u << m)) ? bin_out<T>(map, m) * BPS : 0;
+                const int by = phase + (bo >> 3), sh = bo & 7;
+                unsigned w = (unsigned)hb[by] << 8;
+                if (BPS == 6) w |= (unsigned)hb[by + 1];
+                const unsigned val = (w >> (16 - sh - BPS)) & ((1u << BPS) - 1u);
+                v[m] = (map.mask & (1u << m)) ? map_bits<BPS>(val) : make_float2(0.f, 0.f);
+            }
+            if (s < P.m0) {
+                const float2 *z = P.zc_tx + s * N + j;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = __ldg(z + m * T);
             }
         }
-        fft_group<LOG2N, true, GROUPS>(v, twr, b0, b1, j, gid, pp);
+        fft_group<LOG2N, true, GROUPS>(v, tws, b0, b1, j, gid, pp);
         float3 acc = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
@@ -667,19 +782,24 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             acc.z = fmaf(w, v[m].y, acc.z);
         }
         acc = group_sum3<T, GROUPS>(acc, redf, j, gid);
-        // v holds N * ifft(X).  Reference: t/N -> *sqrt(L/E) -> /sqrt(var)
-        const float E = acc.x * invN * invN;
-        const float s1 = E > 1e-30f ? sqrtf(fL / E) * invN : invN;
-        const float mx = s1 * acc.y / fL, my = s1 * acc.z / fL;
-        const float var = s1 * s1 * acc.x / fL - (mx * mx + my * my);
-        const float g = var > 0.f ? s1 / sqrtf(var) : 0.f;
-        float2 *o = out + si * L + j;
+        // v holds N*ifft(X) = N*t.  Reference: t -> t*sqrt(L/sum|t|^2) -> /sqrt(var); with the first
+        // factor applied the mean power is 1, so var = 1 - |mean|^2 and both steps are one scale g.
+        const float s1 = acc.x > emin ? sqrtL * rsqrtf(acc.x) : 1.f / (float)N;
+        const float mx = s1 * acc.y * invL, my = s1 * acc.z * invL;
+        const float var = s1 * s1 * acc.x * invL - (mx * mx + my * my);
+        const float g = var > 0.f ? s1 * rsqrtf(var) : 0.f;
+        float2 *o = out + (f * fs + s) * L + P.cp + j;
+        float2 *ocp = o - N;                                  // sample n >= N-CP is also output n - (N-CP)
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const float2 z = cscale(v[m], g);
-            __stcs(o + P.cp + m * T, z);
-            if (cpmask & (1u << m)) __stcs(o + (m * T - (N - P.cp)), z);
+            __stcs(o + m * T, z);
+            if (cpmask & (1u << m)) __stcs(ocp + m * T, z);
         }
+        f = fn;
+        s = sn;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) wcur[i] = wnxt[i];
     }
 }
 
