@@ -204,18 +204,39 @@ template <int BPS> __device__ __forceinline__ unsigned read_bits(const uint8_t *
 }
 
 // Pack the per-bin values staged in hb[] (one byte per data bin, zero-padded past ndb) into
-// MSB-first bytes with word-wide shared-memory reads; thread i produces bytes i, i+T, ...
+// MSB-first bytes.  16-QAM / QPSK rows are built four output bytes at a time from one wide
+// shared-memory read and stored with the widest store the row's alignment allows (a 30-byte row is
+// 7 words + 2 bytes instead of 30 single-byte stores); thread i produces chunks i, i+T, ...
+__device__ __forceinline__ void store_chunk(uint8_t *__restrict__ p, unsigned word, int rem) {
+    const unsigned al = (unsigned)(reinterpret_cast<unsigned long long>(p) & 3ull);
+    if (al == 0 && rem >= 4) {
+        *reinterpret_cast<unsigned *>(p) = word;
+    } else if ((al & 1u) == 0) {
+        if (rem >= 2) *reinterpret_cast<uint16_t *>(p) = (uint16_t)word; else p[0] = (uint8_t)word;
+        if (rem >= 4) *reinterpret_cast<uint16_t *>(p + 2) = (uint16_t)(word >> 16);
+        else if (rem == 3) p[2] = (uint8_t)(word >> 16);
+    } else {
+        for (int i = 0; i < 4 && i < rem; ++i) p[i] = (uint8_t)(word >> (8 * i));
+    }
+}
+
 template <int BPS, int T>
 __device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict__ out, int nbytes, int j) {
     if (BPS == 4) {
-        for (int b = j; b < nbytes; b += T) {
-            const unsigned w = *reinterpret_cast<const uint16_t *>(hb + 2 * b);
-            out[b] = (uint8_t)(((w & 15u) << 4) | (w >> 8));
+        const int nchunks = (nbytes + 3) >> 2;
+        for (int c = j; c < nchunks; c += T) {
+            const uint2 w = *reinterpret_cast<const uint2 *>(hb + 8 * c);          // 8 bins, one nibble each
+            const unsigned ux = (w.x << 4) | (w.x >> 8), uy = (w.y << 4) | (w.y >> 8);
+            store_chunk(out + 4 * c, __byte_perm(ux, uy, 0x6420), nbytes - 4 * c);
         }
     } else if (BPS == 2) {
-        for (int b = j; b < nbytes; b += T) {
-            const unsigned w = *reinterpret_cast<const uint32_t *>(hb + 4 * b);
-            out[b] = (uint8_t)(((w & 3u) << 6) | ((w >> 4) & 0x30u) | ((w >> 14) & 0x0cu) | (w >> 24));
+        const int nchunks = (nbytes + 3) >> 2;
+        for (int c = j; c < nchunks; c += T) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(hb + 16 * c);         // 16 bins, two bits each
+            // (n0 | n1<<8 | n2<<16 | n3<<24) * 0x40100401 has n0<<6|n1<<4|n2<<2|n3 in its top byte
+            const unsigned word = ((w.x * 0x40100401u) >> 24) | (((w.y * 0x40100401u) >> 24) << 8) |
+                                  (((w.z * 0x40100401u) >> 24) << 16) | ((w.w * 0x40100401u) & 0xff000000u);
+            store_chunk(out + 4 * c, word, nbytes - 4 * c);
         }
     } else if (BPS == 1) {
         for (int b = j; b < nbytes; b += T) {
@@ -243,13 +264,15 @@ template <int LOG2N, int GROUPS> struct Smem {
     static constexpr int TW_BYTES = C::TW_ENTRIES * 8;                              // pass twiddles, shared by the CTA
     static constexpr int STAGE_BYTES = THREADS * 8 * 8;                             // next symbol: 8 samples per thread
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
-    static constexpr int HB_STRIDE = C::N + 8;                                      // +8: zero pad, staggers banks
+    static constexpr int HB_STRIDE = C::N + 16;                                     // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
+    static constexpr int LUT_BYTES = 72 * 8;                                        // constellation table (TX), entry 64 = 0
     static constexpr int OFF_TW = FFT_BYTES;
     static constexpr int OFF_STAGE = OFF_TW + TW_BYTES;
     static constexpr int OFF_RED = OFF_STAGE + STAGE_BYTES;
     static constexpr int OFF_HB = OFF_RED + RED_BYTES;
-    static constexpr int BYTES = OFF_HB + HB_BYTES;
+    static constexpr int OFF_LUT = OFF_HB + ((HB_BYTES + 7) & ~7);
+    static constexpr int BYTES = OFF_LUT + LUT_BYTES;
     __device__ static float2 *buf0(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s) + gid * GSTRIDE; }
     __device__ static float2 *tws(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_TW); }
     // slot m of thread t: stage[m * THREADS + t] -> lanes hit consecutive 8-byte words
@@ -261,6 +284,7 @@ template <int LOG2N, int GROUPS> struct Smem {
         return reinterpret_cast<float *>(s + OFF_RED + GROUPS * 16 * 8) + gid * 64;
     }
     __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + OFF_HB + gid * HB_STRIDE; }
+    __device__ static float2 *lut(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_LUT); }
 };
 
 // Asynchronous prefetch of this thread's 8 samples of the window that opens at `start` into its
@@ -472,6 +496,22 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
 #ifndef OFDM_MINB_4096
 #define OFDM_MINB_4096 1
 #endif
+#ifndef OFDM_MINB_TX_SMALL
+#define OFDM_MINB_TX_SMALL 4
+#endif
+#ifndef OFDM_MINB_TX_1024
+#define OFDM_MINB_TX_1024 4
+#endif
+#ifndef OFDM_MINB_TX_2048
+#define OFDM_MINB_TX_2048 2
+#endif
+#ifndef OFDM_MINB_TX_4096
+#define OFDM_MINB_TX_4096 1
+#endif
+template <int LOG2N> struct MinBlocksTx {
+    static constexpr int value = LOG2N <= 9 ? OFDM_MINB_TX_SMALL
+                                            : (LOG2N == 10 ? OFDM_MINB_TX_1024 : (LOG2N == 11 ? OFDM_MINB_TX_2048 : OFDM_MINB_TX_4096));
+};
 template <int LOG2N> struct MinBlocks {
     static constexpr int value =
         LOG2N <= 9 ? OFDM_MINB_SMALL : (LOG2N == 10 ? OFDM_MINB_1024 : (LOG2N == 11 ? OFDM_MINB_2048 : OFDM_MINB_4096));
@@ -694,14 +734,23 @@ __device__ __forceinline__ unsigned ld_word_guarded(const uint8_t *__restrict__ 
 }
 
 template <int LOG2N, int BPS, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
+__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocksTx<LOG2N>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
     OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
     constexpr int N = C::N;
-    constexpr int WPT = 2;                                   // ceil(ceil(N*6/8/4 + 1) / T) <= 2 packed words per thread
+    constexpr int WPT = 2;                                   // a payload row spans at most 2 packed words per thread
+    constexpr int ZERO = 64;                                 // LUT entry that maps unused bins to 0
     const int L = N + P.cp, fs = P.m0 + P.d;
+    // constellation table in shared memory: one LDS per bin instead of arithmetic on the bits
+    float2 *lut = S::lut(smem_raw);
+    for (int i = tid; i <= ZERO; i += S::THREADS) lut[i] = i < (1 << BPS) ? map_bits<BPS>((unsigned)i) : make_float2(0.f, 0.f);
+    __syncthreads();
     const BinMap map = make_bin_map<T>(P.ndb, j);
+    // bit position of this thread's first bin of each spectrum half inside a payload row; the other
+    // bins of the half are T*BPS bits (a whole number of bytes) further on
+    const int bop = map.base_p * BPS, bon = (map.base_n - 4 * T) * BPS;
+    const int byp = bop >> 3, shp = 16 - (bop & 7) - BPS, byn = bon >> 3, shn = 16 - (bon & 7) - BPS;
     // this thread's samples n = j + m*T that also go into the cyclic prefix (n >= N - CP)
     unsigned cpmask = 0;
 #pragma unroll
@@ -726,26 +775,23 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     auto clampfs = [&](long long &ff, int &ss) {
         if (ff > last_f || (ff == last_f && ss > last_s)) { ff = last_f; ss = last_s; }
     };
-    clampfs(f, s);
-    unsigned wcur[WPT], wnxt[WPT];
-    {
-        const long long r = row_start(f, s);
+    auto fetch = [&](unsigned (&w)[WPT], long long r) {
 #pragma unroll
         for (int i = 0; i < WPT; ++i)
-            wcur[i] = (r >= 0 && j + i * T < nwords) ? ld_word_guarded(abits, (r & ~3ll) + 4 * (j + i * T), limit) : 0u;
-    }
+            w[i] = (r >= 0 && j + i * T < nwords) ? ld_word_guarded(abits, (r & ~3ll) + 4 * (j + i * T), limit) : 0u;
+    };
+    clampfs(f, s);
+    long long rcur = row_start(f, s);
+    unsigned wcur[WPT], wnxt[WPT];
+    fetch(wcur, rcur);
     for (int it = 0; it < iters; ++it) {
         // next work item and its payload words (in flight while this symbol is built)
         long long fn = f + step_f;
         int sn = s + step_s;
         if (sn >= fs) { sn -= fs; ++fn; }
         clampfs(fn, sn);
-        {
-            const long long r = row_start(fn, sn);
-#pragma unroll
-            for (int i = 0; i < WPT; ++i)
-                wnxt[i] = (r >= 0 && j + i * T < nwords) ? ld_word_guarded(abits, (r & ~3ll) + 4 * (j + i * T), limit) : 0u;
-        }
+        const long long rnxt = row_start(fn, sn);
+        fetch(wnxt, rnxt);
         float2 v[8];
         {
             // Stage the row's packed words, then every thread picks the bits of its own bins.  Groups that
@@ -756,15 +802,14 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             for (int i = 0; i < WPT; ++i)
                 if (j + i * T < nwords) hw[j + i * T] = wcur[i];
             group_sync<T, GROUPS>(gid);
-            const int phase = (int)(row_start(f, s) & 3);
+            const uint8_t *rp = hb + (int)(rcur & 3);
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-                const int bo = (map.mask & (1u << m)) ? bin_out<T>(map, m) * BPS : 0;
-                const int by = phase + (bo >> 3), sh = bo & 7;
-                unsigned w = (unsigned)hb[by] << 8;
-                if (BPS == 6) w |= (unsigned)hb[by + 1];
-                const unsigned val = (w >> (16 - sh - BPS)) & ((1u << BPS) - 1u);
-                v[m] = (map.mask & (1u << m)) ? map_bits<BPS>(val) : make_float2(0.f, 0.f);
+                const uint8_t *q = rp + (m < 4 ? byp : byn) + m * (T * BPS / 8);
+                unsigned w = (unsigned)q[0] << 8;
+                if (BPS == 6) w |= (unsigned)q[1];
+                const unsigned val = (w >> (m < 4 ? shp : shn)) & ((1u << BPS) - 1u);
+                v[m] = lut[(map.mask & (1u << m)) ? val : ZERO];
             }
             if (s < P.m0) {
                 const float2 *z = P.zc_tx + s * N + j;
@@ -798,6 +843,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
         }
         f = fn;
         s = sn;
+        rcur = rnxt;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) wcur[i] = wnxt[i];
     }
