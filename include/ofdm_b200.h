@@ -19,7 +19,8 @@
  *   - the library owns only the plan (twiddles, Zadoff-Chu, bin tables, optional staging buffers
  *     used by the h_* convenience entry points).
  *   - bits are packed MSB-first (numpy.packbits order); each OFDM data symbol owns
- *     ofdm_plan_hard_stride() bytes (= ceil(num_data_bins*bps/8)).
+ *     ofdm_plan_hard_stride() bytes (= ceil(payload_bins*bps/8), payload_bins = ofdm_plan_payload_bins()
+ *     = num_data_bins minus the comb pilots, if any); wherever a size below says "ndb" it means payload_bins.
  */
 #ifndef OFDM_B200_H
 #define OFDM_B200_H
@@ -61,7 +62,16 @@ typedef struct ofdm_params {
     float inv_reg_eq;        /* 1/x in g = conj(H)/(|H|^2 + 1/x), data   (SynchAndChanEst.py:244-246) */
     float inv_reg_eq_synch;  /* same for the synch-symbol equaliser       (SynchAndChanEst.py:213-218) */
     float llr_scale;         /* 1/noise variance multiplying the max-log LLRs */
-    int32_t reserved[8];     /* must be zero */
+    /* Comb pilots inside the data symbols (extension; the reference runs with ref_sigs = 0,
+     * GRR/LEGACY/gr-ofdm-rx/python/txrx_mod/SystemModel.py:30).  pilot_spacing = 0 disables them.  Otherwise
+     * positions pilot_offset, pilot_offset+pilot_spacing, ... of the used-bin list carry a unit-modulus
+     * Zadoff-Chu pilot (root pilot_root); the receiver equalises each data symbol with the LS estimate
+     * on its pilots, linearly interpolated across the list, and every per-symbol row holds
+     * num_data_bins - n_pilots payload bins. */
+    int32_t pilot_spacing;
+    int32_t pilot_offset;
+    int32_t pilot_root;
+    int32_t reserved[5];     /* must be zero */
 } ofdm_params;
 
 typedef struct ofdm_plan ofdm_plan;
@@ -75,6 +85,7 @@ int ofdm_plan_create(const ofdm_params *params, ofdm_plan **plan_out);
 int ofdm_plan_destroy(ofdm_plan *plan);
 int ofdm_plan_hard_stride(const ofdm_plan *plan);          /* bytes of packed bits per data symbol */
 int ofdm_plan_frame_len(const ofdm_plan *plan);            /* (M0+D)*(nfft+cp_len) samples */
+int ofdm_plan_payload_bins(const ofdm_plan *plan);         /* payload bins per data symbol */
 
 /* TX: bits -> QAM + Zadoff-Chu/resource-element insertion -> IFFT -> CP add -> power normalise.
  * Replaces MultiAntennaSystem.multi_ant_binary_map + multi_ant_symb_gen

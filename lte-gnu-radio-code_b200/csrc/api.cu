@@ -104,12 +104,12 @@ __global__ void counters_kernel(const DevParams P, const uint8_t *__restrict__ r
             for (int b = lane; b < P.hard_stride; b += 32) errs += __popc((unsigned)(__ldg(r + b) ^ __ldg(t + b)));
         }
         if (eq != nullptr) {
-            const float2 *q = eq + s * P.ndb;
+            const float2 *q = eq + s * P.ndd;
             switch (P.bps) {
-                case 1: cnt_symbol<1>(P, t, q, P.ndb, e2, r2, lane, 32); break;
-                case 2: cnt_symbol<2>(P, t, q, P.ndb, e2, r2, lane, 32); break;
-                case 4: cnt_symbol<4>(P, t, q, P.ndb, e2, r2, lane, 32); break;
-                default: cnt_symbol<6>(P, t, q, P.ndb, e2, r2, lane, 32); break;
+                case 1: cnt_symbol<1>(P, t, q, P.ndd, e2, r2, lane, 32); break;
+                case 2: cnt_symbol<2>(P, t, q, P.ndd, e2, r2, lane, 32); break;
+                case 4: cnt_symbol<4>(P, t, q, P.ndd, e2, r2, lane, 32); break;
+                default: cnt_symbol<6>(P, t, q, P.ndd, e2, r2, lane, 32); break;
             }
         }
     }
@@ -146,7 +146,7 @@ __global__ void counters_kernel(const DevParams P, const uint8_t *__restrict__ r
             for (long long f = lane; f < n_frames; f += 32) lk += locked[f] ? 1.0 : 0.0;
         for (int o = 16; o > 0; o >>= 1) lk += __shfl_xor_sync(0xffffffffu, lk, o);
         if (lane == 0) {
-            if (rx != nullptr) atomicAdd(cnt + 1, (double)n_sym * (double)(P.ndb * P.bps));
+            if (rx != nullptr) atomicAdd(cnt + 1, (double)n_sym * (double)(P.ndd * P.bps));
             atomicAdd(cnt + 4, lk);
             atomicAdd(cnt + 5, (double)n_frames);
         }
@@ -249,8 +249,12 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     if (p->m0 < 1 || p->m0 > 16 || p->d < 0) return fail(OFDM_EINVAL, "synch_dat out of range%s");
     if (p->bps != 1 && p->bps != 2 && p->bps != 4 && p->bps != 6) return fail(OFDM_EINVAL, "bps must be 1, 2, 4 or 6%s");
     if (p->sync_advance < 0 || p->sync_advance > p->cp_len) return fail(OFDM_EINVAL, "sync_advance must be in 0..cp_len%s");
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 5; ++i)
         if (p->reserved[i] != 0) return fail(OFDM_EINVAL, "reserved fields must be zero%s");
+    if (p->pilot_spacing < 0 || p->pilot_spacing == 1 || p->pilot_spacing > p->num_data_bins / 2)
+        return fail(OFDM_EINVAL, "pilot_spacing must be 0 or in 2..num_data_bins/2%s");
+    if (p->pilot_spacing && (p->pilot_offset < 0 || p->pilot_offset >= p->pilot_spacing))
+        return fail(OFDM_EINVAL, "pilot_offset must be in 0..pilot_spacing-1%s");
 
     ofdm_plan *pl = new (std::nothrow) ofdm_plan();
     if (!pl) return fail(OFDM_ENOMEM, "out of host memory%s");
@@ -315,10 +319,23 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
         zc_dup[2 * s + 1] = make_float2((float)zr[s * nsb + nsb - 1], (float)(-zi[s * nsb + nsb - 1]));
     }
 
+    // comb pilots (extension): unit-modulus Zadoff-Chu of length n_pil placed on used-bin positions off + i*K
+    const int ndb = p->num_data_bins, pk = p->pilot_spacing, poff = p->pilot_offset;
+    const int n_pil = pk ? (ndb - poff + pk - 1) / pk : 0;
+    std::vector<float2> pilot_tx(N, make_float2(0.f, 0.f));
+    for (int i = 0; i < n_pil; ++i) {
+        const int jo = poff + i * pk, hh = ndb / 2;
+        const int sb = jo < hh ? jo - hh : jo - hh + 1;
+        const int k = ((sb % N) + N) % N;
+        const double ii = (double)i;
+        const double q = (n_pil % 2 == 0) ? ii * ii / 2.0 : ii * (ii + 1.0) / 2.0;
+        const double a = -(two_pi / (double)n_pil) * (double)p->pilot_root * q;
+        pilot_tx[k] = make_float2((float)cos(a), (float)sin(a));
+    }
     const size_t b_tw = sizeof(float2) * N, b_zb = sizeof(float2) * m0 * N, b_w = sizeof(float) * N,
-                 b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * m0 * N;
+                 b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * m0 * N, b_pt = sizeof(float2) * N;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt);
+    const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt) + al(b_pt);
     e = cudaMalloc(&pl->d_tables, total);
     if (e != cudaSuccess) {
         delete pl;
@@ -338,6 +355,7 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     D.w_bin = (const float *)put(w_bin.data(), b_w);
     D.zc_dup = (const float2 *)put(zc_dup.data(), b_zd);
     D.zc_tx = (const float2 *)put(zc_tx.data(), b_zt);
+    D.pilot_tx = (const float2 *)put(pilot_tx.data(), b_pt);
     if (e != cudaSuccess) {
         cudaFree(pl->d_tables);
         delete pl;
@@ -352,7 +370,11 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     D.bps = p->bps;
     D.mm = mm;
     D.sync_advance = p->sync_advance;
-    D.hard_stride = (p->num_data_bins * p->bps + 7) / 8;
+    D.pil_k = pk;
+    D.pil_off = poff;
+    D.n_pil = n_pil;
+    D.ndd = ndb - n_pil;
+    D.hard_stride = (D.ndd * p->bps + 7) / 8;
     D.dup_bin = dup_bin;
     D.equalizer = p->equalizer;
     D.gate_thresh = p->gate * (float)mm;
@@ -379,6 +401,7 @@ int ofdm_plan_destroy(ofdm_plan *pl) {
 }
 
 int ofdm_plan_hard_stride(const ofdm_plan *pl) { return pl ? pl->dev.hard_stride : OFDM_EINVAL; }
+int ofdm_plan_payload_bins(const ofdm_plan *pl) { return pl ? pl->dev.ndd : OFDM_EINVAL; }
 int ofdm_plan_frame_len(const ofdm_plan *pl) {
     return pl ? (pl->prm.m0 + pl->prm.d) * (pl->prm.nfft + pl->prm.cp_len) : OFDM_EINVAL;
 }
@@ -519,7 +542,7 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
     if (rc) return rc;
     const ofdm_params &p = pl->prm;
     const int64_t L = p.nfft + p.cp_len, fl = (int64_t)(p.m0 + p.d) * L;
-    const int64_t ndb = p.num_data_bins, hs = pl->dev.hard_stride;
+    const int64_t ndb = pl->dev.ndd, hs = pl->dev.hard_stride;
     // chunk size: ~32 MiB of input per slot so copies and kernels of adjacent chunks overlap
     int64_t per = (32ll << 20) / (frame_stride * 8);
     if (per < 1) per = 1;

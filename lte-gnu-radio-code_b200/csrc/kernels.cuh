@@ -30,7 +30,38 @@ struct DevParams {
     const float *w_bin;       // [N]      how many synch indices map to bin k (0, 1, or 2 for the +-N/2 alias)
     const float2 *zc_dup;     // [M0][2]  conj(zc) of the first / last synch index (alias handling)
     const float2 *zc_tx;      // [M0][N]  ZC value the transmitter puts in bin k of synch symbol m (0 if unused)
+    // comb pilots in data symbols (extension): positions pil_off + i*pil_k of the used-bin list
+    int pil_k, pil_off, n_pil, ndd;   // ndd = payload bins per data symbol = ndb - n_pil
+    const float2 *pilot_tx;   // [N]      pilot value in FFT bin k (0 elsewhere)
 };
+
+// position of a used-bin-list index among pilots / payload bins
+struct PilotPos {
+    bool is_pilot;
+    int ip;        // pilot index (is_pilot) or index of the pilot at or below jo (clamped to 0)
+    int dj;        // payload index (jo minus the pilots before it)
+    float frac;    // interpolation weight towards pilot ip+1 (0 when held constant at an edge)
+};
+__device__ __forceinline__ PilotPos pilot_pos(const DevParams &P, int jo) {
+    PilotPos r;
+    const int rel = jo - P.pil_off;
+    const int q = rel >= 0 ? rel / P.pil_k : 0, rem = rel >= 0 ? rel - q * P.pil_k : 0;
+    r.is_pilot = rel >= 0 && rem == 0 && q < P.n_pil;
+    int before = rel <= 0 ? 0 : q + (rem != 0 ? 1 : 0);            // pilots strictly below jo
+    before = before < P.n_pil ? before : P.n_pil;
+    r.dj = jo - before;
+    if (rel < 0) {
+        r.ip = 0;
+        r.frac = 0.f;
+    } else if (q >= P.n_pil - 1) {
+        r.ip = P.n_pil - 1;
+        r.frac = 0.f;
+    } else {
+        r.ip = q;
+        r.frac = (float)rem / (float)P.pil_k;
+    }
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -267,12 +298,14 @@ template <int LOG2N, int GROUPS> struct Smem {
     static constexpr int HB_STRIDE = C::N + 16;                                     // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
     static constexpr int LUT_BYTES = 72 * 8;                                        // constellation table (TX), entry 64 = 0
+    static constexpr int HP_BYTES = GROUPS * (C::N / 2) * 8;                        // per-symbol pilot estimates (pilot mode)
     static constexpr int OFF_TW = FFT_BYTES;
     static constexpr int OFF_STAGE = OFF_TW + TW_BYTES;
     static constexpr int OFF_RED = OFF_STAGE + STAGE_BYTES;
     static constexpr int OFF_HB = OFF_RED + RED_BYTES;
     static constexpr int OFF_LUT = OFF_HB + ((HB_BYTES + 7) & ~7);
-    static constexpr int BYTES = OFF_LUT + LUT_BYTES;
+    static constexpr int OFF_HP = OFF_LUT + LUT_BYTES;
+    static constexpr int BYTES = OFF_HP + HP_BYTES;
     __device__ static float2 *buf0(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s) + gid * GSTRIDE; }
     __device__ static float2 *tws(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_TW); }
     // slot m of thread t: stage[m * THREADS + t] -> lanes hit consecutive 8-byte words
@@ -285,6 +318,7 @@ template <int LOG2N, int GROUPS> struct Smem {
     }
     __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + OFF_HB + gid * HB_STRIDE; }
     __device__ static float2 *lut(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_LUT); }
+    __device__ static float2 *hp(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s + OFF_HP) + gid * (C::N / 2); }
 };
 
 // Asynchronous prefetch of this thread's 8 samples of the window that opens at `start` into its
@@ -462,6 +496,67 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     }
 }
 
+// Pilot mode (extension): G[] holds the de-rotation only.  Each data symbol is equalised with the LS
+// estimate on its own comb pilots, linearly interpolated across the used-bin list and held constant
+// outside the outermost pilots (the oracle's np.interp).  Off the fast path: positions are recomputed
+// per bin because payload indices are no longer a fixed stride apart.
+template <int LOG2N, int BPS, int GROUPS>
+__device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const DataCtx<LOG2N, BPS> &D,
+                                                    const float2 (&v)[8], const float2 (&R)[8], long long row,
+                                                    float *redf, uint8_t *hb, float2 *hp, int j, int gid,
+                                                    float2 *__restrict__ eq_out, float *__restrict__ llr_out,
+                                                    uint8_t *__restrict__ hard_out) {
+    using C = FftCfg<LOG2N>;
+    constexpr int T = C::T;
+    const unsigned mask = D.map.mask;
+    float pw = 0.f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+        if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
+    pw = group_sum<T, GROUPS>(pw, redf, j, gid);
+    const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;
+    float2 z[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        z[m] = cscale(cmul(R[m], v[m]), p0);
+        if (mask & (1u << m)) {
+            const PilotPos pp = pilot_pos(P, bin_out<T>(D.map, m));
+            if (pp.is_pilot) hp[pp.ip] = cmulc(z[m], __ldg(P.pilot_tx + j + m * T));   // LS: Y * conj(p), |p| = 1
+        }
+    }
+    group_sync<T, GROUPS>(gid);
+    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (mask & (1u << m)) {
+            const PilotPos pp = pilot_pos(P, bin_out<T>(D.map, m));
+            if (!pp.is_pilot) {
+                const float2 ha = hp[pp.ip], hb2 = hp[pp.ip + (pp.frac > 0.f ? 1 : 0)];
+                const float2 h = make_float2(fmaf(pp.frac, hb2.x - ha.x, ha.x), fmaf(pp.frac, hb2.y - ha.y, ha.y));
+                const float den = cabs2(h) + P.inv_reg_eq;
+                const float inv = den > 0.f ? __fdividef(1.f, den) : 0.f;
+                const float2 e = cscale(cmul(make_float2(h.x, -h.y), z[m]), inv);
+                const long long o = row * P.ndd + pp.dj;
+                __stcs(eq_out + o, e);
+                if (soft || hard) {
+                    float Lb[BPS];
+                    unsigned bits;
+                    D.dem.run(e, Lb, bits);
+                    if (soft) {
+#pragma unroll
+                        for (int b = 0; b < BPS; ++b) __stcs(llr_out + o * BPS + b, Lb[b]);
+                    }
+                    if (hard) hb[pp.dj] = (uint8_t)bits;
+                }
+            }
+        }
+    }
+    if (hard) {
+        group_sync<T, GROUPS>(gid);
+        pack_bits<BPS, T>(hb, hard_out + row * P.hard_stride, P.hard_stride, j);
+    }
+}
+
 #define OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)                                            \
     using C = FftCfg<LOG2N>;                                                           \
     using S = Smem<LOG2N, GROUPS>;                                                     \
@@ -474,7 +569,8 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     float *redf = S::redf(smem_raw, gid);                                              \
     unsigned long long *redu = S::redu(smem_raw, gid);                                 \
     uint8_t *hb = S::hb(smem_raw, gid);                                                \
-    (void)redu; (void)redf; (void)stage;                                               \
+    float2 *hp = S::hp(smem_raw, gid);                                                 \
+    (void)redu; (void)redf; (void)stage; (void)hp;                                     \
     for (int i = j; i < S::HB_STRIDE; i += T) hb[i] = 0;                               \
     fill_twiddles<LOG2N>(S::tws(smem_raw), P.tw, tid, S::THREADS);                     \
     __syncthreads();                                                                   \
@@ -522,7 +618,7 @@ template <int LOG2N> struct MinBlocks {
 //     The group walks its frames symbol by symbol; while symbol q is transformed the samples of
 //     symbol q+1 (next symbol of the frame, or the preamble of the group's next frame) are in flight.
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N, int BPS, int GROUPS>
+template <int LOG2N, int BPS, int GROUPS, bool PIL>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
@@ -560,6 +656,13 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                     float2 H[8];
                     sync_finish<LOG2N, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
                     chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq, j, H, G);
+                    if (PIL) {                               // pilot mode equalises per symbol: keep only the rotation
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const float2 w = __ldg(P.tw + ((delay * (j + m * T)) & (N - 1)));
+                            G[m] = make_float2(w.x, -w.y);
+                        }
+                    }
                     if (j == 0) {
                         delay_out[f] = delay;
                         peak_out[f] = peak;
@@ -570,6 +673,9 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                         for (int m = 0; m < 8; ++m) H_out[f * N + j + m * T] = H[m];
                     }
                 }
+            } else if (PIL) {
+                data_epilogue_pilot<LOG2N, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, hp, j, gid, eq_out,
+                                                        llr_out, hard_out);
             } else {
                 data_epilogue<LOG2N, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, j, gid, eq_out, llr_out,
                                                   hard_out);
@@ -687,7 +793,7 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
 // ------------------------------------------------------------------------------------------------
 // K4  data symbols from an explicit symbol list (used by the stream blocks' work()).
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N, int BPS, int GROUPS>
+template <int LOG2N, int BPS, int GROUPS, bool PIL>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
 rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
                 const long long *__restrict__ start_in, const int *__restrict__ delay_in,
@@ -709,10 +815,14 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
             const float2 h = __ldg(Hmat + hrow * N + k);
             const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));
             const float den = cabs2(h) + P.inv_reg_eq;
-            G[m] = cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? __fdividef(1.f, den) : 0.f);
+            G[m] = PIL ? make_float2(w.x, -w.y)
+                       : cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? __fdividef(1.f, den) : 0.f);
         }
         fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
-        data_epilogue<LOG2N, BPS, GROUPS>(P, D, v, G, i, redf, hb, j, gid, eq_out, llr_out, hard_out);
+        if (PIL)
+            data_epilogue_pilot<LOG2N, BPS, GROUPS>(P, D, v, G, i, redf, hb, hp, j, gid, eq_out, llr_out, hard_out);
+        else
+            data_epilogue<LOG2N, BPS, GROUPS>(P, D, v, G, i, redf, hb, j, gid, eq_out, llr_out, hard_out);
     }
 }
 
@@ -733,7 +843,7 @@ __device__ __forceinline__ unsigned ld_word_guarded(const uint8_t *__restrict__ 
     return w;
 }
 
-template <int LOG2N, int BPS, int GROUPS>
+template <int LOG2N, int BPS, int GROUPS, bool PIL>
 __global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocksTx<LOG2N>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
@@ -803,13 +913,27 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                 if (j + i * T < nwords) hw[j + i * T] = wcur[i];
             group_sync<T, GROUPS>(gid);
             const uint8_t *rp = hb + (int)(rcur & 3);
+            if (PIL) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const uint8_t *q = rp + (m < 4 ? byp : byn) + m * (T * BPS / 8);
-                unsigned w = (unsigned)q[0] << 8;
-                if (BPS == 6) w |= (unsigned)q[1];
-                const unsigned val = (w >> (m < 4 ? shp : shn)) & ((1u << BPS) - 1u);
-                v[m] = lut[(map.mask & (1u << m)) ? val : ZERO];
+                for (int m = 0; m < 8; ++m) {
+                    const bool used = (map.mask & (1u << m)) != 0;
+                    const PilotPos pq = pilot_pos(P, used ? bin_out<T>(map, m) : 0);
+                    const int bo = pq.dj * BPS;
+                    const uint8_t *q = rp + (bo >> 3);
+                    unsigned w = (unsigned)q[0] << 8;
+                    if (BPS == 6) w |= (unsigned)q[1];
+                    const unsigned val = (w >> (16 - (bo & 7) - BPS)) & ((1u << BPS) - 1u);
+                    v[m] = !used ? make_float2(0.f, 0.f) : (pq.is_pilot ? __ldg(P.pilot_tx + j + m * T) : lut[val]);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const uint8_t *q = rp + (m < 4 ? byp : byn) + m * (T * BPS / 8);
+                    unsigned w = (unsigned)q[0] << 8;
+                    if (BPS == 6) w |= (unsigned)q[1];
+                    const unsigned val = (w >> (m < 4 ? shp : shn)) & ((1u << BPS) - 1u);
+                    v[m] = lut[(map.mask & (1u << m)) ? val : ZERO];
+                }
             }
             if (s < P.m0) {
                 const float2 *z = P.zc_tx + s * N + j;

@@ -56,12 +56,20 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
     if (n_frames <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
-        constexpr auto k = rx_frames_kernel<LOG2N, BPS, G>;
         LaunchDims d;
-        cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
-        if (e != cudaSuccess) return e;
-        k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H, eq,
-                                  llr, hard);
+        if (P.pil_k) {
+            constexpr auto k = rx_frames_kernel<LOG2N, BPS, G, true>;
+            cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
+            if (e != cudaSuccess) return e;
+            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
+                                      eq, llr, hard);
+        } else {
+            constexpr auto k = rx_frames_kernel<LOG2N, BPS, G, false>;
+            cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
+            if (e != cudaSuccess) return e;
+            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
+                                      eq, llr, hard);
+        }
         count_launch();
     })
     return cudaGetLastError();
@@ -74,11 +82,18 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
     constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
     if (n_sym <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
-        constexpr auto k = rx_demod_kernel<LOG2N, BPS, G>;
         LaunchDims d;
-        cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
-        if (e != cudaSuccess) return e;
-        k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
+        if (P.pil_k) {
+            constexpr auto k = rx_demod_kernel<LOG2N, BPS, G, true>;
+            cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
+            if (e != cudaSuccess) return e;
+            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
+        } else {
+            constexpr auto k = rx_demod_kernel<LOG2N, BPS, G, false>;
+            cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
+            if (e != cudaSuccess) return e;
+            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
+        }
         count_launch();
     })
     return cudaGetLastError();
@@ -90,11 +105,18 @@ cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long
     constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
     if (n_sym_total <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
-        constexpr auto k = tx_kernel<LOG2N, BPS, G>;
         LaunchDims d;
-        cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
-        if (e != cudaSuccess) return e;
-        k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);
+        if (P.pil_k) {
+            constexpr auto k = tx_kernel<LOG2N, BPS, G, true>;
+            cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
+            if (e != cudaSuccess) return e;
+            k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);
+        } else {
+            constexpr auto k = tx_kernel<LOG2N, BPS, G, false>;
+            cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
+            if (e != cudaSuccess) return e;
+            k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);
+        }
         count_launch();
     })
     return cudaGetLastError();

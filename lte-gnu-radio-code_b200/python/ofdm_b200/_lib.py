@@ -16,7 +16,8 @@ class OfdmParams(C.Structure):
         ("zc_root", C.c_int32), ("zc_parity_of", C.c_int32), ("equalizer", C.c_int32),
         ("sync_advance", C.c_int32), ("gate", C.c_float), ("inv_reg_chanest", C.c_float),
         ("inv_reg_eq", C.c_float), ("inv_reg_eq_synch", C.c_float), ("llr_scale", C.c_float),
-        ("reserved", C.c_int32 * 8),
+        ("pilot_spacing", C.c_int32), ("pilot_offset", C.c_int32), ("pilot_root", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -31,6 +32,7 @@ SIGNATURES = {
     "ofdm_plan_destroy": (C.c_int, [_P]),
     "ofdm_plan_hard_stride": (C.c_int, [_P]),
     "ofdm_plan_frame_len": (C.c_int, [_P]),
+    "ofdm_plan_payload_bins": (C.c_int, [_P]),
     "ofdm_tx_modulate": (C.c_int, [_P, _P, _P, _I64, _P]),
     "ofdm_rx_sync_search": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "ofdm_rx_chanest": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),

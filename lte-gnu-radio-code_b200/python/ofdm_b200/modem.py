@@ -32,6 +32,9 @@ class ModemConfig:
     equalizer: str = "mmse"             # "mmse" | "zf"
     sync_advance: int = 0
     noise_var: float = 1.0              # LLR scale = 1/noise_var
+    pilot_spacing: int = 0              # comb pilots in data symbols (extension); 0 = none
+    pilot_offset: int = -1              # -1 -> pilot_spacing // 2
+    pilot_root: int = 25
 
     def __post_init__(self):
         if isinstance(self.bps, str):
@@ -42,6 +45,8 @@ class ModemConfig:
             self.zc_root = 23 if self.compat == "utsa" else 37
         if self.compat == "rxofdm":
             self.gate = 0.4             # hard-coded: gr-RXOFDM/python/synch_and_chan_est.py:170
+        if self.pilot_spacing and self.pilot_offset < 0:
+            self.pilot_offset = self.pilot_spacing // 2
 
     # derived quantities (same names as the oracle's, computed independently)
     @property
@@ -65,8 +70,19 @@ class ModemConfig:
         return 1 if self.compat == "utsa" else self.cp_len - 1
 
     @property
+    def n_pilots(self):
+        if not self.pilot_spacing:
+            return 0
+        return len(range(self.pilot_offset, self.num_data_bins, self.pilot_spacing))
+
+    @property
+    def payload_bins(self):
+        """bins per data symbol that carry payload (num_data_bins minus comb pilots)"""
+        return self.num_data_bins - self.n_pilots
+
+    @property
     def hard_stride(self):
-        return (self.num_data_bins * self.bps + 7) // 8
+        return (self.payload_bins * self.bps + 7) // 8
 
     def regularisers(self):
         """(inv_reg_chanest, inv_reg_eq, inv_reg_eq_synch): SynchAndChanEst.py:99,180,214,245 vs
@@ -89,6 +105,7 @@ class ModemConfig:
         p.gate = self.gate
         p.inv_reg_chanest, p.inv_reg_eq, p.inv_reg_eq_synch = rc, re_, rs
         p.llr_scale = 1.0 / self.noise_var
+        p.pilot_spacing, p.pilot_offset, p.pilot_root = self.pilot_spacing, max(self.pilot_offset, 0), self.pilot_root
         return p
 
 
@@ -121,6 +138,7 @@ class Modem:
             _lib.check(_lib.lib().ofdm_plan_create(C.byref(s), C.byref(self._h)))
         assert _lib.lib().ofdm_plan_hard_stride(self._h) == cfg.hard_stride
         assert _lib.lib().ofdm_plan_frame_len(self._h) == cfg.frame_len
+        assert _lib.lib().ofdm_plan_payload_bins(self._h) == cfg.payload_bins
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -167,8 +185,8 @@ class Modem:
             o["delay"] = self.empty((n_frames,), torch.int32)
             o["peak"] = self.empty((n_frames,), torch.float32)
             o["locked"] = self.empty((n_frames,), torch.uint8)
-            o["eq"] = self.empty((nd, cfg.num_data_bins), torch.complex64)
-            o["llr"] = self.empty((nd, cfg.num_data_bins * cfg.bps), torch.float32) if want_llr else None
+            o["eq"] = self.empty((nd, cfg.payload_bins), torch.complex64)
+            o["llr"] = self.empty((nd, cfg.payload_bins * cfg.bps), torch.float32) if want_llr else None
             o["hard"] = self.empty((nd, cfg.hard_stride), torch.uint8) if want_hard else None
             o["h"] = self.empty((n_frames, cfg.nfft), torch.complex64) if want_h else None
         _lib.check(_lib.lib().ofdm_rx_frames(
@@ -204,8 +222,8 @@ class Modem:
         rx = self._c64(rx)
         n = start.numel()
         assert start.dtype == torch.int64 and delay.dtype == torch.int32 and hrow.dtype == torch.int32
-        eq = self.empty((n, cfg.num_data_bins), torch.complex64)
-        llr = self.empty((n, cfg.num_data_bins * cfg.bps), torch.float32) if want_llr else None
+        eq = self.empty((n, cfg.payload_bins), torch.complex64)
+        llr = self.empty((n, cfg.payload_bins * cfg.bps), torch.float32) if want_llr else None
         hard = self.empty((n, cfg.hard_stride), torch.uint8) if want_hard else None
         _lib.check(_lib.lib().ofdm_rx_demod(self._h, _ptr(rx), rx.numel(), _ptr(start), _ptr(delay), _ptr(hrow),
                                             _ptr(self._c64(h)), n, _ptr(eq), _ptr(llr), _ptr(hard), _stream()))
@@ -256,8 +274,8 @@ class Modem:
             o["delay"] = np.empty(n_frames, np.int32)
             o["peak"] = np.empty(n_frames, np.float32)
             o["locked"] = np.empty(n_frames, np.uint8)
-            o["eq"] = np.empty((nd, cfg.num_data_bins), np.complex64)
-            o["llr"] = np.empty((nd, cfg.num_data_bins * cfg.bps), np.float32) if want_llr else None
+            o["eq"] = np.empty((nd, cfg.payload_bins), np.complex64)
+            o["llr"] = np.empty((nd, cfg.payload_bins * cfg.bps), np.float32) if want_llr else None
             o["hard"] = np.empty((nd, cfg.hard_stride), np.uint8) if want_hard else None
 
         def p(a):

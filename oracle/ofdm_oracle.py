@@ -47,12 +47,18 @@ class ModemParams:
     zc_root: Optional[int] = None    # default: 23 (utsa) / 37 (rxofdm)
     equalizer: str = "mmse"          # "mmse" (reference) or "zf" (extension: regulariser -> 0)
     sync_advance: int = 0            # framed mode: how many samples before the CP end the window opens
+    # comb pilots in the data symbols (EXTENSION, our definition; the reference has ref_sigs = 0):
+    pilot_spacing: int = 0           # 0 = none; else every pilot_spacing-th used bin (list order) is a pilot
+    pilot_offset: int = -1           # first pilot position in the used-bin list; -1 -> pilot_spacing // 2
+    pilot_root: int = 25             # Zadoff-Chu root of the pilot sequence
 
     def __post_init__(self):
         if self.zc_root is None:
             self.zc_root = 23 if self.compat == "utsa" else 37
         if self.compat == "rxofdm":
             self.gate = 0.4
+        if self.pilot_spacing and self.pilot_offset < 0:
+            self.pilot_offset = self.pilot_spacing // 2
 
     # derived -------------------------------------------------------------------------------
     @property
@@ -70,6 +76,24 @@ class ModemParams:
     @property
     def mm(self):                    # MM, SynchAndChanEst.py:48-49
         return self.m0 * self.num_synch_bins
+
+    @property
+    def pilot_pos(self):
+        """positions (in the used-bin list) that carry pilots"""
+        if not self.pilot_spacing:
+            return np.zeros(0, dtype=np.int64)
+        return np.arange(self.pilot_offset, self.num_data_bins, self.pilot_spacing, dtype=np.int64)
+
+    @property
+    def data_pos(self):
+        """positions (in the used-bin list) that carry payload"""
+        m = np.ones(self.num_data_bins, dtype=bool)
+        m[self.pilot_pos] = False
+        return np.nonzero(m)[0]
+
+    @property
+    def n_payload_bins(self):
+        return self.num_data_bins - len(self.pilot_pos)
 
     @property
     def stride(self):                # SynchAndChanEst.py:77 vs gr-RXOFDM/python/synch_and_chan_est.py:81
@@ -208,9 +232,10 @@ def tx_freq_grid(bits, prm: ModemParams, n_frames):
     zc = zadoff_chu(prm.mm, prm.zc_root)            # TX side always keys parity on MM (SynchSignal.py:24)
     sb = bins_used(prm.num_synch_bins, N)
     db = bins_used(prm.num_data_bins, N)
-    per_sym = prm.num_data_bins * prm.bps
+    per_sym = prm.n_payload_bins * prm.bps
     bits = np.asarray(bits).reshape(-1)
     assert bits.size == n_frames * prm.d * per_sym
+    ppos, dpos, pv = prm.pilot_pos, prm.data_pos, pilot_values(prm)
     grid = np.zeros((n_frames * prm.frame_syms, N), dtype=complex)
     data_i = 0
     for f in range(n_frames):
@@ -220,7 +245,8 @@ def tx_freq_grid(bits, prm: ModemParams, n_frames):
                 grid[row, sb] = zc[s * prm.num_synch_bins:(s + 1) * prm.num_synch_bins]
             else:
                 chunk = bits[data_i * per_sym:(data_i + 1) * per_sym]
-                grid[row, db] = bits_to_symbols(chunk, prm.bps)
+                grid[row, db[dpos]] = bits_to_symbols(chunk, prm.bps)
+                grid[row, db[ppos]] = pv
                 data_i += 1
     return grid
 
@@ -245,6 +271,12 @@ def tx_symb_gen(grid, cp_len):
         t = t * (1.0 / np.sqrt(np.var(t)))
         out[s * L:(s + 1) * L] = t
     return out
+
+
+def pilot_values(prm: ModemParams):
+    """Unit-modulus pilot sequence: Zadoff-Chu of length n_pilots (EXTENSION, our definition)."""
+    n = len(prm.pilot_pos)
+    return zadoff_chu(n, prm.pilot_root) if n else np.zeros(0, dtype=complex)
 
 
 def tx_modulate(bits, prm: ModemParams, n_frames):
@@ -384,6 +416,17 @@ def demod_symbol(in0, ptr, delay, h_full, prm: ModemParams, literal=False):
     fd = fd * p0
     hd = h_full[db]
     inv_reg = 0.0 if np.isinf(prm.reg_eq) else 1.0 / prm.reg_eq
+    if prm.pilot_spacing:
+        # EXTENSION (our definition): per-symbol LS estimate on the comb pilots, linear interpolation
+        # across the used-bin list (held constant outside the outermost pilots), then the same one-tap
+        # equaliser on the payload bins.  Timing (delay) still comes from the preamble.
+        z = fd * np.exp(((1j * (TWO_PI / N)) * delay) * db)
+        ppos, dpos = prm.pilot_pos, prm.data_pos
+        hp = z[ppos] * np.conj(pilot_values(prm))
+        jo = np.arange(prm.num_data_bins)
+        hi = np.interp(jo, ppos, hp.real) + 1j * np.interp(jo, ppos, hp.imag)
+        g = np.conj(hi) / (inv_reg + hi * np.conj(hi))
+        return (g * z)[dpos]
     if literal:
         arg = [((1j * (TWO_PI / N)) * delay) * kk for kk in db]
         z = np.matmul(np.diag(fd), np.exp(arg))
@@ -414,7 +457,7 @@ def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, litera
     peak = np.zeros(n_frames)
     locked = np.zeros(n_frames, dtype=np.uint8)
     h = np.zeros((n_frames, prm.nfft), dtype=complex)
-    eq = np.zeros((n_frames, prm.d, prm.num_data_bins), dtype=complex)
+    eq = np.zeros((n_frames, prm.d, prm.n_payload_bins), dtype=complex)
     for f in range(n_frames):
         pos = first + f * fs + prm.cp_len - prm.sync_advance
         d_i, d_v, sd = sync_trial(rx, pos, prm, zc, bank, literal)

@@ -30,7 +30,8 @@ def oracle_prm(cfg):
     return oo.ModemParams(nfft=cfg.nfft, cp_len=cfg.cp_len, num_synch_bins=cfg.num_synch_bins,
                           num_data_bins=cfg.num_data_bins, m0=cfg.m0, d=cfg.d, bps=cfg.bps, snr=cfg.snr,
                           gate=cfg.gate, compat=cfg.compat, zc_root=cfg.zc_root, equalizer=cfg.equalizer,
-                          sync_advance=cfg.sync_advance)
+                          sync_advance=cfg.sync_advance, pilot_spacing=cfg.pilot_spacing,
+                          pilot_offset=cfg.pilot_offset, pilot_root=cfg.pilot_root)
 
 
 def pack_symbols(bits, n_sym, per_sym, hard_stride):
@@ -106,3 +107,40 @@ def test_rx_frames_matches_oracle(kw):
     # LLR
     ref_llr = oo.maxlog_llr(ref["eq"].reshape(n_frames * cfg.d, -1), cfg.bps, 1.0 / cfg.noise_var)
     assert rel_err(got["llr"].cpu().numpy(), ref_llr) < RTOL
+
+
+PILOT_CASES = [
+    dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2, pilot_spacing=6),
+    dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4, pilot_spacing=4, pilot_offset=1),
+    dict(nfft=256, cp_len=64, num_synch_bins=254, num_data_bins=240, m0=1, d=2, bps=6, pilot_spacing=8),
+    dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=2, bps=4, pilot_spacing=6, pilot_offset=0),
+]
+
+
+@pytest.mark.parametrize("kw", PILOT_CASES, ids=lambda k: "N%d_b%d_K%d" % (k["nfft"], k["bps"], k["pilot_spacing"]))
+def test_comb_pilot_mode_matches_oracle(kw):
+    """Extension (unpinned: the reference has no pilots): resource-element insertion on TX, per-symbol LS
+    on the comb + linear frequency interpolation on RX."""
+    m = make(dict(kw, snr=100, gate=0.5, noise_var=0.02))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    assert cfg.payload_bins == prm.n_payload_bins
+    n_frames = 5
+    rng = np.random.default_rng(17)
+    per_sym = cfg.payload_bins * cfg.bps
+    bits = rng.integers(0, 2, n_frames * cfg.d * per_sym)
+    ref_tx = oo.tx_modulate(bits, prm, n_frames)
+    packed = pack_symbols(bits, n_frames * cfg.d, per_sym, cfg.hard_stride)
+    tx = m.tx_modulate(torch.from_numpy(packed).cuda(), n_frames).cpu().numpy()
+    assert rel_err(tx, ref_tx) < RTOL
+    rx = oo.add_awgn(oo.apply_channel(ref_tx, oo.reference_channel(cfg.nfft))[:len(ref_tx)], 1e-4, rng).astype(np.complex64)
+    ref = oo.rx_frames(rx, n_frames, prm)
+    got = m.rx_frames(torch.from_numpy(rx).cuda(), n_frames)
+    assert np.array_equal(got["delay"].cpu().numpy(), ref["delay"])
+    eq = got["eq"].cpu().numpy().reshape(ref["eq"].shape)
+    assert rel_err(eq, ref["eq"]) < RTOL
+    ref_llr = oo.maxlog_llr(ref["eq"].reshape(n_frames * cfg.d, -1), cfg.bps, 1.0 / cfg.noise_var)
+    assert rel_err(got["llr"].cpu().numpy(), ref_llr) < RTOL
+    got_bits = unpack_symbols(got["hard"].cpu().numpy(), per_sym)
+    assert np.array_equal(got_bits, oo.hard_bits(ref["eq"].reshape(-1), cfg.bps))
+    assert np.mean(got_bits != bits) < (1e-9 if cfg.bps <= 2 else 2e-2)
