@@ -1,6 +1,8 @@
 // launch.cuh -- host-side launchers, instantiated once per log2(NFFT) in inst_n*.cu so the
 // translation units compile in parallel.
 #pragma once
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace ofdm {
@@ -18,8 +20,11 @@ void count_launch();
 
 // grid = min(#CTAs needed, resident CTAs on the whole device): persistent groups stride over the work
 template <auto kernel>
-static inline cudaError_t plan_launch(int threads, int smem, int groups, long long work, int sms, LaunchDims &dims) {
+static inline cudaError_t plan_launch(int threads, int &smem, int groups, long long work, int sms, LaunchDims &dims) {
     static int cached_dev = -1, cached_bps = 0;
+    // tuning aid: OFDM_SMEM_PAD=<bytes> inflates the dynamic shared-memory request to lower occupancy
+    static const int pad = getenv("OFDM_SMEM_PAD") ? atoi(getenv("OFDM_SMEM_PAD")) : 0;
+    smem += pad;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -53,7 +58,8 @@ template <int LOG2N>
 cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_samples, long long first,
                              long long frame_stride, long long n_frames, int *delay, float *peak, uint8_t *locked,
                              float2 *H, float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
+    int SM = Smem<LOG2N, G>::BYTES;
     if (n_frames <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
@@ -79,7 +85,8 @@ template <int LOG2N>
 cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_samples, const long long *start,
                             const int *delay, const int *hrow, const float2 *H, long long n_sym, float2 *eq,
                             float *llr, uint8_t *hard, cudaStream_t st, int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
+    int SM = Smem<LOG2N, G>::BYTES;
     if (n_sym <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
@@ -102,7 +109,8 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
 template <int LOG2N>
 cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long long n_sym_total, cudaStream_t st,
                       int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
+    int SM = Smem<LOG2N, G>::BYTES;
     if (n_sym_total <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
@@ -126,7 +134,8 @@ template <int LOG2N>
 cudaError_t launch_sync_search(const DevParams &P, const float2 *x, long long n_samples, long long first_start,
                                long long stride, long long n_trials, float *peak, int *delay, cudaStream_t st,
                                int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
+    int SM = Smem<LOG2N, G>::BYTES;
     if (n_trials <= 0) return cudaSuccess;
     constexpr auto k = rx_sync_search_kernel<LOG2N, G>;
     LaunchDims d;
@@ -141,7 +150,8 @@ template <int LOG2N>
 cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samples, const long long *pos,
                            const int *delay, long long n_locks, float2 *H, float2 *htime, float2 *synch_eq,
                            cudaStream_t st, int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G, SM = Smem<LOG2N, G>::BYTES;
+    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
+    int SM = Smem<LOG2N, G>::BYTES;
     if (n_locks <= 0) return cudaSuccess;
     constexpr auto k = rx_chanest_kernel<LOG2N, G>;
     LaunchDims d;
