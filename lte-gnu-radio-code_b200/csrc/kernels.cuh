@@ -166,6 +166,9 @@ __device__ __forceinline__ float flip_sign_of(float mag, float x) {       // mag
 }
 __device__ __forceinline__ unsigned neg_bit(float x) { return __float_as_uint(x) >> 31; }
 
+// append the sign bit of x to an MSB-first bit accumulator: one funnel shift per bit
+__device__ __forceinline__ unsigned push_sign(unsigned acc, float x) { return __funnelshift_l(__float_as_uint(x), acc, 1); }
+
 template <int BPS> struct Demapper {
     static constexpr float A = BPS == 2 ? 0.70710678118654752440f
                                         : (BPS == 4 ? 0.31622776601683793320f : 0.15430334996209191026f);
@@ -179,28 +182,31 @@ template <int BPS> struct Demapper {
         } else if (BPS == 2) {
             L[0] = -c * z.x;
             L[1] = -c * z.y;
-            bits = (neg_bit(z.x) << 1) | neg_bit(z.y);
+            bits = push_sign(push_sign(0u, z.x), z.y);
         } else if (BPS == 4) {
             const float ux = fabsf(z.x) - 2.f * A, uy = fabsf(z.y) - 2.f * A;
             L[0] = flip_sign_of(c * (fabsf(z.x) + fmaxf(ux, 0.f)), z.x);
             L[1] = flip_sign_of(c * (fabsf(z.y) + fmaxf(uy, 0.f)), z.y);
             L[2] = c * ux;
             L[3] = c * uy;
-            bits = (neg_bit(z.x) << 3) | (neg_bit(z.y) << 2) | ((neg_bit(ux) ^ 1u) << 1) | (neg_bit(uy) ^ 1u);
+            // hard bits = [x<0, y<0, |x|>2a, |y|>2a]: the last two are the inverted signs of ux, uy
+            bits = push_sign(push_sign(push_sign(push_sign(0u, z.x), z.y), ux), uy) ^ 3u;
         } else {
+            // with m2 = max(t-2a,0), m4 = max(t-4a,0), m6 = max(t-6a,0):
+            //   b0: -sgn(x) c (t + m2 + m4 + m6)    b1: c (2t - 6a - m2 + m6)    b2: c (2 m4 - t + 2a)
             float a0[2], a1[2], a2[2];
             const float xs[2] = {z.x, z.y};
+            const float c2 = 2.f * c, k1 = -6.f * A * c, k2 = 2.f * A * c;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const float t = fabsf(xs[i]);
-                const float u2 = t - 2.f * A, u4 = t - 4.f * A, u6 = t - 6.f * A;
-                a0[i] = flip_sign_of(c * (t + fmaxf(u2, 0.f) + fmaxf(u4, 0.f) + fmaxf(u6, 0.f)), xs[i]);
-                a1[i] = c * (u4 + fminf(u2, 0.f) + fmaxf(u6, 0.f));
-                a2[i] = c * (fabsf(u4) - 2.f * A);
+                const float m2 = fmaxf(t - 2.f * A, 0.f), m4 = fmaxf(t - 4.f * A, 0.f), m6 = fmaxf(t - 6.f * A, 0.f);
+                a0[i] = flip_sign_of(c * ((t + m2) + (m4 + m6)), xs[i]);
+                a1[i] = fmaf(c, m6 - m2, fmaf(c2, t, k1));
+                a2[i] = fmaf(c2, m4, fmaf(-c, t, k2));
             }
             L[0] = a0[0]; L[1] = a0[1]; L[2] = a1[0]; L[3] = a1[1]; L[4] = a2[0]; L[5] = a2[1];
-            bits = (neg_bit(z.x) << 5) | (neg_bit(z.y) << 4) | ((unsigned)(a1[0] > 0.f) << 3) |
-                   ((unsigned)(a1[1] > 0.f) << 2) | ((unsigned)(a2[0] > 0.f) << 1) | (unsigned)(a2[1] > 0.f);
+            bits = push_sign(push_sign(push_sign(push_sign(push_sign(push_sign(0u, z.x), z.y), a1[0]), a1[1]), a2[0]), a2[1]) ^ 15u;
         }
     }
 };
@@ -275,13 +281,17 @@ __device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict
             out[b] = (uint8_t)((((w.x * 0x08040201u) >> 24) << 4) | ((w.y * 0x08040201u) >> 24));
         }
     } else {
-        const int quads = (nbytes + 2) / 3;
-        for (int q = j; q < quads; q += T) {
-            const unsigned w = *reinterpret_cast<const uint32_t *>(hb + 4 * q);
-            const unsigned v = ((w & 63u) << 18) | (((w >> 8) & 63u) << 12) | (((w >> 16) & 63u) << 6) | (w >> 24);
-            if (3 * q + 0 < nbytes) out[3 * q + 0] = (uint8_t)(v >> 16);
-            if (3 * q + 1 < nbytes) out[3 * q + 1] = (uint8_t)(v >> 8);
-            if (3 * q + 2 < nbytes) out[3 * q + 2] = (uint8_t)v;
+        // 64-QAM: 16 bins (one 128-bit read) -> four 24-bit groups -> three 32-bit words
+        const int nchunks = (nbytes + 11) / 12;
+        for (int c = j; c < nchunks; c += T) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(hb + 16 * c);
+            auto g24 = [](unsigned x) { return ((x & 63u) << 18) | (((x >> 8) & 63u) << 12) | (((x >> 16) & 63u) << 6) | (x >> 24); };
+            const unsigned v0 = g24(w.x), v1 = g24(w.y), v2 = g24(w.z), v3 = g24(w.w);   // bytes (msb..lsb) = b0 b1 b2
+            const int rem = nbytes - 12 * c;
+            uint8_t *p = out + 12 * c;
+            store_chunk(p, __byte_perm(v0, v1, 0x6012), rem);
+            if (rem > 4) store_chunk(p + 4, __byte_perm(v1, v2, 0x5601), rem - 4);
+            if (rem > 8) store_chunk(p + 8, __byte_perm(v2, v3, 0x4560), rem - 8);
         }
     }
 }
