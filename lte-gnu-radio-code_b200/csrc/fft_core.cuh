@@ -1,11 +1,12 @@
-// fft_core.cuh -- batched power-of-two FFT for one "symbol group" of T = N/8 threads.
+// fft_core.cuh -- batched power-of-two FFT for one "symbol group" of T = N/PPT threads.
 //
-// Every thread keeps 8 complex points in registers.  The transform is a Stockham autosort
-// sequence of radix-8 passes followed by at most one radix-4 or radix-2 pass; between passes the
-// group exchanges data through shared memory (two ping-pong buffers, one group barrier per
-// exchange).  Invariants used by every kernel in this library:
+// Every thread keeps PPT complex points in registers (PPT = 8 for N <= 512, 16 above: half the
+// threads, two exchanges instead of three at N = 2048, twice the independent work per thread).
+// The transform is a Stockham autosort sequence of radix-PPT passes followed by at most one smaller
+// power-of-two pass; between passes the group exchanges data through shared memory (two ping-pong
+// buffers, one group barrier per exchange).  Invariants used by every kernel in this library:
 //
-//   * before each pass and after the last one, thread j holds element  j + m*T  in v[m], m=0..7.
+//   * before each pass and after the last one, thread j holds element  j + m*T  in v[m], m=0..PPT-1.
 //     Inputs can therefore be loaded straight from HBM with warp-contiguous 8-byte accesses and
 //     the output bins come out warp-contiguous too -- no staging pass on either side;
 //   * pass twiddles live in a per-CTA shared-memory table laid out [pass][q][j mod Ns], so lanes
@@ -37,38 +38,74 @@ template <bool INV> __device__ __forceinline__ float2 mul_mi(float2 a) {
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 
-// pass structure: N8 radix-8 passes, then one radix-4 (LOG2N%3==2) or radix-2 (LOG2N%3==1) pass
-__host__ __device__ constexpr int fft_radix(int log2n, int p) { return p < log2n / 3 ? 8 : (1 << (log2n % 3)); }
-__host__ __device__ constexpr int fft_ns(int log2n, int p) { return 1 << (3 * (p < log2n / 3 ? p : log2n / 3)); }
+// pass structure: NFULL radix-PPT passes, then one pass of radix 2^(LOG2N mod log2 PPT) if that is > 1
+__host__ __device__ constexpr int fft_lp(int ppt) { return ppt == 16 ? 4 : 3; }
+__host__ __device__ constexpr int fft_radix(int log2n, int ppt, int p) {
+    return p < log2n / fft_lp(ppt) ? ppt : (1 << (log2n % fft_lp(ppt)));
+}
+__host__ __device__ constexpr int fft_ns(int log2n, int ppt, int p) {
+    return 1 << (fft_lp(ppt) * (p < log2n / fft_lp(ppt) ? p : log2n / fft_lp(ppt)));
+}
 // shared twiddle table: pass p >= 1 holds (R-1) rows of Ns entries, row q-1 entry r = W_N^(q*r*N/(Ns*R))
-__host__ __device__ constexpr int fft_tw_off(int log2n, int p) {
+__host__ __device__ constexpr int fft_tw_off(int log2n, int ppt, int p) {
     int o = 0;
-    for (int i = 1; i < p; ++i) o += (fft_radix(log2n, i) - 1) * fft_ns(log2n, i);
+    for (int i = 1; i < p; ++i) o += (fft_radix(log2n, ppt, i) - 1) * fft_ns(log2n, ppt, i);
     return o;
 }
 
-template <int LOG2N> struct FftCfg {
+template <int LOG2N_, int PPT_> struct FftCfg {
+    static constexpr int LOG2N = LOG2N_, PPT = PPT_;
     static constexpr int N = 1 << LOG2N;
-    static constexpr int T = N / 8;                       // threads per symbol group
-    static constexpr int N8 = LOG2N / 3;                  // number of radix-8 passes
-    static constexpr int REM = LOG2N % 3;                 // 0: none, 1: radix-2, 2: radix-4 last pass
-    static constexpr int NPASS = N8 + (REM ? 1 : 0);
+    static constexpr int T = N / PPT;                     // threads per symbol group
+    static constexpr int LP = fft_lp(PPT);
+    static constexpr int NFULL = LOG2N / LP;              // number of radix-PPT passes
+    static constexpr int REM = LOG2N % LP;                // log2 of the last pass' radix (0: none)
+    static constexpr int NPASS = NFULL + (REM ? 1 : 0);
     static constexpr int NEXCH = NPASS - 1;               // shared-memory exchanges per transform
-    static constexpr int TW_ENTRIES = fft_tw_off(LOG2N, NPASS);
+    static constexpr int TW_ENTRIES = fft_tw_off(LOG2N, PPT, NPASS);
     // padded buffer length in complex slots; N == 64 uses a pad-per-8 layout (see lay())
     static constexpr int BUF = (LOG2N == 6) ? 72 : N;
-    __host__ __device__ static constexpr int radix(int p) { return fft_radix(LOG2N, p); }
-    __host__ __device__ static constexpr int ns(int p) { return fft_ns(LOG2N, p); }
-    __host__ __device__ static constexpr int tw_off(int p) { return fft_tw_off(LOG2N, p); }
+    __host__ __device__ static constexpr int radix(int p) { return fft_radix(LOG2N, PPT, p); }
+    __host__ __device__ static constexpr int ns(int p) { return fft_ns(LOG2N, PPT, p); }
+    __host__ __device__ static constexpr int tw_off(int p) { return fft_tw_off(LOG2N, PPT, p); }
 };
 
-// Exchange layout for the buffer written by pass P (Ns = 8^P):
-//   N == 64            : i + (i >> 3)             (two 8-lane groups share a half-warp; base stride 72)
-//   Ns == 1  (P == 0)  : i ^ ((i >> 4) & 7)       stride-8 scatter -> distinct bank pairs
-//   Ns == 8  (P == 1)  : i ^ ((i >> 3) & 8)       bit 6 folded into bit 3
-//   Ns >= 64           : identity (writes are already lane-contiguous)
-template <int LOG2N, int P> __device__ __forceinline__ int lay(int i) {
-    if (LOG2N == 6) return i + (i >> 3);
+// Points per thread for each transform size and kernel family (overridable for A/B runs, e.g.
+// -DOFDM_PPT_RX_4096=8).  Measured on B200 (tools/sweep_minb.sh): 16 points per thread speed the
+// transmitter up by 20-28 % at N >= 1024 and the receiver by 14 % at N = 4096; at N = 1024/2048 the
+// receiver also carries 16 equaliser gains per thread and is faster with 8.
+#ifndef OFDM_PPT_TX_LARGE
+#define OFDM_PPT_TX_LARGE 16
+#endif
+#ifndef OFDM_PPT_RX_1024
+#define OFDM_PPT_RX_1024 8
+#endif
+#ifndef OFDM_PPT_RX_2048
+#define OFDM_PPT_RX_2048 8
+#endif
+#ifndef OFDM_PPT_RX_4096
+#define OFDM_PPT_RX_4096 16
+#endif
+template <int LOG2N> struct PptRx {
+    static constexpr int value = LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RX_1024 : (LOG2N == 11 ? OFDM_PPT_RX_2048 : OFDM_PPT_RX_4096));
+};
+template <int LOG2N> struct PptTx {
+    static constexpr int value = LOG2N >= 10 ? OFDM_PPT_TX_LARGE : 8;
+};
+template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value>;
+template <int LOG2N> using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value>;
+
+// Exchange layout for the buffer written by pass P (Ns = PPT^P), chosen so that the scattered write
+// out[(j/Ns)*Ns*R + j%Ns + q*Ns] and the contiguous read in[j + m*T] both hit 16 distinct 8-byte
+// bank pairs per half-warp:
+//   N == 64 (PPT 8)    : i + (i >> 3)             (two 8-lane groups share a half-warp; base stride 72)
+//   PPT 8,  P == 0     : i ^ ((i >> 4) & 7)       stride-8 scatter
+//   PPT 8,  P == 1     : i ^ ((i >> 3) & 8)       bit 6 folded into bit 3
+//   PPT 16, P == 0     : i ^ ((i >> 4) & 15)      stride-16 scatter
+//   otherwise          : identity (writes are already lane-contiguous)
+template <class C, int P> __device__ __forceinline__ int lay(int i) {
+    if (C::LOG2N == 6) return i + (i >> 3);
+    if (C::PPT == 16) return P == 0 ? (i ^ ((i >> 4) & 15)) : i;
     if (P == 0) return i ^ ((i >> 4) & 7);
     if (P == 1) return i ^ ((i >> 3) & 8);
     return i;
@@ -113,6 +150,50 @@ template <bool INV> __device__ __forceinline__ void bfly8(float2 (&a)[8]) {
     a[1] = c0; a[3] = c1; a[5] = c2; a[7] = c3;
 }
 
+// 16-point DFT as 4 x 4 (n = 4*n1 + n2, k = k1 + 4*k2): DFT4 over n1, twiddle W16^(n2*k1), DFT4 over n2.
+template <bool INV> __device__ __forceinline__ float2 mul_w16(float2 a, int m) {
+    // W16^m = exp(-2*pi*i*m/16) (forward), conjugate for the inverse; m in {1,2,3,4,6,9}
+    const float c = 0.92387953251128675613f, s = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    float wr, wi;
+    switch (m) {
+        case 1: wr = c; wi = -s; break;
+        case 2: wr = h; wi = -h; break;
+        case 3: wr = s; wi = -c; break;
+        case 4: wr = 0.f; wi = -1.f; break;
+        case 6: wr = -h; wi = -h; break;
+        default: wr = -c; wi = s; break;   // 9
+    }
+    if (INV) wi = -wi;
+    if (m == 4) return make_float2(-a.y * wi, a.x * wi);
+    if (m == 2 || m == 6) {                 // |wr| == |wi|: two adds, two multiplies
+        const float sr = a.x * wr, si = a.y * wr;                       // wr = +-h
+        return (wi == wr) ? make_float2(sr - si, sr + si) : make_float2(sr + si, si - sr);
+    }
+    return make_float2(fmaf(a.x, wr, -a.y * wi), fmaf(a.x, wi, a.y * wr));
+}
+
+template <bool INV> __device__ __forceinline__ void bfly16(float2 (&a)[16]) {
+    float2 y[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        float2 t0 = a[n2], t1 = a[4 + n2], t2 = a[8 + n2], t3 = a[12 + n2];
+        bfly4<INV>(t0, t1, t2, t3);                 // k1 = 0..3
+        y[n2] = t0;
+        y[4 + n2] = n2 ? mul_w16<INV>(t1, n2) : t1;         // y[4*k1 + n2] *= W16^(n2*k1)
+        y[8 + n2] = n2 ? mul_w16<INV>(t2, 2 * n2) : t2;
+        y[12 + n2] = n2 ? mul_w16<INV>(t3, 3 * n2) : t3;
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        float2 t0 = y[4 * k1], t1 = y[4 * k1 + 1], t2 = y[4 * k1 + 2], t3 = y[4 * k1 + 3];
+        bfly4<INV>(t0, t1, t2, t3);                 // k2 = 0..3
+        a[k1] = t0;
+        a[k1 + 4] = t1;
+        a[k1 + 8] = t2;
+        a[k1 + 12] = t3;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // group barrier: T <= 32 -> the group lives inside one warp; otherwise either the whole CTA is one
 // group (bar 0) or several groups share a CTA and use named barriers 1..15.
@@ -128,9 +209,8 @@ template <int T, int GROUPS> __device__ __forceinline__ void group_sync(int gid)
 }
 
 // Fill the CTA's shared twiddle table from the global table tw[k] = exp(-2*pi*i*k/N).
-template <int LOG2N>
+template <class C>
 __device__ __forceinline__ void fill_twiddles(float2 *tws, const float2 *__restrict__ tw, int tid, int nthreads) {
-    using C = FftCfg<LOG2N>;
 #pragma unroll
     for (int p = 1; p < C::NPASS; ++p) {
         const int R = C::radix(p), Ns = C::ns(p), off = C::tw_off(p);
@@ -146,63 +226,65 @@ template <bool INV> __device__ __forceinline__ float2 twmul(float2 a, float2 w) 
     return INV ? cmulc(a, w) : cmul(a, w);
 }
 
-// One pass P of the transform, fully unrolled by the caller through template recursion.
-template <int LOG2N, bool INV, int GROUPS, int P> struct Pass {
-    using C = FftCfg<LOG2N>;
-    static __device__ __forceinline__ void run(float2 (&v)[8], const float2 *tws, float2 *buf0, float2 *buf1,
+// radix-R butterfly on registers v[b], v[b+B], ..., v[b+(R-1)B]
+template <bool INV, int R, int B, int PPT> __device__ __forceinline__ void bfly_strided(float2 (&v)[PPT], int b) {
+    if constexpr (R == 16) {
+        bfly16<INV>(v);
+    } else if constexpr (R == 8) {
+        float2 t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = v[b + q * B];
+        bfly8<INV>(t);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[b + q * B] = t[q];
+    } else if constexpr (R == 4) {
+        bfly4<INV>(v[b], v[b + B], v[b + 2 * B], v[b + 3 * B]);
+    } else {
+        bfly2<INV>(v[b], v[b + B]);
+    }
+}
+
+// One pass P of the transform, fully unrolled through template recursion.  Butterfly b of a thread
+// works on registers b + q*B (B = PPT/R butterflies per thread), i.e. on elements j + b*T + q*N/R.
+template <class C, bool INV, int GROUPS, int P> struct Pass {
+    static __device__ __forceinline__ void run(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1,
                                                int j, int gid, int &pp) {
-        constexpr int R = C::radix(P), Ns = C::ns(P);
+        constexpr int R = C::radix(P), Ns = C::ns(P), B = C::PPT / R;
         if (P > 0) {
             constexpr int off = C::tw_off(P);
-            if (R == 8) {
-                const float2 *t = tws + off + (j & (Ns - 1));
 #pragma unroll
-                for (int q = 1; q < 8; ++q) v[q] = twmul<INV>(v[q], t[(q - 1) * Ns]);
-            } else if (R == 4) {
+            for (int b = 0; b < B; ++b) {
+                const float2 *t = tws + off + ((j + b * C::T) & (Ns - 1));
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const float2 *t = tws + off + ((j + b * C::T) & (Ns - 1));
-#pragma unroll
-                    for (int q = 1; q < 4; ++q) v[b + 2 * q] = twmul<INV>(v[b + 2 * q], t[(q - 1) * Ns]);
-                }
-            } else {
-#pragma unroll
-                for (int b = 0; b < 4; ++b) v[b + 4] = twmul<INV>(v[b + 4], tws[off + ((j + b * C::T) & (Ns - 1))]);
+                for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], t[(q - 1) * Ns]);
             }
         }
-        if (R == 8) {
-            bfly8<INV>(v);
-        } else if (R == 4) {
-            bfly4<INV>(v[0], v[2], v[4], v[6]);
-            bfly4<INV>(v[1], v[3], v[5], v[7]);
-        } else {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bfly2<INV>(v[b], v[b + 4]);
-        }
+        for (int b = 0; b < B; ++b) bfly_strided<INV, R, B, C::PPT>(v, b);
         if (P < C::NPASS - 1) {
-            // only radix-8 passes are followed by an exchange
+            // only full-radix passes are followed by an exchange (B == 1)
             float2 *buf = (pp & 1) ? buf1 : buf0;
             pp ^= 1;
-            const int e = (j / Ns) * (Ns * 8) + (j & (Ns - 1));
+            const int e = (j / Ns) * (Ns * C::PPT) + (j & (Ns - 1));
 #pragma unroll
-            for (int q = 0; q < 8; ++q) buf[lay<LOG2N, P>(e + q * Ns)] = v[q];
+            for (int q = 0; q < C::PPT; ++q) buf[lay<C, P>(e + q * Ns)] = v[q];
             group_sync<C::T, GROUPS>(gid);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = buf[lay<LOG2N, P>(j + m * C::T)];
-            Pass<LOG2N, INV, GROUPS, P + 1>::run(v, tws, buf0, buf1, j, gid, pp);
+            for (int m = 0; m < C::PPT; ++m) v[m] = buf[lay<C, P>(j + m * C::T)];
+            Pass<C, INV, GROUPS, P + 1>::run(v, tws, buf0, buf1, j, gid, pp);
         }
     }
 };
-template <int LOG2N, bool INV, int GROUPS> struct Pass<LOG2N, INV, GROUPS, 4> {
-    static __device__ __forceinline__ void run(float2 (&)[8], const float2 *, float2 *, float2 *, int, int, int &) {}
+template <class C, bool INV, int GROUPS> struct Pass<C, INV, GROUPS, 4> {
+    static __device__ __forceinline__ void run(float2 (&)[C::PPT], const float2 *, float2 *, float2 *, int, int, int &) {}
 };
 
 // In-place transform of the group's symbol.  pp is the running ping-pong selector (kept across
 // calls so that consecutive transforms never need a second barrier per exchange).
-template <int LOG2N, bool INV, int GROUPS>
-__device__ __forceinline__ void fft_group(float2 (&v)[8], const float2 *tws, float2 *buf0, float2 *buf1, int j,
+template <class C, bool INV, int GROUPS>
+__device__ __forceinline__ void fft_group(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1, int j,
                                           int gid, int &pp) {
-    Pass<LOG2N, INV, GROUPS, 0>::run(v, tws, buf0, buf1, j, gid, pp);
+    Pass<C, INV, GROUPS, 0>::run(v, tws, buf0, buf1, j, gid, pp);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -74,31 +74,31 @@ __device__ __forceinline__ int used_index(int k, int N, int n) {
     return -1;
 }
 
-// Where thread j's eight bins (j + m*T) land in a used-bin list of length n.  m < 4 is the positive
-// half of the spectrum (incl. DC), m >= 4 the negative half; inside a half consecutive m are T apart
+// Where thread j's PPT bins (j + m*T) land in a used-bin list of length n.  m < PPT/2 is the positive
+// half of the spectrum (incl. DC), m >= PPT/2 the negative half; inside a half consecutive m are T apart
 // in the output as well, so a store is  half_base + m*T  with m*T a compile-time constant.
 struct BinMap {
-    int base_p;        // output index of bin j (m = 0) if it were used:      j - 1 + n/2
-    int base_n;        // output index of bin j + 4T (m = 4) if it were used: j + 4T - (N - n/2)
+    int base_p;        // output index of bin j (m = 0) if it were used:            j - 1 + n/2
+    int base_n;        // output index of bin j + N/2 (m = PPT/2) if it were used:  j + N/2 - (N - n/2)
     unsigned mask;     // bit m set <=> bin j + m*T is in the list
 };
-template <int T> __device__ __forceinline__ BinMap make_bin_map(int n, int j) {
-    constexpr int N = 8 * T;
+template <int T, int PPT> __device__ __forceinline__ BinMap make_bin_map(int n, int j) {
+    constexpr int N = PPT * T, H = PPT / 2;
     const int h = n >> 1;
     BinMap b;
     b.base_p = j - 1 + h;
-    b.base_n = j + 4 * T - (N - h);
+    b.base_n = j + H * T - (N - h);
     b.mask = 0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < PPT; ++m) {
         const int k = j + m * T;
-        const bool used = (m < 4) ? (k >= 1 && k <= h) : (k >= N - h);
+        const bool used = (m < H) ? (k >= 1 && k <= h) : (k >= N - h);
         b.mask |= used ? (1u << m) : 0u;
     }
     return b;
 }
-template <int T> __device__ __forceinline__ int bin_out(const BinMap &b, int m) {
-    return (m < 4 ? b.base_p : b.base_n - 4 * T) + m * T;
+template <int T, int PPT> __device__ __forceinline__ int bin_out(const BinMap &b, int m) {
+    return (m < PPT / 2 ? b.base_p : b.base_n - (PPT / 2) * T) + m * T;
 }
 
 __device__ __forceinline__ float2 ld_stream(const float2 *p) {      // read-once data: do not allocate in L1
@@ -107,18 +107,18 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p) {      // read-once
     return r;
 }
 
-// this thread's 8 samples of the N-sample window that opens at `start` (zero beyond the buffer)
-template <int T>
-__device__ __forceinline__ void load8(float2 (&v)[8], const float2 *__restrict__ x, long long start, long long n,
-                                      int j) {
-    constexpr int N = 8 * T;
+// this thread's PPT samples of the N-sample window that opens at `start` (zero beyond the buffer)
+template <int T, int PPT>
+__device__ __forceinline__ void load_pts(float2 (&v)[PPT], const float2 *__restrict__ x, long long start, long long n,
+                                         int j) {
+    constexpr int N = PPT * T;
     if (start >= 0 && start + N <= n) {
         const float2 *p = x + start + j;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = ld_stream(p + m * T);
+        for (int m = 0; m < PPT; ++m) v[m] = ld_stream(p + m * T);
     } else {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
+        for (int m = 0; m < PPT; ++m) {
             const long long i = start + j + m * T;
             v[m] = (i >= 0 && i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
         }
@@ -297,13 +297,12 @@ __device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict
 }
 
 // shared-memory carve-up per CTA
-template <int LOG2N, int GROUPS> struct Smem {
-    using C = FftCfg<LOG2N>;
+template <class C, int GROUPS> struct Smem {
     static constexpr int THREADS = C::T * GROUPS;
-    static constexpr int GSTRIDE = (LOG2N == 6) ? (2 * C::BUF + 8) : 2 * C::BUF;   // complex slots per group
+    static constexpr int GSTRIDE = (C::LOG2N == 6) ? (2 * C::BUF + 8) : 2 * C::BUF;   // complex slots per group
     static constexpr int FFT_BYTES = GROUPS * GSTRIDE * 8;
     static constexpr int TW_BYTES = C::TW_ENTRIES * 8;                              // pass twiddles, shared by the CTA
-    static constexpr int STAGE_BYTES = THREADS * 8 * 8;                             // next symbol: 8 samples per thread
+    static constexpr int STAGE_BYTES = THREADS * C::PPT * 8;                        // next symbol: PPT samples per thread
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
     static constexpr int HB_STRIDE = C::N + 16;                                     // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
@@ -331,23 +330,23 @@ template <int LOG2N, int GROUPS> struct Smem {
     __device__ static float2 *hp(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s + OFF_HP) + gid * (C::N / 2); }
 };
 
-// Asynchronous prefetch of this thread's 8 samples of the window that opens at `start` into its
+// Asynchronous prefetch of this thread's PPT samples of the window that opens at `start` into its
 // private shared-memory slots (LDGSTS, no registers held while the data is in flight).  Samples
 // outside [0, n) are zero-filled by the hardware (src-size 0).  The thread that issued the copies
 // is the only one that reads them back, so cp.async.wait_group is the only synchronisation needed.
-template <int T, int THREADS>
-__device__ __forceinline__ void prefetch8(float2 *stage, const float2 *__restrict__ x, long long start, long long n,
-                                          int j, int tid) {
-    constexpr int N = 8 * T;
+template <int T, int PPT, int THREADS>
+__device__ __forceinline__ void prefetch_pts(float2 *stage, const float2 *__restrict__ x, long long start, long long n,
+                                             int j, int tid) {
+    constexpr int N = PPT * T;
     const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + tid);
     if (start >= 0 && start + N <= n) {
         const float2 *p = x + start + j;
 #pragma unroll
-        for (int m = 0; m < 8; ++m)
+        for (int m = 0; m < PPT; ++m)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + m * THREADS * 8), "l"(p + m * T) : "memory");
     } else {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
+        for (int m = 0; m < PPT; ++m) {
             const long long i = start + j + m * T;
             const bool ok = (i >= 0 && i < n);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + m * THREADS * 8),
@@ -356,10 +355,10 @@ __device__ __forceinline__ void prefetch8(float2 *stage, const float2 *__restric
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
-template <int THREADS> __device__ __forceinline__ void take8(float2 (&v)[8], const float2 *stage, int tid) {
+template <int PPT, int THREADS> __device__ __forceinline__ void take_pts(float2 (&v)[PPT], const float2 *stage, int tid) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-    for (int m = 0; m < 8; ++m) v[m] = stage[m * THREADS + tid];
+    for (int m = 0; m < PPT; ++m) v[m] = stage[m * THREADS + tid];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,14 +370,14 @@ template <int THREADS> __device__ __forceinline__ void take8(float2 (&v)[8], con
 //   (c[d] = sum_k ys_k e^{+j2pi dk/N} is an N-point inverse DFT sampled at d = 0..CP) instead of
 //   the reference's dense (CP+1) x MM matmul, then max / first argmax over d (:160-164).
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N>
-__device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2 (&v)[8], int s, int j,
-                                                float2 (&ys)[8], float2 (&ydup)[2], float &pw) {
-    constexpr int T = FftCfg<LOG2N>::T, N = FftCfg<LOG2N>::N;
+template <class C>
+__device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2 (&v)[C::PPT], int s, int j,
+                                                float2 (&ys)[C::PPT], float2 (&ydup)[2], float &pw) {
+    constexpr int T = C::T, N = C::N, PPT = C::PPT;
     const float2 *zb = P.zc_bin + s * N + j;
     const float *wb = P.w_bin + j;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < PPT; ++m) {
         pw = fmaf(__ldg(wb + m * T), cabs2(v[m]), pw);
         const float2 z = __ldg(zb + m * T);
         ys[m].x = fmaf(v[m].x, z.x, fmaf(-v[m].y, z.y, ys[m].x));
@@ -386,7 +385,7 @@ __device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2
     }
     if (P.dup_bin >= 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m)
+        for (int m = 0; m < PPT; ++m)
             if (j + m * T == P.dup_bin) {
                 ydup[0] = cadd(ydup[0], cmul(v[m], __ldg(P.zc_dup + 2 * s)));
                 ydup[1] = cadd(ydup[1], cmul(v[m], __ldg(P.zc_dup + 2 * s + 1)));
@@ -394,21 +393,20 @@ __device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2
     }
 }
 
-template <int LOG2N, int GROUPS>
-__device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&ys)[8], float pw, const float2 *tws,
+template <class C, int GROUPS>
+__device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&ys)[C::PPT], float pw, const float2 *tws,
                                             float2 *b0, float2 *b1, float *redf, unsigned long long *redu, int j,
                                             int gid, int &pp, float &p_est, float &peak, int &delay) {
-    using C = FftCfg<LOG2N>;
-    constexpr int T = C::T;
+    constexpr int T = C::T, PPT = C::PPT;
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     p_est = pw > 0.f ? sqrtf((float)P.mm / pw) : 0.f;
-    float2 c[8];
+    float2 c[C::PPT];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) c[m] = ys[m];
-    fft_group<LOG2N, true, GROUPS>(c, tws, b0, b1, j, gid, pp);
+    for (int m = 0; m < PPT; ++m) c[m] = ys[m];
+    fft_group<C, true, GROUPS>(c, tws, b0, b1, j, gid, pp);
     unsigned long long key = 0ull;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < PPT; ++m) {
         const int dd = j + m * T;
         if (dd <= P.cp) {
             const unsigned long long kk =
@@ -424,15 +422,14 @@ __device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&y
 // channel estimate + equaliser gain for this thread's 8 bins from the correlation sums.
 // H_k = rot_k * p_est * ys_k / ((1+1/x) * M0)        SynchAndChanEst.py:177-188
 // G_k = conj(H_k) / (|H_k|^2 + inv_reg) * rot_k      :237-246 (de-rotation folded into the gain)
-template <int LOG2N>
-__device__ __forceinline__ void chan_core(const DevParams &P, const float2 (&ys)[8], const float2 (&ydup)[2],
-                                          float p_est, int delay, float inv_reg, int j, float2 (&H)[8],
-                                          float2 (&G)[8]) {
-    using C = FftCfg<LOG2N>;
-    constexpr int T = C::T, N = C::N;
+template <class C>
+__device__ __forceinline__ void chan_core(const DevParams &P, const float2 (&ys)[C::PPT], const float2 (&ydup)[2],
+                                          float p_est, int delay, float inv_reg, int j, float2 (&H)[C::PPT],
+                                          float2 (&G)[C::PPT]) {
+    constexpr int T = C::T, N = C::N, PPT = C::PPT;
     const float sc = p_est * P.chanest_scale;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < PPT; ++m) {
         const int k = j + m * T;
         const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));   // exp(-j*2pi*d*k/N); rot = conj(w)
         float2 y = ys[m];
@@ -446,46 +443,45 @@ __device__ __forceinline__ void chan_core(const DevParams &P, const float2 (&ys)
 }
 
 // Everything a data symbol's epilogue needs that does not change from symbol to symbol.
-template <int LOG2N, int BPS> struct DataCtx {
+template <class C, int BPS> struct DataCtx {
     BinMap map;
     Demapper<BPS> dem;
     float sqrt_ndb;
     __device__ __forceinline__ DataCtx(const DevParams &P, int j)
-        : map(make_bin_map<FftCfg<LOG2N>::T>(P.ndb, j)), dem(P.llr_scale), sqrt_ndb(sqrtf((float)P.ndb)) {}
+        : map(make_bin_map<C::T, C::PPT>(P.ndb, j)), dem(P.llr_scale), sqrt_ndb(sqrtf((float)P.ndb)) {}
 };
 
 // equalise + demap + store one data symbol held in v[] (FFT output).  SynchAndChanEst.py:232-248.
-template <int LOG2N, int BPS, int GROUPS>
-__device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<LOG2N, BPS> &D, const float2 (&v)[8],
-                                              const float2 (&G)[8], long long row, float *redf, uint8_t *hb, int j,
+template <class C, int BPS, int GROUPS>
+__device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<C, BPS> &D, const float2 (&v)[C::PPT],
+                                              const float2 (&G)[C::PPT], long long row, float *redf, uint8_t *hb, int j,
                                               int gid, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                                               uint8_t *__restrict__ hard_out) {
-    using C = FftCfg<LOG2N>;
-    constexpr int T = C::T;
+    constexpr int T = C::T, PPT = C::PPT;
     const unsigned mask = D.map.mask;
     float pw = 0.f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m)
+    for (int m = 0; m < PPT; ++m)
         if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
     float2 *eqp = eq_out + row * P.ndb + D.map.base_p;
-    float2 *eqn = eq_out + row * P.ndb + (D.map.base_n - 4 * T);
+    float2 *eqn = eq_out + row * P.ndb + (D.map.base_n - (PPT / 2) * T);
     float *lp = llr_out + (row * P.ndb + D.map.base_p) * BPS;
-    float *ln = llr_out + (row * P.ndb + (D.map.base_n - 4 * T)) * BPS;
-    uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - 4 * T);
+    float *ln = llr_out + (row * P.ndb + (D.map.base_n - (PPT / 2) * T)) * BPS;
+    uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - (PPT / 2) * T);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < PPT; ++m) {
         if (mask & (1u << m)) {
             const float2 z = cscale(cmul(G[m], v[m]), p0);
-            __stcs((m < 4 ? eqp : eqn) + m * T, z);
+            __stcs((m < PPT / 2 ? eqp : eqn) + m * T, z);
             if (soft || hard) {
                 float Lb[BPS];
                 unsigned bits;
                 D.dem.run(z, Lb, bits);
                 if (soft) {
-                    float *q = (m < 4 ? lp : ln) + m * T * BPS;
+                    float *q = (m < PPT / 2 ? lp : ln) + m * T * BPS;
                     if (BPS == 1) {
                         __stcs(q, Lb[0]);
                     } else if (BPS == 4) {
@@ -496,7 +492,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
                             __stcs(reinterpret_cast<float2 *>(q + b), make_float2(Lb[b], Lb[b + 1]));
                     }
                 }
-                if (hard) (m < 4 ? hp : hn)[m * T] = (uint8_t)bits;
+                if (hard) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
             }
         }
     }
@@ -510,36 +506,35 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
 // estimate on its own comb pilots, linearly interpolated across the used-bin list and held constant
 // outside the outermost pilots (the oracle's np.interp).  Off the fast path: positions are recomputed
 // per bin because payload indices are no longer a fixed stride apart.
-template <int LOG2N, int BPS, int GROUPS>
-__device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const DataCtx<LOG2N, BPS> &D,
-                                                    const float2 (&v)[8], const float2 (&R)[8], long long row,
+template <class C, int BPS, int GROUPS>
+__device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const DataCtx<C, BPS> &D,
+                                                    const float2 (&v)[C::PPT], const float2 (&R)[C::PPT], long long row,
                                                     float *redf, uint8_t *hb, float2 *hp, int j, int gid,
                                                     float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                                                     uint8_t *__restrict__ hard_out) {
-    using C = FftCfg<LOG2N>;
-    constexpr int T = C::T;
+    constexpr int T = C::T, PPT = C::PPT;
     const unsigned mask = D.map.mask;
     float pw = 0.f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m)
+    for (int m = 0; m < PPT; ++m)
         if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;
-    float2 z[8];
+    float2 z[C::PPT];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < PPT; ++m) {
         z[m] = cscale(cmul(R[m], v[m]), p0);
         if (mask & (1u << m)) {
-            const PilotPos pp = pilot_pos(P, bin_out<T>(D.map, m));
+            const PilotPos pp = pilot_pos(P, bin_out<T, PPT>(D.map, m));
             if (pp.is_pilot) hp[pp.ip] = cmulc(z[m], __ldg(P.pilot_tx + j + m * T));   // LS: Y * conj(p), |p| = 1
         }
     }
     group_sync<T, GROUPS>(gid);
     const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < PPT; ++m) {
         if (mask & (1u << m)) {
-            const PilotPos pp = pilot_pos(P, bin_out<T>(D.map, m));
+            const PilotPos pp = pilot_pos(P, bin_out<T, PPT>(D.map, m));
             if (!pp.is_pilot) {
                 const float2 ha = hp[pp.ip], hb2 = hp[pp.ip + (pp.frac > 0.f ? 1 : 0)];
                 const float2 h = make_float2(fmaf(pp.frac, hb2.x - ha.x, ha.x), fmaf(pp.frac, hb2.y - ha.y, ha.y));
@@ -567,10 +562,9 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
     }
 }
 
-#define OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)                                            \
-    using C = FftCfg<LOG2N>;                                                           \
-    using S = Smem<LOG2N, GROUPS>;                                                     \
-    constexpr int T = C::T;                                                            \
+#define OFDM_KERNEL_PROLOGUE(GROUPS)                                                  \
+    using S = Smem<C, GROUPS>;                                                     \
+    constexpr int T = C::T, PPT = C::PPT;                                              \
     extern __shared__ __align__(16) unsigned char smem_raw[];                          \
     const int tid = threadIdx.x, gid = tid / T, j = tid % T;                           \
     float2 *b0 = S::buf0(smem_raw, gid), *b1 = b0 + C::BUF;                            \
@@ -582,45 +576,29 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
     float2 *hp = S::hp(smem_raw, gid);                                                 \
     (void)redu; (void)redf; (void)stage; (void)hp;                                     \
     for (int i = j; i < S::HB_STRIDE; i += T) hb[i] = 0;                               \
-    fill_twiddles<LOG2N>(S::tws(smem_raw), P.tw, tid, S::THREADS);                     \
+    fill_twiddles<C>(S::tws(smem_raw), P.tw, tid, S::THREADS);                              \
     __syncthreads();                                                                   \
     const long long total_groups = (long long)gridDim.x * GROUPS;                      \
     const long long gg = (long long)blockIdx.x * GROUPS + gid;                         \
     int pp = 0;
 
-// resident CTAs per SM the register allocator should aim for (threads per CTA = max(T,128));
-// overridable at build time for tuning sweeps:  make EXTRA="-DOFDM_MINB_SMALL=6 -DOFDM_MINB_2048=3"
+// Resident CTAs per SM the register allocator should aim for (threads per CTA = max(T,128)).
+// Receiver kernels hold the equaliser gains in registers and want ~128 (PPT 8) / ~255 (PPT 16)
+// registers per thread; the transmitter fits 128 with 16 points per thread.  Overridable at build
+// time for tuning sweeps, e.g.  make EXTRA="-DOFDM_MINB_SMALL=6".
 #ifndef OFDM_MINB_SMALL
 #define OFDM_MINB_SMALL 4
 #endif
-#ifndef OFDM_MINB_1024
-#define OFDM_MINB_1024 4
-#endif
-#ifndef OFDM_MINB_2048
-#define OFDM_MINB_2048 2
-#endif
-#ifndef OFDM_MINB_4096
-#define OFDM_MINB_4096 1
-#endif
-#ifndef OFDM_MINB_TX_SMALL
-#define OFDM_MINB_TX_SMALL 4
-#endif
-#ifndef OFDM_MINB_TX_1024
-#define OFDM_MINB_TX_1024 4
-#endif
-#ifndef OFDM_MINB_TX_2048
-#define OFDM_MINB_TX_2048 2
-#endif
-#ifndef OFDM_MINB_TX_4096
-#define OFDM_MINB_TX_4096 1
-#endif
-template <int LOG2N> struct MinBlocksTx {
-    static constexpr int value = LOG2N <= 9 ? OFDM_MINB_TX_SMALL
-                                            : (LOG2N == 10 ? OFDM_MINB_TX_1024 : (LOG2N == 11 ? OFDM_MINB_TX_2048 : OFDM_MINB_TX_4096));
+template <class C> struct MinBlocks {
+    static constexpr int THREADS = C::T >= 128 ? C::T : 128;
+    static constexpr int REGS = C::PPT == 16 ? 255 : 128;
+    static constexpr int byregs = 65536 / (THREADS * REGS);
+    static constexpr int value = C::LOG2N <= 9 ? OFDM_MINB_SMALL : (byregs < 1 ? 1 : byregs);
 };
-template <int LOG2N> struct MinBlocks {
-    static constexpr int value =
-        LOG2N <= 9 ? OFDM_MINB_SMALL : (LOG2N == 10 ? OFDM_MINB_1024 : (LOG2N == 11 ? OFDM_MINB_2048 : OFDM_MINB_4096));
+template <class C> struct MinBlocksTx {
+    static constexpr int THREADS = C::T >= 128 ? C::T : 128;
+    static constexpr int byregs = 65536 / (THREADS * 128);
+    static constexpr int value = C::LOG2N <= 9 ? OFDM_MINB_SMALL : (byregs < 1 ? 1 : byregs);
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -628,47 +606,47 @@ template <int LOG2N> struct MinBlocks {
 //     The group walks its frames symbol by symbol; while symbol q is transformed the samples of
 //     symbol q+1 (next symbol of the frame, or the preamble of the group's next frame) are in flight.
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N, int BPS, int GROUPS, bool PIL>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
+template <class C, int BPS, int GROUPS, bool PIL>
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
                  float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, float2 *__restrict__ H_out,
                  float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
-    OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
+    OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
     const int L = N + P.cp, fs = P.m0 + P.d;
-    const DataCtx<LOG2N, BPS> D(P, j);
+    const DataCtx<C, BPS> D(P, j);
     const long long last_frame = n_frames - 1;
     const long long off0 = first + P.cp - P.sync_advance;
     long long f = gg < last_frame ? gg : last_frame;
     long long pos = off0 + f * frame_stride;
-    prefetch8<T, S::THREADS>(stage, x, pos, n_samples, j, tid);
+    prefetch_pts<T, PPT, S::THREADS>(stage, x, pos, n_samples, j, tid);
     for (int it = 0; it < iters; ++it) {
         long long fn = gg + (long long)(it + 1) * total_groups;
         fn = fn < last_frame ? fn : last_frame;
         const long long npos = off0 + fn * frame_stride;
-        float2 ys[8], ydup[2], G[8];
+        float2 ys[C::PPT], ydup[2], G[C::PPT];
         float pw = 0.f;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
+        for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
         ydup[0] = ydup[1] = make_float2(0.f, 0.f);
         for (int s = 0; s < fs; ++s) {
-            float2 cur[8];
-            take8<S::THREADS>(cur, stage, tid);
+            float2 cur[C::PPT];
+            take_pts<PPT, S::THREADS>(cur, stage, tid);
             // request the next symbol (the last request of the kernel re-reads a valid window)
-            prefetch8<T, S::THREADS>(stage, x, (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos, n_samples, j, tid);
-            fft_group<LOG2N, false, GROUPS>(cur, tws, b0, b1, j, gid, pp);
+            prefetch_pts<T, PPT, S::THREADS>(stage, x, (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos, n_samples, j, tid);
+            fft_group<C, false, GROUPS>(cur, tws, b0, b1, j, gid, pp);
             if (s < P.m0) {
-                sync_accumulate<LOG2N>(P, cur, s, j, ys, ydup, pw);
+                sync_accumulate<C>(P, cur, s, j, ys, ydup, pw);
                 if (s == P.m0 - 1) {
                     float p_est, peak;
                     int delay;
-                    float2 H[8];
-                    sync_finish<LOG2N, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
-                    chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq, j, H, G);
+                    float2 H[C::PPT];
+                    sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+                    chan_core<C>(P, ys, ydup, p_est, delay, P.inv_reg_eq, j, H, G);
                     if (PIL) {                               // pilot mode equalises per symbol: keep only the rotation
 #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
+                        for (int m = 0; m < PPT; ++m) {
                             const float2 w = __ldg(P.tw + ((delay * (j + m * T)) & (N - 1)));
                             G[m] = make_float2(w.x, -w.y);
                         }
@@ -680,14 +658,14 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                     }
                     if (H_out != nullptr) {
 #pragma unroll
-                        for (int m = 0; m < 8; ++m) H_out[f * N + j + m * T] = H[m];
+                        for (int m = 0; m < PPT; ++m) H_out[f * N + j + m * T] = H[m];
                     }
                 }
             } else if (PIL) {
-                data_epilogue_pilot<LOG2N, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, hp, j, gid, eq_out,
+                data_epilogue_pilot<C, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, hp, j, gid, eq_out,
                                                         llr_out, hard_out);
             } else {
-                data_epilogue<LOG2N, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, j, gid, eq_out, llr_out,
+                data_epilogue<C, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, j, gid, eq_out, llr_out,
                                                   hard_out);
             }
         }
@@ -700,31 +678,31 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
 // ------------------------------------------------------------------------------------------------
 // K2  sliding search: one trial per group iteration.  Outputs max|c| and argmax per trial.
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
+template <class C, int GROUPS>
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
                       long long stride, long long n_trials, int iters, float *__restrict__ peak_out,
                       int *__restrict__ delay_out) {
-    OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
+    OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
     const int L = N + P.cp;
     for (int it = 0; it < iters; ++it) {
         long long t = gg + (long long)it * total_groups;
         t = t < n_trials - 1 ? t : n_trials - 1;
         const long long pos = first_start + t * stride;
-        float2 ys[8], ydup[2];
+        float2 ys[C::PPT], ydup[2];
         float pw = 0.f, p_est, peak;
         int delay;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
+        for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
         ydup[0] = ydup[1] = make_float2(0.f, 0.f);
         for (int s = 0; s < P.m0; ++s) {
-            float2 v[8];
-            load8<T>(v, x, pos + (long long)s * L, n_samples, j);
-            fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
-            sync_accumulate<LOG2N>(P, v, s, j, ys, ydup, pw);
+            float2 v[C::PPT];
+            load_pts<T, PPT>(v, x, pos + (long long)s * L, n_samples, j);
+            fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
+            sync_accumulate<C>(P, v, s, j, ys, ydup, pw);
         }
-        sync_finish<LOG2N, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+        sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
         if (j == 0) {
             peak_out[t] = peak;
             delay_out[t] = delay;
@@ -735,12 +713,12 @@ rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long
 // ------------------------------------------------------------------------------------------------
 // K3  channel estimate for accepted locks (+ optional time-domain channel and equalised preamble).
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N, int GROUPS>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
+template <class C, int GROUPS>
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
                   const long long *__restrict__ pos_in, const int *__restrict__ delay_in, long long n_locks, int iters,
                   float2 *__restrict__ H_out, float2 *__restrict__ htime_out, float2 *__restrict__ synch_eq_out) {
-    OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
+    OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
     const int L = N + P.cp;
     for (int it = 0; it < iters; ++it) {
@@ -748,37 +726,37 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
         i = i < n_locks - 1 ? i : n_locks - 1;
         const long long pos = pos_in[i];
         const int delay = delay_in[i];
-        float2 ys[8], ydup[2], H[8], G[8];
+        float2 ys[C::PPT], ydup[2], H[C::PPT], G[C::PPT];
         float pw = 0.f, p_est, peak;
         int dfound;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) ys[m] = make_float2(0.f, 0.f);
+        for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
         ydup[0] = ydup[1] = make_float2(0.f, 0.f);
         for (int s = 0; s < P.m0; ++s) {
-            float2 v[8];
-            load8<T>(v, x, pos + (long long)s * L, n_samples, j);
-            fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
-            sync_accumulate<LOG2N>(P, v, s, j, ys, ydup, pw);
+            float2 v[C::PPT];
+            load_pts<T, PPT>(v, x, pos + (long long)s * L, n_samples, j);
+            fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
+            sync_accumulate<C>(P, v, s, j, ys, ydup, pw);
         }
-        sync_finish<LOG2N, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, dfound);
-        chan_core<LOG2N>(P, ys, ydup, p_est, delay, P.inv_reg_eq_synch, j, H, G);
+        sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, dfound);
+        chan_core<C>(P, ys, ydup, p_est, delay, P.inv_reg_eq_synch, j, H, G);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) H_out[i * N + j + m * T] = H[m];
+        for (int m = 0; m < PPT; ++m) H_out[i * N + j + m * T] = H[m];
         if (htime_out != nullptr) {                              // ifft(chan_est1): SynchAndChanEst.py:202
-            float2 c[8];
+            float2 c[C::PPT];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) c[m] = H[m];
-            fft_group<LOG2N, true, GROUPS>(c, tws, b0, b1, j, gid, pp);
+            for (int m = 0; m < PPT; ++m) c[m] = H[m];
+            fft_group<C, true, GROUPS>(c, tws, b0, b1, j, gid, pp);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) htime_out[i * N + j + m * T] = cscale(c[m], 1.f / (float)N);
+            for (int m = 0; m < PPT; ++m) htime_out[i * N + j + m * T] = cscale(c[m], 1.f / (float)N);
         }
         if (synch_eq_out != nullptr) {                           // eq_gain_ext * data_recov: :213-218
             for (int s = 0; s < P.m0; ++s) {
-                float2 v[8];
-                load8<T>(v, x, pos + (long long)s * L, n_samples, j);
-                fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
+                float2 v[C::PPT];
+                load_pts<T, PPT>(v, x, pos + (long long)s * L, n_samples, j);
+                fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
+                for (int m = 0; m < PPT; ++m) {
                     const int k = j + m * T;
                     const int idx = used_index(k, N, P.nsb);
                     if (idx >= 0) {
@@ -803,24 +781,24 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
 // ------------------------------------------------------------------------------------------------
 // K4  data symbols from an explicit symbol list (used by the stream blocks' work()).
 // ------------------------------------------------------------------------------------------------
-template <int LOG2N, int BPS, int GROUPS, bool PIL>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocks<LOG2N>::value)
+template <class C, int BPS, int GROUPS, bool PIL>
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
                 const long long *__restrict__ start_in, const int *__restrict__ delay_in,
                 const int *__restrict__ hrow_in, const float2 *__restrict__ Hmat, long long n_sym, int iters,
                 float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
-    OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
+    OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
-    const DataCtx<LOG2N, BPS> D(P, j);
+    const DataCtx<C, BPS> D(P, j);
     for (int it = 0; it < iters; ++it) {
         long long i = gg + (long long)it * total_groups;
         i = i < n_sym - 1 ? i : n_sym - 1;
         const int delay = delay_in[i];
         const long long hrow = hrow_in[i];
-        float2 v[8], G[8];
-        load8<T>(v, x, start_in[i], n_samples, j);
+        float2 v[C::PPT], G[C::PPT];
+        load_pts<T, PPT>(v, x, start_in[i], n_samples, j);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
+        for (int m = 0; m < PPT; ++m) {
             const int k = j + m * T;
             const float2 h = __ldg(Hmat + hrow * N + k);
             const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));
@@ -828,11 +806,11 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
             G[m] = PIL ? make_float2(w.x, -w.y)
                        : cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? __fdividef(1.f, den) : 0.f);
         }
-        fft_group<LOG2N, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
+        fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
         if (PIL)
-            data_epilogue_pilot<LOG2N, BPS, GROUPS>(P, D, v, G, i, redf, hb, hp, j, gid, eq_out, llr_out, hard_out);
+            data_epilogue_pilot<C, BPS, GROUPS>(P, D, v, G, i, redf, hb, hp, j, gid, eq_out, llr_out, hard_out);
         else
-            data_epilogue<LOG2N, BPS, GROUPS>(P, D, v, G, i, redf, hb, j, gid, eq_out, llr_out, hard_out);
+            data_epilogue<C, BPS, GROUPS>(P, D, v, G, i, redf, hb, j, gid, eq_out, llr_out, hard_out);
     }
 }
 
@@ -853,28 +831,28 @@ __device__ __forceinline__ unsigned ld_word_guarded(const uint8_t *__restrict__ 
     return w;
 }
 
-template <int LOG2N, int BPS, int GROUPS, bool PIL>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::T *GROUPS, MinBlocksTx<LOG2N>::value)
+template <class C, int BPS, int GROUPS, bool PIL>
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocksTx<C>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
-    OFDM_KERNEL_PROLOGUE(LOG2N, GROUPS)
+    OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
-    constexpr int WPT = 2;                                   // a payload row spans at most 2 packed words per thread
+    constexpr int WPT = PPT / 4;                             // a payload row spans at most PPT/4 packed words per thread
     constexpr int ZERO = 64;                                 // LUT entry that maps unused bins to 0
     const int L = N + P.cp, fs = P.m0 + P.d;
     // constellation table in shared memory: one LDS per bin instead of arithmetic on the bits
     float2 *lut = S::lut(smem_raw);
     for (int i = tid; i <= ZERO; i += S::THREADS) lut[i] = i < (1 << BPS) ? map_bits<BPS>((unsigned)i) : make_float2(0.f, 0.f);
     __syncthreads();
-    const BinMap map = make_bin_map<T>(P.ndb, j);
+    const BinMap map = make_bin_map<T, PPT>(P.ndb, j);
     // bit position of this thread's first bin of each spectrum half inside a payload row; the other
     // bins of the half are T*BPS bits (a whole number of bytes) further on
-    const int bop = map.base_p * BPS, bon = (map.base_n - 4 * T) * BPS;
+    const int bop = map.base_p * BPS, bon = (map.base_n - (PPT / 2) * T) * BPS;
     const int byp = bop >> 3, shp = 16 - (bop & 7) - BPS, byn = bon >> 3, shn = 16 - (bon & 7) - BPS;
     // this thread's samples n = j + m*T that also go into the cyclic prefix (n >= N - CP)
     unsigned cpmask = 0;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) cpmask |= (j + m * T >= N - P.cp) ? (1u << m) : 0u;
+    for (int m = 0; m < PPT; ++m) cpmask |= (j + m * T >= N - P.cp) ? (1u << m) : 0u;
     const float sqrtL = sqrtf((float)L), invL = 1.f / (float)L;
     const float emin = 1e-30f * (float)N * (float)N;
     // the payload buffer, viewed from its 4-byte-aligned base
@@ -912,7 +890,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
         clampfs(fn, sn);
         const long long rnxt = row_start(fn, sn);
         fetch(wnxt, rnxt);
-        float2 v[8];
+        float2 v[C::PPT];
         {
             // Stage the row's packed words, then every thread picks the bits of its own bins.  Groups that
             // share a warp can be on different symbol types, so the barrier is executed unconditionally
@@ -925,9 +903,9 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             const uint8_t *rp = hb + (int)(rcur & 3);
             if (PIL) {
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
+                for (int m = 0; m < PPT; ++m) {
                     const bool used = (map.mask & (1u << m)) != 0;
-                    const PilotPos pq = pilot_pos(P, used ? bin_out<T>(map, m) : 0);
+                    const PilotPos pq = pilot_pos(P, used ? bin_out<T, PPT>(map, m) : 0);
                     const int bo = pq.dj * BPS;
                     const uint8_t *q = rp + (bo >> 3);
                     unsigned w = (unsigned)q[0] << 8;
@@ -937,24 +915,24 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                 }
             } else {
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const uint8_t *q = rp + (m < 4 ? byp : byn) + m * (T * BPS / 8);
+                for (int m = 0; m < PPT; ++m) {
+                    const uint8_t *q = rp + (m < PPT / 2 ? byp : byn) + m * (T * BPS / 8);
                     unsigned w = (unsigned)q[0] << 8;
                     if (BPS == 6) w |= (unsigned)q[1];
-                    const unsigned val = (w >> (m < 4 ? shp : shn)) & ((1u << BPS) - 1u);
+                    const unsigned val = (w >> (m < PPT / 2 ? shp : shn)) & ((1u << BPS) - 1u);
                     v[m] = lut[(map.mask & (1u << m)) ? val : ZERO];
                 }
             }
             if (s < P.m0) {
                 const float2 *z = P.zc_tx + s * N + j;
 #pragma unroll
-                for (int m = 0; m < 8; ++m) v[m] = __ldg(z + m * T);
+                for (int m = 0; m < PPT; ++m) v[m] = __ldg(z + m * T);
             }
         }
-        fft_group<LOG2N, true, GROUPS>(v, tws, b0, b1, j, gid, pp);
+        fft_group<C, true, GROUPS>(v, tws, b0, b1, j, gid, pp);
         float3 acc = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
+        for (int m = 0; m < PPT; ++m) {
             const float w = (cpmask & (1u << m)) ? 2.f : 1.f;
             acc.x = fmaf(w, cabs2(v[m]), acc.x);
             acc.y = fmaf(w, v[m].x, acc.y);
@@ -970,7 +948,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
         float2 *o = out + (f * fs + s) * L + P.cp + j;
         float2 *ocp = o - N;                                  // sample n >= N-CP is also output n - (N-CP)
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
+        for (int m = 0; m < PPT; ++m) {
             const float2 z = cscale(v[m], g);
             __stcs(o + m * T, z);
             if (cpmask & (1u << m)) __stcs(ocp + m * T, z);

@@ -7,9 +7,9 @@
 
 namespace ofdm {
 
-template <int LOG2N> struct GroupsFor {
+template <class C> struct GroupsFor {
     // threads per CTA = max(T, 128): several small symbols share a CTA
-    static constexpr int value = (LOG2N >= 10) ? 1 : (128 / FftCfg<LOG2N>::T);
+    static constexpr int value = C::T >= 128 ? 1 : (128 / C::T);
 };
 
 struct LaunchDims {
@@ -58,19 +58,20 @@ template <int LOG2N>
 cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_samples, long long first,
                              long long frame_stride, long long n_frames, int *delay, float *peak, uint8_t *locked,
                              float2 *H, float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
-    int SM = Smem<LOG2N, G>::BYTES;
+    using C = CfgRx<LOG2N>;
+    constexpr int G = GroupsFor<C>::value, TH = C::T * G;
+    int SM = Smem<C, G>::BYTES;
     if (n_frames <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
         if (P.pil_k) {
-            constexpr auto k = rx_frames_kernel<LOG2N, BPS, G, true>;
+            constexpr auto k = rx_frames_kernel<C, BPS, G, true>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
                                       eq, llr, hard);
         } else {
-            constexpr auto k = rx_frames_kernel<LOG2N, BPS, G, false>;
+            constexpr auto k = rx_frames_kernel<C, BPS, G, false>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
@@ -85,18 +86,19 @@ template <int LOG2N>
 cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_samples, const long long *start,
                             const int *delay, const int *hrow, const float2 *H, long long n_sym, float2 *eq,
                             float *llr, uint8_t *hard, cudaStream_t st, int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
-    int SM = Smem<LOG2N, G>::BYTES;
+    using C = CfgRx<LOG2N>;
+    constexpr int G = GroupsFor<C>::value, TH = C::T * G;
+    int SM = Smem<C, G>::BYTES;
     if (n_sym <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
         if (P.pil_k) {
-            constexpr auto k = rx_demod_kernel<LOG2N, BPS, G, true>;
+            constexpr auto k = rx_demod_kernel<C, BPS, G, true>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
         } else {
-            constexpr auto k = rx_demod_kernel<LOG2N, BPS, G, false>;
+            constexpr auto k = rx_demod_kernel<C, BPS, G, false>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
@@ -109,18 +111,19 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
 template <int LOG2N>
 cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long long n_sym_total, cudaStream_t st,
                       int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
-    int SM = Smem<LOG2N, G>::BYTES;
+    using C = CfgTx<LOG2N>;
+    constexpr int G = GroupsFor<C>::value, TH = C::T * G;
+    int SM = Smem<C, G>::BYTES;
     if (n_sym_total <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
         if (P.pil_k) {
-            constexpr auto k = tx_kernel<LOG2N, BPS, G, true>;
+            constexpr auto k = tx_kernel<C, BPS, G, true>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);
         } else {
-            constexpr auto k = tx_kernel<LOG2N, BPS, G, false>;
+            constexpr auto k = tx_kernel<C, BPS, G, false>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);
@@ -134,10 +137,11 @@ template <int LOG2N>
 cudaError_t launch_sync_search(const DevParams &P, const float2 *x, long long n_samples, long long first_start,
                                long long stride, long long n_trials, float *peak, int *delay, cudaStream_t st,
                                int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
-    int SM = Smem<LOG2N, G>::BYTES;
+    using C = CfgRx<LOG2N>;
+    constexpr int G = GroupsFor<C>::value, TH = C::T * G;
+    int SM = Smem<C, G>::BYTES;
     if (n_trials <= 0) return cudaSuccess;
-    constexpr auto k = rx_sync_search_kernel<LOG2N, G>;
+    constexpr auto k = rx_sync_search_kernel<C, G>;
     LaunchDims d;
     cudaError_t e = plan_launch<k>(TH, SM, G, n_trials, sms, d);
     if (e != cudaSuccess) return e;
@@ -150,10 +154,11 @@ template <int LOG2N>
 cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samples, const long long *pos,
                            const int *delay, long long n_locks, float2 *H, float2 *htime, float2 *synch_eq,
                            cudaStream_t st, int sms) {
-    constexpr int G = GroupsFor<LOG2N>::value, TH = FftCfg<LOG2N>::T * G;
-    int SM = Smem<LOG2N, G>::BYTES;
+    using C = CfgRx<LOG2N>;
+    constexpr int G = GroupsFor<C>::value, TH = C::T * G;
+    int SM = Smem<C, G>::BYTES;
     if (n_locks <= 0) return cudaSuccess;
-    constexpr auto k = rx_chanest_kernel<LOG2N, G>;
+    constexpr auto k = rx_chanest_kernel<C, G>;
     LaunchDims d;
     cudaError_t e = plan_launch<k>(TH, SM, G, n_locks, sms, d);
     if (e != cudaSuccess) return e;
