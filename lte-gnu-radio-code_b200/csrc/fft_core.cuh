@@ -72,7 +72,7 @@ template <int LOG2N_, int PPT_> struct FftCfg {
 
 // Points per thread for each transform size and kernel family (overridable for A/B runs, e.g.
 // -DOFDM_PPT_RX_4096=8).  Measured on B200 (tools/sweep_minb.sh): 16 points per thread speed the
-// transmitter up by 20-28 % at N >= 1024 and the receiver by 14 % at N = 4096; at N = 1024/2048 the
+// transmitter up by 11-28 % at N >= 512 and the receiver by 14 % at N = 4096; at N = 1024/2048 the
 // receiver also carries 16 equaliser gains per thread and is faster with 8.
 #ifndef OFDM_PPT_TX_LARGE
 #define OFDM_PPT_TX_LARGE 16
@@ -89,8 +89,11 @@ template <int LOG2N_, int PPT_> struct FftCfg {
 template <int LOG2N> struct PptRx {
     static constexpr int value = LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RX_1024 : (LOG2N == 11 ? OFDM_PPT_RX_2048 : OFDM_PPT_RX_4096));
 };
+#ifndef OFDM_PPT_TX_MIN_LOG2N
+#define OFDM_PPT_TX_MIN_LOG2N 9
+#endif
 template <int LOG2N> struct PptTx {
-    static constexpr int value = LOG2N >= 10 ? OFDM_PPT_TX_LARGE : 8;
+    static constexpr int value = LOG2N >= OFDM_PPT_TX_MIN_LOG2N ? OFDM_PPT_TX_LARGE : 8;
 };
 template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value>;
 template <int LOG2N> using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value>;

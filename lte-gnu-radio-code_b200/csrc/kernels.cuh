@@ -297,17 +297,17 @@ __device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict
 }
 
 // shared-memory carve-up per CTA
-template <class C, int GROUPS> struct Smem {
+template <class C, int GROUPS, bool TXK = false> struct Smem {
     static constexpr int THREADS = C::T * GROUPS;
     static constexpr int GSTRIDE = (C::LOG2N == 6) ? (2 * C::BUF + 8) : 2 * C::BUF;   // complex slots per group
     static constexpr int FFT_BYTES = GROUPS * GSTRIDE * 8;
     static constexpr int TW_BYTES = C::TW_ENTRIES * 8;                              // pass twiddles, shared by the CTA
-    static constexpr int STAGE_BYTES = THREADS * C::PPT * 8;                        // next symbol: PPT samples per thread
+    static constexpr int STAGE_BYTES = TXK ? 0 : THREADS * C::PPT * 8;              // next symbol: PPT samples per thread (RX)
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
     static constexpr int HB_STRIDE = C::N + 16;                                     // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
     static constexpr int LUT_BYTES = 72 * 8;                                        // constellation table (TX), entry 64 = 0
-    static constexpr int HP_BYTES = GROUPS * (C::N / 2) * 8;                        // per-symbol pilot estimates (pilot mode)
+    static constexpr int HP_BYTES = TXK ? 0 : GROUPS * (C::N / 2) * 8;              // per-symbol pilot estimates (RX, pilot mode)
     static constexpr int OFF_TW = FFT_BYTES;
     static constexpr int OFF_STAGE = OFF_TW + TW_BYTES;
     static constexpr int OFF_RED = OFF_STAGE + STAGE_BYTES;
@@ -562,8 +562,8 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
     }
 }
 
-#define OFDM_KERNEL_PROLOGUE(GROUPS)                                                  \
-    using S = Smem<C, GROUPS>;                                                     \
+#define OFDM_KERNEL_PROLOGUE_(GROUPS, TXK)                                            \
+    using S = Smem<C, GROUPS, TXK>;                                                \
     constexpr int T = C::T, PPT = C::PPT;                                              \
     extern __shared__ __align__(16) unsigned char smem_raw[];                          \
     const int tid = threadIdx.x, gid = tid / T, j = tid % T;                           \
@@ -589,6 +589,8 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
 #ifndef OFDM_MINB_SMALL
 #define OFDM_MINB_SMALL 4
 #endif
+#define OFDM_KERNEL_PROLOGUE(GROUPS) OFDM_KERNEL_PROLOGUE_(GROUPS, false)
+
 template <class C> struct MinBlocks {
     static constexpr int THREADS = C::T >= 128 ? C::T : 128;
     static constexpr int REGS = C::PPT == 16 ? 255 : 128;
@@ -835,7 +837,7 @@ template <class C, int BPS, int GROUPS, bool PIL>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksTx<C>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
-    OFDM_KERNEL_PROLOGUE(GROUPS)
+    OFDM_KERNEL_PROLOGUE_(GROUPS, true)
     constexpr int N = C::N;
     constexpr int WPT = PPT / 4;                             // a payload row spans at most PPT/4 packed words per thread
     constexpr int ZERO = 64;                                 // LUT entry that maps unused bins to 0

@@ -113,7 +113,7 @@ cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long
                       int sms) {
     using C = CfgTx<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
-    int SM = Smem<C, G>::BYTES;
+    int SM = Smem<C, G, true>::BYTES;
     if (n_sym_total <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
