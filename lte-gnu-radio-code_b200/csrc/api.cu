@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -375,6 +376,15 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     D.n_pil = n_pil;
     D.ndd = ndb - n_pil;
     D.hard_stride = (D.ndd * p->bps + 7) / 8;
+    // 64-QAM LLR rows are staged in shared memory (kernels.cuh, data_epilogue); group stride = row length
+    // rounded so that neighbouring groups start 16 banks apart.  Only for transforms up to
+    // OFDM_LLR_STAGE_MAX_N points (environment override for A/B runs; 0 disables): from N = 128 on the extra
+    // shared-memory traffic costs more than the partial-sector stores it removes (B200, 64-QAM: N=64 0.53 -> 0.39 ms, N=128 0.37 -> 0.42 ms, N=2048 0.76 -> 0.81 ms).
+    {
+        const char *env = getenv("OFDM_LLR_STAGE_MAX_N");
+        const int max_n = env ? atoi(env) : 64;
+        D.ls_stride = (p->bps == 6 && pk == 0 && N <= max_n) ? (((ndb * 6 + 31) & ~31) + 16) : 0;
+    }
     D.dup_bin = dup_bin;
     D.equalizer = p->equalizer;
     D.gate_thresh = p->gate * (float)mm;

@@ -46,15 +46,20 @@ __host__ __device__ constexpr int fft_radix(int log2n, int ppt, int p) {
 __host__ __device__ constexpr int fft_ns(int log2n, int ppt, int p) {
     return 1 << (fft_lp(ppt) * (p < log2n / fft_lp(ppt) ? p : log2n / fft_lp(ppt)));
 }
-// shared twiddle table: pass p >= 1 holds (R-1) rows of Ns entries, row q-1 entry r = W_N^(q*r*N/(Ns*R))
-__host__ __device__ constexpr int fft_tw_off(int log2n, int ppt, int p) {
+// shared twiddle table: pass p >= 1 holds rows of Ns entries, row for multiplier q entry r = W_N^(q*r*N/(Ns*R)).
+// Full table: rows q = 1..R-1.  Chained table (CH): rows q = 1, 2, 4, .. only; the other multipliers are
+// products of those (3 = 1*2, 5 = 1*4, ...), which trades shared-memory reads for FMA-pipe work.
+__host__ __device__ constexpr int fft_log2(int r) { return r <= 1 ? 0 : 1 + fft_log2(r / 2); }
+__host__ __device__ constexpr int fft_tw_rows(int r, bool ch) { return ch ? fft_log2(r) : r - 1; }
+__host__ __device__ constexpr int fft_tw_off(int log2n, int ppt, int p, bool ch = false) {
     int o = 0;
-    for (int i = 1; i < p; ++i) o += (fft_radix(log2n, ppt, i) - 1) * fft_ns(log2n, ppt, i);
+    for (int i = 1; i < p; ++i) o += fft_tw_rows(fft_radix(log2n, ppt, i), ch) * fft_ns(log2n, ppt, i);
     return o;
 }
 
-template <int LOG2N_, int PPT_> struct FftCfg {
+template <int LOG2N_, int PPT_, bool CH_ = false> struct FftCfg {
     static constexpr int LOG2N = LOG2N_, PPT = PPT_;
+    static constexpr bool CH = CH_;
     static constexpr int N = 1 << LOG2N;
     static constexpr int T = N / PPT;                     // threads per symbol group
     static constexpr int LP = fft_lp(PPT);
@@ -62,12 +67,12 @@ template <int LOG2N_, int PPT_> struct FftCfg {
     static constexpr int REM = LOG2N % LP;                // log2 of the last pass' radix (0: none)
     static constexpr int NPASS = NFULL + (REM ? 1 : 0);
     static constexpr int NEXCH = NPASS - 1;               // shared-memory exchanges per transform
-    static constexpr int TW_ENTRIES = fft_tw_off(LOG2N, PPT, NPASS);
+    static constexpr int TW_ENTRIES = fft_tw_off(LOG2N, PPT, NPASS, CH);
     // padded buffer length in complex slots; N == 64 uses a pad-per-8 layout (see lay())
     static constexpr int BUF = (LOG2N == 6) ? 72 : N;
     __host__ __device__ static constexpr int radix(int p) { return fft_radix(LOG2N, PPT, p); }
     __host__ __device__ static constexpr int ns(int p) { return fft_ns(LOG2N, PPT, p); }
-    __host__ __device__ static constexpr int tw_off(int p) { return fft_tw_off(LOG2N, PPT, p); }
+    __host__ __device__ static constexpr int tw_off(int p) { return fft_tw_off(LOG2N, PPT, p, CH); }
 };
 
 // Points per thread for each transform size and kernel family (overridable for A/B runs, e.g.
@@ -95,8 +100,47 @@ template <int LOG2N> struct PptRx {
 template <int LOG2N> struct PptTx {
     static constexpr int value = LOG2N >= OFDM_PPT_TX_MIN_LOG2N ? OFDM_PPT_TX_LARGE : 8;
 };
+// chained twiddles (FftCfg CH) from this size on; 13 = never.  Measured on B200: +2 % for the framed
+// receiver at N >= 1024, +3 % for the transmitter at N = 4096, neutral or slightly negative below.
+#ifndef OFDM_TW_CHAIN_TX_MIN_LOG2N
+#define OFDM_TW_CHAIN_TX_MIN_LOG2N 12
+#endif
+#ifndef OFDM_TW_CHAIN_RXF_MIN_LOG2N
+#define OFDM_TW_CHAIN_RXF_MIN_LOG2N 10
+#endif
 template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value>;
-template <int LOG2N> using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value>;
+
+// The fused framed receiver (rx_frames_kernel) has its own knobs, because it is the one kernel that
+// keeps per-frame state (the equaliser gains) alive across symbols:
+//   OFDM_PPT_RXF_<N>        points per thread
+//   OFDM_GSM_MIN_LOG2N      from this size on the gains live in thread-private shared-memory slots
+//                           instead of registers (frees 2*PPT registers per thread)
+//   OFDM_SB_MIN_LOG2N       from this size on the FFT exchanges use ONE buffer and two barriers
+//                           instead of two ping-pong buffers and one barrier (halves that footprint)
+#ifndef OFDM_PPT_RXF_1024
+#define OFDM_PPT_RXF_1024 OFDM_PPT_RX_1024
+#endif
+#ifndef OFDM_PPT_RXF_2048
+#define OFDM_PPT_RXF_2048 OFDM_PPT_RX_2048
+#endif
+#ifndef OFDM_PPT_RXF_4096
+#define OFDM_PPT_RXF_4096 OFDM_PPT_RX_4096
+#endif
+#ifndef OFDM_GSM_MIN_LOG2N
+#define OFDM_GSM_MIN_LOG2N 13
+#endif
+#ifndef OFDM_SB_MIN_LOG2N
+#define OFDM_SB_MIN_LOG2N 13
+#endif
+template <int LOG2N> struct PptRxF {
+    static constexpr int value = LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RXF_1024 : (LOG2N == 11 ? OFDM_PPT_RXF_2048 : OFDM_PPT_RXF_4096));
+};
+template <int LOG2N> using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N)>;
+template <int LOG2N> struct RxFOpts {
+    static constexpr bool GSM = LOG2N >= OFDM_GSM_MIN_LOG2N;
+    static constexpr bool SB = LOG2N >= OFDM_SB_MIN_LOG2N;
+};
+template <int LOG2N> using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_TX_MIN_LOG2N)>;
 
 // Exchange layout for the buffer written by pass P (Ns = PPT^P), chosen so that the scattered write
 // out[(j/Ns)*Ns*R + j%Ns + q*Ns] and the contiguous read in[j + m*T] both hit 16 distinct 8-byte
@@ -218,8 +262,9 @@ __device__ __forceinline__ void fill_twiddles(float2 *tws, const float2 *__restr
     for (int p = 1; p < C::NPASS; ++p) {
         const int R = C::radix(p), Ns = C::ns(p), off = C::tw_off(p);
         const int step = C::N / (Ns * R);
-        for (int i = tid; i < (R - 1) * Ns; i += nthreads) {
-            const int q = i / Ns + 1, r = i & (Ns - 1);
+        for (int i = tid; i < fft_tw_rows(R, C::CH) * Ns; i += nthreads) {
+            const int row = i / Ns, r = i & (Ns - 1);
+            const int q = C::CH ? (1 << row) : row + 1;
             tws[off + i] = __ldg(&tw[(q * r * step) & (C::N - 1)]);
         }
     }
@@ -249,7 +294,7 @@ template <bool INV, int R, int B, int PPT> __device__ __forceinline__ void bfly_
 
 // One pass P of the transform, fully unrolled through template recursion.  Butterfly b of a thread
 // works on registers b + q*B (B = PPT/R butterflies per thread), i.e. on elements j + b*T + q*N/R.
-template <class C, bool INV, int GROUPS, int P> struct Pass {
+template <class C, bool INV, int GROUPS, int P, bool SB = false> struct Pass {
     static __device__ __forceinline__ void run(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1,
                                                int j, int gid, int &pp) {
         constexpr int R = C::radix(P), Ns = C::ns(P), B = C::PPT / R;
@@ -258,36 +303,53 @@ template <class C, bool INV, int GROUPS, int P> struct Pass {
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 const float2 *t = tws + off + ((j + b * C::T) & (Ns - 1));
+                if constexpr (!C::CH) {
 #pragma unroll
-                for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], t[(q - 1) * Ns]);
+                    for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], t[(q - 1) * Ns]);
+                } else {
+                    // rows hold W^(1*r), W^(2*r), W^(4*r), ..; multiplier q = 2^a + rest is built as w[2^a] * w[rest],
+                    // visiting q in an order that lets every product be used and dropped at once
+                    float2 w[R];
+#pragma unroll
+                    for (int a = 0; (1 << a) < R; ++a) w[1 << a] = t[a * Ns];
+#pragma unroll
+                    for (int q = 3; q < R; ++q) {
+                        const int hi = 1 << (31 - __builtin_clz((unsigned)q));
+                        if (q != hi) w[q] = cmul(w[hi], w[q - hi]);
+                    }
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], w[q]);
+                }
             }
         }
 #pragma unroll
         for (int b = 0; b < B; ++b) bfly_strided<INV, R, B, C::PPT>(v, b);
         if (P < C::NPASS - 1) {
             // only full-radix passes are followed by an exchange (B == 1)
-            float2 *buf = (pp & 1) ? buf1 : buf0;
-            pp ^= 1;
+            // SB: one buffer, so a second barrier keeps the next exchange's writes behind these reads
+            float2 *buf = SB ? buf0 : ((pp & 1) ? buf1 : buf0);
+            if (!SB) pp ^= 1;
             const int e = (j / Ns) * (Ns * C::PPT) + (j & (Ns - 1));
 #pragma unroll
             for (int q = 0; q < C::PPT; ++q) buf[lay<C, P>(e + q * Ns)] = v[q];
             group_sync<C::T, GROUPS>(gid);
 #pragma unroll
             for (int m = 0; m < C::PPT; ++m) v[m] = buf[lay<C, P>(j + m * C::T)];
-            Pass<C, INV, GROUPS, P + 1>::run(v, tws, buf0, buf1, j, gid, pp);
+            if (SB) group_sync<C::T, GROUPS>(gid);
+            Pass<C, INV, GROUPS, P + 1, SB>::run(v, tws, buf0, buf1, j, gid, pp);
         }
     }
 };
-template <class C, bool INV, int GROUPS> struct Pass<C, INV, GROUPS, 4> {
+template <class C, bool INV, int GROUPS, bool SB> struct Pass<C, INV, GROUPS, 4, SB> {
     static __device__ __forceinline__ void run(float2 (&)[C::PPT], const float2 *, float2 *, float2 *, int, int, int &) {}
 };
 
 // In-place transform of the group's symbol.  pp is the running ping-pong selector (kept across
 // calls so that consecutive transforms never need a second barrier per exchange).
-template <class C, bool INV, int GROUPS>
+template <class C, bool INV, int GROUPS, bool SB = false>
 __device__ __forceinline__ void fft_group(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1, int j,
                                           int gid, int &pp) {
-    Pass<C, INV, GROUPS, 0>::run(v, tws, buf0, buf1, j, gid, pp);
+    Pass<C, INV, GROUPS, 0, SB>::run(v, tws, buf0, buf1, j, gid, pp);
 }
 
 // ------------------------------------------------------------------------------------------------

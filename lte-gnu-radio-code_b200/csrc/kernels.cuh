@@ -32,6 +32,7 @@ struct DevParams {
     const float2 *zc_tx;      // [M0][N]  ZC value the transmitter puts in bin k of synch symbol m (0 if unused)
     // comb pilots in data symbols (extension): positions pil_off + i*pil_k of the used-bin list
     int pil_k, pil_off, n_pil, ndd;   // ndd = payload bins per data symbol = ndb - n_pil
+    int ls_stride;                    // floats per group of the 64-QAM LLR row staging area (0: none)
     const float2 *pilot_tx;   // [N]      pilot value in FFT bin k (0 elsewhere)
 };
 
@@ -257,64 +258,113 @@ __device__ __forceinline__ void store_chunk(uint8_t *__restrict__ p, unsigned wo
     }
 }
 
-template <int BPS, int T>
-__device__ __forceinline__ void pack_bits(const uint8_t *hb, uint8_t *__restrict__ out, int nbytes, int j) {
+// Packed row word `c` (row bytes 4c..4c+3, little-endian) from the per-bin values in hb[]; `c3` selects the
+// word inside a 64-QAM 12-byte chunk.
+template <int BPS> __device__ __forceinline__ unsigned pack_word(const uint8_t *hb, int c) {
     if (BPS == 4) {
-        const int nchunks = (nbytes + 3) >> 2;
-        for (int c = j; c < nchunks; c += T) {
-            const uint2 w = *reinterpret_cast<const uint2 *>(hb + 8 * c);          // 8 bins, one nibble each
-            const unsigned ux = (w.x << 4) | (w.x >> 8), uy = (w.y << 4) | (w.y >> 8);
-            store_chunk(out + 4 * c, __byte_perm(ux, uy, 0x6420), nbytes - 4 * c);
-        }
+        const uint2 w = *reinterpret_cast<const uint2 *>(hb + 8 * c);              // 8 bins, one nibble each
+        const unsigned ux = (w.x << 4) | (w.x >> 8), uy = (w.y << 4) | (w.y >> 8);
+        return __byte_perm(ux, uy, 0x6420);
     } else if (BPS == 2) {
-        const int nchunks = (nbytes + 3) >> 2;
-        for (int c = j; c < nchunks; c += T) {
-            const uint4 w = *reinterpret_cast<const uint4 *>(hb + 16 * c);         // 16 bins, two bits each
-            // (n0 | n1<<8 | n2<<16 | n3<<24) * 0x40100401 has n0<<6|n1<<4|n2<<2|n3 in its top byte
-            const unsigned word = ((w.x * 0x40100401u) >> 24) | (((w.y * 0x40100401u) >> 24) << 8) |
-                                  (((w.z * 0x40100401u) >> 24) << 16) | ((w.w * 0x40100401u) & 0xff000000u);
-            store_chunk(out + 4 * c, word, nbytes - 4 * c);
+        const uint4 w = *reinterpret_cast<const uint4 *>(hb + 16 * c);             // 16 bins, two bits each
+        // (n0 | n1<<8 | n2<<16 | n3<<24) * 0x40100401 has n0<<6|n1<<4|n2<<2|n3 in its top byte
+        return ((w.x * 0x40100401u) >> 24) | (((w.y * 0x40100401u) >> 24) << 8) |
+               (((w.z * 0x40100401u) >> 24) << 16) | ((w.w * 0x40100401u) & 0xff000000u);
+    } else {                                                                       // BPS == 1: 32 bins, one bit each
+        const uint4 a = *reinterpret_cast<const uint4 *>(hb + 32 * c), b = *reinterpret_cast<const uint4 *>(hb + 32 * c + 16);
+        auto nib = [](unsigned x) { return (x * 0x08040201u) >> 24; };
+        return ((nib(a.x) << 4) | nib(a.y)) | (((nib(a.z) << 4) | nib(a.w)) << 8) | (((nib(b.x) << 4) | nib(b.y)) << 16) |
+               (((nib(b.z) << 4) | nib(b.w)) << 24);
+    }
+}
+// 64-QAM: 16 bins (one 128-bit read) -> four 24-bit groups -> three 32-bit words
+__device__ __forceinline__ void pack_words6(const uint8_t *hb, int c, unsigned (&o)[3]) {
+    const uint4 w = *reinterpret_cast<const uint4 *>(hb + 16 * c);
+    auto g24 = [](unsigned x) { return ((x & 63u) << 18) | (((x >> 8) & 63u) << 12) | (((x >> 16) & 63u) << 6) | (x >> 24); };
+    const unsigned v0 = g24(w.x), v1 = g24(w.y), v2 = g24(w.z), v3 = g24(w.w);           // bytes (msb..lsb) = b0 b1 b2
+    o[0] = __byte_perm(v0, v1, 0x6012);
+    o[1] = __byte_perm(v1, v2, 0x5601);
+    o[2] = __byte_perm(v2, v3, 0x4560);
+}
+
+// Pack one symbol's hard decisions and store the row.  Rows whose length is even are stored straight
+// from the packing step (32-bit or 16-bit stores depending on the row's phase).  Odd-length rows
+// (15 and 45 bytes in the reference numerology) start at every byte phase, so they are packed into
+// shared memory first and then written as ALIGNED 32-bit words assembled from two neighbouring packed
+// words with a funnel shift; only the partial first / last word of a row falls back to byte stores.
+template <int BPS, int T, int GROUPS>
+__device__ __forceinline__ void pack_bits(const uint8_t *hb, unsigned *pk, uint8_t *__restrict__ out, int nbytes, int j,
+                                          int gid) {
+    const int nwords = (nbytes + 3) >> 2;
+    if ((nbytes & 1) == 0) {
+        if (BPS == 6) {
+            for (int c = j; 3 * c < nwords; c += T) {
+                unsigned o[3];
+                pack_words6(hb, c, o);
+                const int rem = nbytes - 12 * c;
+                store_chunk(out + 12 * c, o[0], rem);
+                if (rem > 4) store_chunk(out + 12 * c + 4, o[1], rem - 4);
+                if (rem > 8) store_chunk(out + 12 * c + 8, o[2], rem - 8);
+            }
+        } else {
+            for (int c = j; c < nwords; c += T) store_chunk(out + 4 * c, pack_word<BPS>(hb, c), nbytes - 4 * c);
         }
-    } else if (BPS == 1) {
-        for (int b = j; b < nbytes; b += T) {
-            const uint2 w = *reinterpret_cast<const uint2 *>(hb + 8 * b);
-            out[b] = (uint8_t)((((w.x * 0x08040201u) >> 24) << 4) | ((w.y * 0x08040201u) >> 24));
+        return;
+    }
+    if (BPS == 6) {
+        for (int c = j; 3 * c < nwords; c += T) {
+            unsigned o[3];
+            pack_words6(hb, c, o);
+            pk[3 * c] = o[0];
+            pk[3 * c + 1] = o[1];
+            pk[3 * c + 2] = o[2];
         }
     } else {
-        // 64-QAM: 16 bins (one 128-bit read) -> four 24-bit groups -> three 32-bit words
-        const int nchunks = (nbytes + 11) / 12;
-        for (int c = j; c < nchunks; c += T) {
-            const uint4 w = *reinterpret_cast<const uint4 *>(hb + 16 * c);
-            auto g24 = [](unsigned x) { return ((x & 63u) << 18) | (((x >> 8) & 63u) << 12) | (((x >> 16) & 63u) << 6) | (x >> 24); };
-            const unsigned v0 = g24(w.x), v1 = g24(w.y), v2 = g24(w.z), v3 = g24(w.w);   // bytes (msb..lsb) = b0 b1 b2
-            const int rem = nbytes - 12 * c;
-            uint8_t *p = out + 12 * c;
-            store_chunk(p, __byte_perm(v0, v1, 0x6012), rem);
-            if (rem > 4) store_chunk(p + 4, __byte_perm(v1, v2, 0x5601), rem - 4);
-            if (rem > 8) store_chunk(p + 8, __byte_perm(v2, v3, 0x4560), rem - 8);
+        for (int c = j; c < nwords; c += T) pk[c] = pack_word<BPS>(hb, c);
+    }
+    group_sync<T, GROUPS>(gid);
+    const int a = (int)(reinterpret_cast<unsigned long long>(out) & 3ull);     // row phase inside its first aligned word
+    unsigned *ow = reinterpret_cast<unsigned *>(out - a);
+    const int end = a + nbytes, nout = (end + 3) >> 2;
+    for (int i = j; i < nout; i += T) {
+        const unsigned lo = i > 0 ? pk[i - 1] : 0u, hi = i < nwords ? pk[i] : 0u;
+        const unsigned word = __funnelshift_rc(lo, hi, 8 * (4 - a));           // row bytes 4i-a .. 4i-a+3
+        const int t0 = a - 4 * i, t1 = end - 4 * i;                               // valid bytes of this word: [t0, t1)
+        if (t0 <= 0 && t1 >= 4) {
+            ow[i] = word;
+        } else {
+            uint8_t *pb = reinterpret_cast<uint8_t *>(ow + i);
+            for (int t = (t0 > 0 ? t0 : 0); t < 4 && t < t1; ++t) pb[t] = (uint8_t)(word >> (8 * t));
         }
     }
 }
 
-// shared-memory carve-up per CTA
-template <class C, int GROUPS, bool TXK = false> struct Smem {
+// shared-memory carve-up per CTA.  TXK: transmitter (no staging, no packed-row area); PIL: room for the
+// per-symbol pilot estimates; GSM: per-frame equaliser gains in thread-private slots; SB: one FFT
+// exchange buffer instead of two.
+template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = false, bool SB = false> struct Smem {
     static constexpr int THREADS = C::T * GROUPS;
-    static constexpr int GSTRIDE = (C::LOG2N == 6) ? (2 * C::BUF + 8) : 2 * C::BUF;   // complex slots per group
+    static constexpr int NBUF = SB ? 1 : 2;
+    static constexpr int GSTRIDE = (C::LOG2N == 6) ? (NBUF * C::BUF + 8) : NBUF * C::BUF;   // complex slots per group
     static constexpr int FFT_BYTES = GROUPS * GSTRIDE * 8;
     static constexpr int TW_BYTES = C::TW_ENTRIES * 8;                              // pass twiddles, shared by the CTA
     static constexpr int STAGE_BYTES = TXK ? 0 : THREADS * C::PPT * 8;              // next symbol: PPT samples per thread (RX)
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
-    static constexpr int HB_STRIDE = C::N + 16;                                     // +16: zero pad, keeps 16-byte alignment
+    static constexpr int PK_BYTES = TXK ? 0 : 3 * C::N / 4 + 16;                    // packed row staged for aligned stores
+    static constexpr int HB_STRIDE = C::N + 16 + PK_BYTES;                          // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
-    static constexpr int LUT_BYTES = 72 * 8;                                        // constellation table (TX), entry 64 = 0
-    static constexpr int HP_BYTES = TXK ? 0 : GROUPS * (C::N / 2) * 8;              // per-symbol pilot estimates (RX, pilot mode)
+    static constexpr int LUT_BYTES = TXK ? 72 * 8 : 0;                              // constellation table (TX), entry 64 = 0
+    static constexpr int HP_BYTES = (TXK || !PIL) ? 0 : GROUPS * (C::N / 2) * 8;    // per-symbol pilot estimates (RX, pilot mode)
+    static constexpr int GS_BYTES = GSM ? GROUPS * C::N * 8 : 0;                    // equaliser gains, slot m*T + j of the group
     static constexpr int OFF_TW = FFT_BYTES;
     static constexpr int OFF_STAGE = OFF_TW + TW_BYTES;
     static constexpr int OFF_RED = OFF_STAGE + STAGE_BYTES;
     static constexpr int OFF_HB = OFF_RED + RED_BYTES;
     static constexpr int OFF_LUT = OFF_HB + ((HB_BYTES + 7) & ~7);
     static constexpr int OFF_HP = OFF_LUT + LUT_BYTES;
-    static constexpr int BYTES = OFF_HP + HP_BYTES;
+    static constexpr int OFF_GS = OFF_HP + HP_BYTES;
+    static constexpr int BYTES = OFF_GS + GS_BYTES;
+    static_assert(BYTES % 16 == 0, "the dynamic tail (LLR row staging) needs 16-byte alignment");
     __device__ static float2 *buf0(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s) + gid * GSTRIDE; }
     __device__ static float2 *tws(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_TW); }
     // slot m of thread t: stage[m * THREADS + t] -> lanes hit consecutive 8-byte words
@@ -328,6 +378,18 @@ template <class C, int GROUPS, bool TXK = false> struct Smem {
     __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + OFF_HB + gid * HB_STRIDE; }
     __device__ static float2 *lut(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_LUT); }
     __device__ static float2 *hp(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s + OFF_HP) + gid * (C::N / 2); }
+    __device__ static float2 *gs(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s + OFF_GS) + gid * C::N; }
+};
+
+// The frame's equaliser gains: PPT registers per thread, or (GSM) the thread's own shared-memory slots
+// m*T + j -- written and read by the same thread, so no barrier is involved.
+template <class C, bool GSM> struct Gains {
+    float2 r[GSM ? 1 : C::PPT];
+    float2 *s;
+    __device__ __forceinline__ float2 get(int m) const { return GSM ? s[m * C::T] : r[GSM ? 0 : m]; }
+    __device__ __forceinline__ void set(int m, float2 g) {
+        if (GSM) s[m * C::T] = g; else r[GSM ? 0 : m] = g;
+    }
 };
 
 // Asynchronous prefetch of this thread's PPT samples of the window that opens at `start` into its
@@ -393,17 +455,15 @@ __device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2
     }
 }
 
-template <class C, int GROUPS>
-__device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&ys)[C::PPT], float pw, const float2 *tws,
+// c[] holds the correlation sums on entry and is overwritten by the delay bank.
+template <class C, int GROUPS, bool SB = false>
+__device__ __forceinline__ void sync_finish(const DevParams &P, float2 (&c)[C::PPT], float pw, const float2 *tws,
                                             float2 *b0, float2 *b1, float *redf, unsigned long long *redu, int j,
                                             int gid, int &pp, float &p_est, float &peak, int &delay) {
     constexpr int T = C::T, PPT = C::PPT;
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     p_est = pw > 0.f ? sqrtf((float)P.mm / pw) : 0.f;
-    float2 c[C::PPT];
-#pragma unroll
-    for (int m = 0; m < PPT; ++m) c[m] = ys[m];
-    fft_group<C, true, GROUPS>(c, tws, b0, b1, j, gid, pp);
+    fft_group<C, true, GROUPS, SB>(c, tws, b0, b1, j, gid, pp);
     unsigned long long key = 0ull;
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
@@ -419,9 +479,18 @@ __device__ __forceinline__ void sync_finish(const DevParams &P, const float2 (&y
     peak = p_est * sqrtf(__uint_as_float((unsigned)(key >> 32)));
 }
 
-// channel estimate + equaliser gain for this thread's 8 bins from the correlation sums.
+// channel estimate + equaliser gain for one bin from its correlation sum.
 // H_k = rot_k * p_est * ys_k / ((1+1/x) * M0)        SynchAndChanEst.py:177-188
 // G_k = conj(H_k) / (|H_k|^2 + inv_reg) * rot_k      :237-246 (de-rotation folded into the gain)
+template <int N>
+__device__ __forceinline__ void chan_bin(const DevParams &P, float2 y, int k, float sc, int delay, float inv_reg, float2 &h,
+                                         float2 &g) {
+    const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));       // exp(-j*2pi*d*k/N); rot = conj(w)
+    h = cscale(cmulc(y, w), sc);
+    const float den = cabs2(h) + inv_reg;
+    const float inv = den > 0.f ? __fdividef(1.f, den) : 0.f;
+    g = cscale(cmulc(make_float2(h.x, -h.y), w), inv);
+}
 template <class C>
 __device__ __forceinline__ void chan_core(const DevParams &P, const float2 (&ys)[C::PPT], const float2 (&ydup)[2],
                                           float p_est, int delay, float inv_reg, int j, float2 (&H)[C::PPT],
@@ -431,14 +500,7 @@ __device__ __forceinline__ void chan_core(const DevParams &P, const float2 (&ys)
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
         const int k = j + m * T;
-        const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));   // exp(-j*2pi*d*k/N); rot = conj(w)
-        float2 y = ys[m];
-        if (k == P.dup_bin) y = ydup[1];                          // numpy fancy assignment: last index wins
-        const float2 h = cscale(cmulc(y, w), sc);
-        H[m] = h;
-        const float den = cabs2(h) + inv_reg;
-        const float inv = den > 0.f ? __fdividef(1.f, den) : 0.f;
-        G[m] = cscale(cmulc(make_float2(h.x, -h.y), w), inv);
+        chan_bin<N>(P, k == P.dup_bin ? ydup[1] : ys[m], k, sc, delay, inv_reg, H[m], G[m]);   // fancy assignment: last index wins
     }
 }
 
@@ -452,10 +514,10 @@ template <class C, int BPS> struct DataCtx {
 };
 
 // equalise + demap + store one data symbol held in v[] (FFT output).  SynchAndChanEst.py:232-248.
-template <class C, int BPS, int GROUPS>
+template <class C, int BPS, int GROUPS, bool GSM>
 __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<C, BPS> &D, const float2 (&v)[C::PPT],
-                                              const float2 (&G)[C::PPT], long long row, float *redf, uint8_t *hb, int j,
-                                              int gid, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
+                                              const Gains<C, GSM> &G, long long row, float *redf, uint8_t *hb, float *ls,
+                                              int j, int gid, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                                               uint8_t *__restrict__ hard_out) {
     constexpr int T = C::T, PPT = C::PPT;
     const unsigned mask = D.map.mask;
@@ -466,15 +528,19 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
+    // 64-QAM: a bin's six LLRs are 24 bytes, so per-lane stores would leave every 32-byte sector
+    // half-written by each instruction (2.9x the sector writes at L2, ncu).  The row is assembled in
+    // shared memory instead and written with full 16-byte lanes.
+    const bool staged = (BPS == 6) && soft && (ls != nullptr);
     float2 *eqp = eq_out + row * P.ndb + D.map.base_p;
     float2 *eqn = eq_out + row * P.ndb + (D.map.base_n - (PPT / 2) * T);
-    float *lp = llr_out + (row * P.ndb + D.map.base_p) * BPS;
-    float *ln = llr_out + (row * P.ndb + (D.map.base_n - (PPT / 2) * T)) * BPS;
+    float *lp = (staged ? ls : llr_out + row * P.ndb * BPS) + D.map.base_p * BPS;
+    float *ln = (staged ? ls : llr_out + row * P.ndb * BPS) + (D.map.base_n - (PPT / 2) * T) * BPS;
     uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - (PPT / 2) * T);
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
         if (mask & (1u << m)) {
-            const float2 z = cscale(cmul(G[m], v[m]), p0);
+            const float2 z = cscale(cmul(G.get(m), v[m]), p0);
             __stcs((m < PPT / 2 ? eqp : eqn) + m * T, z);
             if (soft || hard) {
                 float Lb[BPS];
@@ -486,6 +552,9 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
                         __stcs(q, Lb[0]);
                     } else if (BPS == 4) {
                         __stcs(reinterpret_cast<float4 *>(q), make_float4(Lb[0], Lb[1], Lb[2], Lb[3]));
+                    } else if (staged) {
+#pragma unroll
+                        for (int b = 0; b + 1 < BPS; b += 2) *reinterpret_cast<float2 *>(q + b) = make_float2(Lb[b], Lb[b + 1]);
                     } else {
 #pragma unroll
                         for (int b = 0; b + 1 < BPS; b += 2)
@@ -496,19 +565,24 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
             }
         }
     }
-    if (hard) {
-        group_sync<T, GROUPS>(gid);
-        pack_bits<BPS, T>(hb, hard_out + row * P.hard_stride, P.hard_stride, j);
+    if (hard || staged) group_sync<T, GROUPS>(gid);
+    if (staged) {
+        float4 *dst = reinterpret_cast<float4 *>(llr_out + row * P.ndb * BPS);
+        const float4 *src = reinterpret_cast<const float4 *>(ls);
+        const int nq = (P.ndb * BPS) >> 2;
+        for (int i = j; i < nq; i += T) __stcs(dst + i, src[i]);
     }
+    if (hard)
+        pack_bits<BPS, T, GROUPS>(hb, reinterpret_cast<unsigned *>(hb + C::N + 16), hard_out + row * P.hard_stride, P.hard_stride, j, gid);
 }
 
 // Pilot mode (extension): G[] holds the de-rotation only.  Each data symbol is equalised with the LS
 // estimate on its own comb pilots, linearly interpolated across the used-bin list and held constant
 // outside the outermost pilots (the oracle's np.interp).  Off the fast path: positions are recomputed
 // per bin because payload indices are no longer a fixed stride apart.
-template <class C, int BPS, int GROUPS>
+template <class C, int BPS, int GROUPS, bool GSM>
 __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const DataCtx<C, BPS> &D,
-                                                    const float2 (&v)[C::PPT], const float2 (&R)[C::PPT], long long row,
+                                                    const float2 (&v)[C::PPT], const Gains<C, GSM> &R, long long row,
                                                     float *redf, uint8_t *hb, float2 *hp, int j, int gid,
                                                     float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                                                     uint8_t *__restrict__ hard_out) {
@@ -523,7 +597,7 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
     float2 z[C::PPT];
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
-        z[m] = cscale(cmul(R[m], v[m]), p0);
+        z[m] = cscale(cmul(R.get(m), v[m]), p0);
         if (mask & (1u << m)) {
             const PilotPos pp = pilot_pos(P, bin_out<T, PPT>(D.map, m));
             if (pp.is_pilot) hp[pp.ip] = cmulc(z[m], __ldg(P.pilot_tx + j + m * T));   // LS: Y * conj(p), |p| = 1
@@ -558,23 +632,24 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
     }
     if (hard) {
         group_sync<T, GROUPS>(gid);
-        pack_bits<BPS, T>(hb, hard_out + row * P.hard_stride, P.hard_stride, j);
+        pack_bits<BPS, T, GROUPS>(hb, reinterpret_cast<unsigned *>(hb + C::N + 16), hard_out + row * P.hard_stride, P.hard_stride, j, gid);
     }
 }
 
-#define OFDM_KERNEL_PROLOGUE_(GROUPS, TXK)                                            \
-    using S = Smem<C, GROUPS, TXK>;                                                \
+#define OFDM_KERNEL_PROLOGUE_(GROUPS, ...)                                            \
+    using S = Smem<C, GROUPS, __VA_ARGS__>;                                            \
     constexpr int T = C::T, PPT = C::PPT;                                              \
     extern __shared__ __align__(16) unsigned char smem_raw[];                          \
     const int tid = threadIdx.x, gid = tid / T, j = tid % T;                           \
-    float2 *b0 = S::buf0(smem_raw, gid), *b1 = b0 + C::BUF;                            \
+    float2 *b0 = S::buf0(smem_raw, gid), *b1 = b0 + (S::NBUF - 1) * C::BUF;                            \
     const float2 *tws = S::tws(smem_raw);                                              \
     float2 *stage = S::stage(smem_raw);                                                \
     float *redf = S::redf(smem_raw, gid);                                              \
     unsigned long long *redu = S::redu(smem_raw, gid);                                 \
     uint8_t *hb = S::hb(smem_raw, gid);                                                \
     float2 *hp = S::hp(smem_raw, gid);                                                 \
-    (void)redu; (void)redf; (void)stage; (void)hp;                                     \
+    float *ls = P.ls_stride ? reinterpret_cast<float *>(smem_raw + S::BYTES) + gid * P.ls_stride : nullptr; \
+    (void)redu; (void)redf; (void)stage; (void)hp; (void)ls;                           \
     for (int i = j; i < S::HB_STRIDE; i += T) hb[i] = 0;                               \
     fill_twiddles<C>(S::tws(smem_raw), P.tw, tid, S::THREADS);                              \
     __syncthreads();                                                                   \
@@ -608,16 +683,37 @@ template <class C> struct MinBlocksTx {
 //     The group walks its frames symbol by symbol; while symbol q is transformed the samples of
 //     symbol q+1 (next symbol of the frame, or the preamble of the group's next frame) are in flight.
 // ------------------------------------------------------------------------------------------------
-template <class C, int BPS, int GROUPS, bool PIL>
-__global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
+// Register target of the framed receiver: gains in registers want ~128 (PPT 8) / ~255 (PPT 16) per thread;
+// with the gains in shared memory 16 points per thread fit a 128..168-register budget.
+#ifndef OFDM_MINB_RXF_1024
+#define OFDM_MINB_RXF_1024 0
+#endif
+#ifndef OFDM_MINB_RXF_2048
+#define OFDM_MINB_RXF_2048 0
+#endif
+#ifndef OFDM_MINB_RXF_4096
+#define OFDM_MINB_RXF_4096 0
+#endif
+template <class C, bool GSM> struct MinBlocksRxF {
+    static constexpr int THREADS = C::T >= 128 ? C::T : 128;
+    static constexpr int REGS = (C::PPT == 16 && !GSM) ? 255 : 128;
+    static constexpr int byregs = 65536 / (THREADS * REGS);
+    static constexpr int forced = C::LOG2N == 10 ? OFDM_MINB_RXF_1024 : (C::LOG2N == 11 ? OFDM_MINB_RXF_2048 : (C::LOG2N == 12 ? OFDM_MINB_RXF_4096 : 0));
+    static constexpr int value = C::LOG2N <= 9 ? OFDM_MINB_SMALL : (forced > 0 ? forced : (byregs < 1 ? 1 : byregs));
+};
+
+template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB>
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
                  float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, float2 *__restrict__ H_out,
                  float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
-    OFDM_KERNEL_PROLOGUE(GROUPS)
+    OFDM_KERNEL_PROLOGUE_(GROUPS, false, PIL, GSM, SB)
     constexpr int N = C::N;
     const int L = N + P.cp, fs = P.m0 + P.d;
     const DataCtx<C, BPS> D(P, j);
+    Gains<C, GSM> G;
+    G.s = S::gs(smem_raw, gid) + j;
     const long long last_frame = n_frames - 1;
     const long long off0 = first + P.cp - P.sync_advance;
     long long f = gg < last_frame ? gg : last_frame;
@@ -627,7 +723,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
         long long fn = gg + (long long)(it + 1) * total_groups;
         fn = fn < last_frame ? fn : last_frame;
         const long long npos = off0 + fn * frame_stride;
-        float2 ys[C::PPT], ydup[2], G[C::PPT];
+        float2 ys[C::PPT], ydup[2];
         float pw = 0.f;
 #pragma unroll
         for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
@@ -637,37 +733,46 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
             take_pts<PPT, S::THREADS>(cur, stage, tid);
             // request the next symbol (the last request of the kernel re-reads a valid window)
             prefetch_pts<T, PPT, S::THREADS>(stage, x, (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos, n_samples, j, tid);
-            fft_group<C, false, GROUPS>(cur, tws, b0, b1, j, gid, pp);
+            fft_group<C, false, GROUPS, SB>(cur, tws, b0, b1, j, gid, pp);
             if (s < P.m0) {
                 sync_accumulate<C>(P, cur, s, j, ys, ydup, pw);
                 if (s == P.m0 - 1) {
                     float p_est, peak;
                     int delay;
-                    float2 H[C::PPT];
-                    sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
-                    chan_core<C>(P, ys, ydup, p_est, delay, P.inv_reg_eq, j, H, G);
-                    if (PIL) {                               // pilot mode equalises per symbol: keep only the rotation
+                    // the correlation sums are needed again after the delay bank has consumed them: park them
+                    // in the gain slots (GSM) or keep a register copy
+                    float2 keep[GSM ? 1 : C::PPT];
 #pragma unroll
-                        for (int m = 0; m < PPT; ++m) {
-                            const float2 w = __ldg(P.tw + ((delay * (j + m * T)) & (N - 1)));
-                            G[m] = make_float2(w.x, -w.y);
+                    for (int m = 0; m < PPT; ++m) {
+                        if (GSM) G.s[m * T] = ys[m]; else keep[GSM ? 0 : m] = ys[m];
+                    }
+                    sync_finish<C, GROUPS, SB>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+                    const float sc = p_est * P.chanest_scale;
+#pragma unroll
+                    for (int m = 0; m < PPT; ++m) {
+                        const int k = j + m * T;
+                        float2 y = GSM ? G.s[m * T] : keep[GSM ? 0 : m];
+                        if (k == P.dup_bin) y = ydup[1];                      // numpy fancy assignment: last index wins
+                        float2 h, g;
+                        chan_bin<N>(P, y, k, sc, delay, P.inv_reg_eq, h, g);
+                        if (PIL) {                               // pilot mode equalises per symbol: keep only the rotation
+                            const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));
+                            g = make_float2(w.x, -w.y);
                         }
+                        G.set(m, g);
+                        if (H_out != nullptr) H_out[f * N + k] = h;
                     }
                     if (j == 0) {
                         delay_out[f] = delay;
                         peak_out[f] = peak;
                         locked_out[f] = peak > P.gate_thresh ? 1 : 0;
                     }
-                    if (H_out != nullptr) {
-#pragma unroll
-                        for (int m = 0; m < PPT; ++m) H_out[f * N + j + m * T] = H[m];
-                    }
                 }
             } else if (PIL) {
-                data_epilogue_pilot<C, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, hp, j, gid, eq_out,
+                data_epilogue_pilot<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, hp, j, gid, eq_out,
                                                         llr_out, hard_out);
             } else {
-                data_epilogue<C, BPS, GROUPS>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, j, gid, eq_out, llr_out,
+                data_epilogue<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, j, gid, eq_out, llr_out,
                                                   hard_out);
             }
         }
@@ -704,7 +809,7 @@ rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long
             fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
             sync_accumulate<C>(P, v, s, j, ys, ydup, pw);
         }
-        sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+        sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);   // consumes ys
         if (j == 0) {
             peak_out[t] = peak;
             delay_out[t] = delay;
@@ -740,7 +845,12 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
             fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
             sync_accumulate<C>(P, v, s, j, ys, ydup, pw);
         }
-        sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, dfound);
+        {
+            float2 c[C::PPT];
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) c[m] = ys[m];
+            sync_finish<C, GROUPS>(P, c, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, dfound);
+        }
         chan_core<C>(P, ys, ydup, p_est, delay, P.inv_reg_eq_synch, j, H, G);
 #pragma unroll
         for (int m = 0; m < PPT; ++m) H_out[i * N + j + m * T] = H[m];
@@ -797,7 +907,8 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
         i = i < n_sym - 1 ? i : n_sym - 1;
         const int delay = delay_in[i];
         const long long hrow = hrow_in[i];
-        float2 v[C::PPT], G[C::PPT];
+        float2 v[C::PPT];
+        Gains<C, false> G;
         load_pts<T, PPT>(v, x, start_in[i], n_samples, j);
 #pragma unroll
         for (int m = 0; m < PPT; ++m) {
@@ -805,14 +916,14 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
             const float2 h = __ldg(Hmat + hrow * N + k);
             const float2 w = __ldg(P.tw + ((delay * k) & (N - 1)));
             const float den = cabs2(h) + P.inv_reg_eq;
-            G[m] = PIL ? make_float2(w.x, -w.y)
-                       : cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? __fdividef(1.f, den) : 0.f);
+            G.r[m] = PIL ? make_float2(w.x, -w.y)
+                         : cscale(cmulc(make_float2(h.x, -h.y), w), den > 0.f ? __fdividef(1.f, den) : 0.f);
         }
         fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
         if (PIL)
-            data_epilogue_pilot<C, BPS, GROUPS>(P, D, v, G, i, redf, hb, hp, j, gid, eq_out, llr_out, hard_out);
+            data_epilogue_pilot<C, BPS, GROUPS, false>(P, D, v, G, i, redf, hb, hp, j, gid, eq_out, llr_out, hard_out);
         else
-            data_epilogue<C, BPS, GROUPS>(P, D, v, G, i, redf, hb, j, gid, eq_out, llr_out, hard_out);
+            data_epilogue<C, BPS, GROUPS, false>(P, D, v, G, i, redf, hb, ls, j, gid, eq_out, llr_out, hard_out);
     }
 }
 
@@ -837,12 +948,14 @@ template <class C, int BPS, int GROUPS, bool PIL>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksTx<C>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
-    OFDM_KERNEL_PROLOGUE_(GROUPS, true)
+    OFDM_KERNEL_PROLOGUE_(GROUPS, true, false)
     constexpr int N = C::N;
     constexpr int WPT = PPT / 4;                             // a payload row spans at most PPT/4 packed words per thread
     constexpr int ZERO = 64;                                 // LUT entry that maps unused bins to 0
     const int L = N + P.cp, fs = P.m0 + P.d;
     // constellation table in shared memory: one LDS per bin instead of arithmetic on the bits
+    // (bank-private copies of the table were tried: the 2-way conflicts of random lookups cost less than the
+    // larger table's index arithmetic -- 2-3 % slower at every size, B200)
     float2 *lut = S::lut(smem_raw);
     for (int i = tid; i <= ZERO; i += S::THREADS) lut[i] = i < (1 << BPS) ? map_bits<BPS>((unsigned)i) : make_float2(0.f, 0.f);
     __syncthreads();
@@ -918,6 +1031,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             } else {
 #pragma unroll
                 for (int m = 0; m < PPT; ++m) {
+                    // (skipping the fetch + lookup for guard bins was tried: the branches cost 10-15 %, B200)
                     const uint8_t *q = rp + (m < PPT / 2 ? byp : byn) + m * (T * BPS / 8);
                     unsigned w = (unsigned)q[0] << 8;
                     if (BPS == 6) w |= (unsigned)q[1];

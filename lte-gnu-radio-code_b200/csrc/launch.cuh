@@ -18,23 +18,28 @@ struct LaunchDims {
 
 void count_launch();
 
-// grid = min(#CTAs needed, resident CTAs on the whole device): persistent groups stride over the work
+// grid = min(#CTAs needed, resident CTAs on the whole device): persistent groups stride over the work.
+// The occupancy query is cached per (device, dynamic shared-memory size).
 template <auto kernel>
 static inline cudaError_t plan_launch(int threads, int &smem, int groups, long long work, int sms, LaunchDims &dims) {
-    static int cached_dev = -1, cached_bps = 0;
+    static int cached_dev = -1, cached_bps = 0, cached_smem = -1, max_smem = -1;
     // tuning aid: OFDM_SMEM_PAD=<bytes> inflates the dynamic shared-memory request to lower occupancy
     static const int pad = getenv("OFDM_SMEM_PAD") ? atoi(getenv("OFDM_SMEM_PAD")) : 0;
     smem += pad;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev != cached_dev) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
+    if (dev != cached_dev || smem != cached_smem) {
+        if (dev != cached_dev || smem > max_smem) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            max_smem = smem;
+        }
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_bps, kernel, threads, smem);
         if (e != cudaSuccess) return e;
         if (cached_bps < 1) cached_bps = 1;
         cached_dev = dev;
+        cached_smem = smem;
     }
     const long long need = (work + groups - 1) / groups;
     const long long cap = (long long)sms * cached_bps;
@@ -58,20 +63,22 @@ template <int LOG2N>
 cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_samples, long long first,
                              long long frame_stride, long long n_frames, int *delay, float *peak, uint8_t *locked,
                              float2 *H, float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
-    using C = CfgRx<LOG2N>;
+    using C = CfgRxF<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
-    int SM = Smem<C, G>::BYTES;
+    constexpr bool GSM = RxFOpts<LOG2N>::GSM, SB = RxFOpts<LOG2N>::SB;
     if (n_frames <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
         if (P.pil_k) {
-            constexpr auto k = rx_frames_kernel<C, BPS, G, true>;
+            constexpr auto k = rx_frames_kernel<C, BPS, G, true, GSM, SB>;
+            int SM = Smem<C, G, false, true, GSM, SB>::BYTES;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
                                       eq, llr, hard);
         } else {
-            constexpr auto k = rx_frames_kernel<C, BPS, G, false>;
+            constexpr auto k = rx_frames_kernel<C, BPS, G, false, GSM, SB>;
+            int SM = Smem<C, G, false, false, GSM, SB>::BYTES + G * P.ls_stride * 4;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
@@ -99,6 +106,7 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
         } else {
             constexpr auto k = rx_demod_kernel<C, BPS, G, false>;
+            SM += G * P.ls_stride * 4;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
@@ -113,7 +121,7 @@ cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long
                       int sms) {
     using C = CfgTx<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
-    int SM = Smem<C, G, true>::BYTES;
+    int SM = Smem<C, G, true, false>::BYTES;
     if (n_sym_total <= 0) return cudaSuccess;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;

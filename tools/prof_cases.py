@@ -8,18 +8,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "lte-gnu-radio-code_b200", "python"))
 from ofdm_b200 import Modem, ModemConfig  # noqa: E402
 
+
+def n64(bps):
+    return (ModemConfig(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=bps, snr=100,
+                        gate=0.5, noise_var=0.01), 333334)
+
+
 CASES = {
-    "n64": (ModemConfig(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4, snr=100,
-                        gate=0.5, noise_var=0.01), 333334),
+    "n64": n64(4),
+    "n64_qpsk": n64(2),
+    "n64_64qam": n64(6),
     "lte": (ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100,
                         gate=0.5, noise_var=0.01), 4096),
     "n1024": (ModemConfig(nfft=1024, cp_len=256, num_synch_bins=1022, num_data_bins=960, m0=1, d=3, bps=4, snr=100,
                           gate=0.5, noise_var=0.01), 13107),
+    "n4096": (ModemConfig(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=3, bps=4, snr=100,
+                          gate=0.5, noise_var=0.01), 3276),
 }
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(CASES)
-    reps = 3
+    reps = 2
     for name in which:
         cfg, nf = CASES[name]
         m = Modem(cfg)
