@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OFDM_B200_ABI_VERSION 1
+#define OFDM_B200_ABI_VERSION 2
 
 enum {
     OFDM_OK = 0,
@@ -127,6 +127,36 @@ int ofdm_rx_frames(ofdm_plan *plan, const float *d_time, int64_t n_samples, int6
                    int64_t frame_stride, int64_t n_frames, int32_t *d_delay, float *d_peak,
                    uint8_t *d_locked, float *d_H, float *d_eq, float *d_llr, uint8_t *d_hard,
                    void *stream);
+
+/* Frequency-offset hypothesis bank (GRR/LEGACY/gr-ofdm-rx/python/SynchEstAndFO.py:196): hypothesis h
+ * multiplies sample n of every FFT window by exp(j*2pi*cycles_per_sample[h]*n), n = 0..nfft-1 (the
+ * reference's fo_range[h]/fs).  n_hyp = 0 removes the bank; at most 64 rows; not combined with comb pilots.
+ * With a bank installed
+ *   - the search evaluates every hypothesis per trial and reports the one with the largest peak (first on
+ *     ties) in d_hyp (nullable)                                            (SynchEstAndFO.py:247-277);
+ *   - ofdm_rx_chanest_cfo / ofdm_rx_demod_cfo de-rotate each lock / symbol with row d_hyp[i] (NULL = no
+ *     rotation)                                                            (:252-256, :331-333);
+ *   - the framed receiver picks the hypothesis per frame on the preamble, applies it to the frame's data
+ *     windows and reports it in d_hyp (nullable).
+ * phase_continuous = 0 restarts the phasor at every window like the reference, which leaves windows L samples
+ * apart with a relative phase of 2*pi*nu*L (harmless only for offsets far below the symbol rate).
+ * phase_continuous = 1 (extension, oracle-defined) continues it from the buffer origin: a window that opens at
+ * absolute sample s is de-rotated by exp(j*2pi*nu*(s+n)) -- what undoing a real carrier offset needs.
+ * The entry points without the _cfo suffix are the same calls with d_hyp = NULL. */
+int ofdm_plan_set_cfo_bank(ofdm_plan *plan, const double *cycles_per_sample, int32_t n_hyp, int32_t phase_continuous);
+int ofdm_rx_sync_search_cfo(ofdm_plan *plan, const float *d_time, int64_t n_samples, int64_t first_start,
+                            int64_t stride, int64_t n_trials, float *d_peak, int32_t *d_delay, int32_t *d_hyp,
+                            void *stream);
+int ofdm_rx_chanest_cfo(ofdm_plan *plan, const float *d_time, int64_t n_samples, const int64_t *d_pos,
+                        const int32_t *d_delay, const int32_t *d_hyp, int64_t n_locks, float *d_H, float *d_htime,
+                        float *d_synch_eq, void *stream);
+int ofdm_rx_demod_cfo(ofdm_plan *plan, const float *d_time, int64_t n_samples, const int64_t *d_start,
+                      const int32_t *d_delay, const int32_t *d_hrow, const int32_t *d_hyp, const float *d_H,
+                      int64_t n_sym, float *d_eq, float *d_llr, uint8_t *d_hard, void *stream);
+int ofdm_rx_frames_cfo(ofdm_plan *plan, const float *d_time, int64_t n_samples, int64_t first,
+                       int64_t frame_stride, int64_t n_frames, int32_t *d_delay, float *d_peak,
+                       uint8_t *d_locked, int32_t *d_hyp, float *d_H, float *d_eq, float *d_llr, uint8_t *d_hard,
+                       void *stream);
 
 /* Legacy QPSK soft/hard demapper with a buffer-wide noise estimate.  Replaces BitRecovery.work
  * (GRR/LEGACY/gr-ofdm-rx/python/BitRecovery.py:77-157).  Two launches: the first reduces

@@ -207,6 +207,7 @@ struct ofdm_plan {
     const KernelSet *ks;
     int device, sms, log2n;
     void *d_tables;                // one allocation holding every table
+    void *d_cfo;                   // frequency-offset hypothesis bank (optional)
     // staging for the host-buffer entry points (grown on demand, freed with the plan)
     static const int NSLOT = 2;
     cudaStream_t st[NSLOT];
@@ -399,6 +400,7 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
 int ofdm_plan_destroy(ofdm_plan *pl) {
     if (!pl) return OFDM_OK;
     cudaFree(pl->d_tables);
+    if (pl->d_cfo) cudaFree(pl->d_cfo);
     for (int i = 0; i < ofdm_plan::NSLOT; ++i) {
         if (pl->stage[i]) cudaFree(pl->stage[i]);
         if (pl->streams_made) {
@@ -424,48 +426,99 @@ int ofdm_tx_modulate(ofdm_plan *pl, const uint8_t *d_bits, float *d_time, int64_
     return OFDM_OK;
 }
 
-int ofdm_rx_sync_search(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first_start, int64_t stride,
-                        int64_t n_trials, float *d_peak, int32_t *d_delay, void *stream) {
-    if (pl && n_trials == 0) return OFDM_OK;
-    if (!pl || !d_time || !d_peak || !d_delay || n_trials < 0 || stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_sync_search: bad argument%s");
-    CU(pl->ks->sync_search(pl->dev, (const float2 *)d_time, n_samples, first_start, stride, n_trials, d_peak, d_delay,
-                           (cudaStream_t)stream, pl->sms),
-       "ofdm_rx_sync_search");
+int ofdm_plan_set_cfo_bank(ofdm_plan *pl, const double *cycles_per_sample, int32_t n_hyp, int32_t phase_continuous) {
+    if (!pl || n_hyp < 0 || n_hyp > 64 || (n_hyp > 0 && !cycles_per_sample))
+        return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: bad argument (0..64 hypotheses)%s");
+    if (n_hyp > 0 && pl->prm.pilot_spacing) return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: not available with comb pilots%s");
+    if (pl->d_cfo) cudaFree(pl->d_cfo);
+    pl->d_cfo = nullptr;
+    pl->dev.n_cfo = 0;
+    pl->dev.cfo = nullptr;
+    pl->dev.cfo_nu = nullptr;
+    pl->dev.cfo_continuous = 0;
+    if (n_hyp == 0) return OFDM_OK;
+    const int N = pl->prm.nfft;
+    std::vector<float2> tab((size_t)n_hyp * N);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int h = 0; h < n_hyp; ++h)
+        for (int n = 0; n < N; ++n) {
+            const double a = two_pi * cycles_per_sample[h] * (double)n;          // SynchEstAndFO.py:196
+            tab[(size_t)h * N + n] = make_float2((float)cos(a), (float)sin(a));
+        }
+    // one allocation: [n_hyp] double frequencies (8-byte aligned first), then the phasor rows
+    const size_t b_nu = ((size_t)n_hyp * sizeof(double) + 255) & ~(size_t)255;
+    CU(cudaMalloc(&pl->d_cfo, b_nu + tab.size() * sizeof(float2)), "ofdm_plan_set_cfo_bank(cudaMalloc)");
+    CU(cudaMemcpy(pl->d_cfo, cycles_per_sample, (size_t)n_hyp * sizeof(double), cudaMemcpyHostToDevice), "ofdm_plan_set_cfo_bank(cudaMemcpy)");
+    CU(cudaMemcpy((char *)pl->d_cfo + b_nu, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice), "ofdm_plan_set_cfo_bank(cudaMemcpy)");
+    pl->dev.cfo_nu = (const double *)pl->d_cfo;
+    pl->dev.cfo = (const float2 *)((char *)pl->d_cfo + b_nu);
+    pl->dev.n_cfo = n_hyp;
+    pl->dev.cfo_continuous = phase_continuous ? 1 : 0;
     return OFDM_OK;
 }
 
-int ofdm_rx_chanest(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_pos, const int32_t *d_delay,
-                    int64_t n_locks, float *d_H, float *d_htime, float *d_synch_eq, void *stream) {
+int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first_start, int64_t stride,
+                            int64_t n_trials, float *d_peak, int32_t *d_delay, int32_t *d_hyp, void *stream) {
+    if (pl && n_trials == 0) return OFDM_OK;
+    if (!pl || !d_time || !d_peak || !d_delay || n_trials < 0 || stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_sync_search: bad argument%s");
+    CU(pl->ks->sync_search(pl->dev, (const float2 *)d_time, n_samples, first_start, stride, n_trials, d_peak, d_delay,
+                           d_hyp, (cudaStream_t)stream, pl->sms),
+       "ofdm_rx_sync_search");
+    return OFDM_OK;
+}
+int ofdm_rx_sync_search(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first_start, int64_t stride,
+                        int64_t n_trials, float *d_peak, int32_t *d_delay, void *stream) {
+    return ofdm_rx_sync_search_cfo(pl, d_time, n_samples, first_start, stride, n_trials, d_peak, d_delay, nullptr, stream);
+}
+
+int ofdm_rx_chanest_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_pos,
+                        const int32_t *d_delay, const int32_t *d_hyp, int64_t n_locks, float *d_H, float *d_htime,
+                        float *d_synch_eq, void *stream) {
     if (pl && n_locks == 0) return OFDM_OK;
     if (!pl || !d_time || !d_pos || !d_delay || !d_H || n_locks < 0) return fail(OFDM_EINVAL, "ofdm_rx_chanest: bad argument%s");
-    CU(pl->ks->chanest(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_pos, d_delay, n_locks,
+    CU(pl->ks->chanest(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_pos, d_delay, d_hyp, n_locks,
                        (float2 *)d_H, (float2 *)d_htime, (float2 *)d_synch_eq, (cudaStream_t)stream, pl->sms),
        "ofdm_rx_chanest");
     return OFDM_OK;
 }
+int ofdm_rx_chanest(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_pos, const int32_t *d_delay,
+                    int64_t n_locks, float *d_H, float *d_htime, float *d_synch_eq, void *stream) {
+    return ofdm_rx_chanest_cfo(pl, d_time, n_samples, d_pos, d_delay, nullptr, n_locks, d_H, d_htime, d_synch_eq, stream);
+}
 
-int ofdm_rx_demod(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_start, const int32_t *d_delay,
-                  const int32_t *d_hrow, const float *d_H, int64_t n_sym, float *d_eq, float *d_llr, uint8_t *d_hard,
-                  void *stream) {
+int ofdm_rx_demod_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_start,
+                      const int32_t *d_delay, const int32_t *d_hrow, const int32_t *d_hyp, const float *d_H, int64_t n_sym,
+                      float *d_eq, float *d_llr, uint8_t *d_hard, void *stream) {
     if (pl && n_sym == 0) return OFDM_OK;
     if (!pl || !d_time || !d_start || !d_delay || !d_hrow || !d_H || !d_eq || n_sym < 0)
         return fail(OFDM_EINVAL, "ofdm_rx_demod: bad argument%s");
-    CU(pl->ks->rx_demod(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_start, d_delay, d_hrow,
+    CU(pl->ks->rx_demod(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_start, d_delay, d_hrow, d_hyp,
                         (const float2 *)d_H, n_sym, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms),
        "ofdm_rx_demod");
     return OFDM_OK;
 }
+int ofdm_rx_demod(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_start, const int32_t *d_delay,
+                  const int32_t *d_hrow, const float *d_H, int64_t n_sym, float *d_eq, float *d_llr, uint8_t *d_hard,
+                  void *stream) {
+    return ofdm_rx_demod_cfo(pl, d_time, n_samples, d_start, d_delay, d_hrow, nullptr, d_H, n_sym, d_eq, d_llr, d_hard, stream);
+}
 
-int ofdm_rx_frames(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first, int64_t frame_stride,
-                   int64_t n_frames, int32_t *d_delay, float *d_peak, uint8_t *d_locked, float *d_H, float *d_eq,
-                   float *d_llr, uint8_t *d_hard, void *stream) {
+int ofdm_rx_frames_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first, int64_t frame_stride,
+                       int64_t n_frames, int32_t *d_delay, float *d_peak, uint8_t *d_locked, int32_t *d_hyp, float *d_H,
+                       float *d_eq, float *d_llr, uint8_t *d_hard, void *stream) {
     if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_time || !d_delay || !d_peak || !d_locked || !d_eq || n_frames < 0)
         return fail(OFDM_EINVAL, "ofdm_rx_frames: bad argument%s");
     CU(pl->ks->rx_frames(pl->dev, (const float2 *)d_time, n_samples, first, frame_stride, n_frames, d_delay, d_peak,
-                         d_locked, (float2 *)d_H, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms),
+                         d_locked, d_hyp, (float2 *)d_H, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms),
        "ofdm_rx_frames");
     return OFDM_OK;
+}
+int ofdm_rx_frames(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first, int64_t frame_stride,
+                   int64_t n_frames, int32_t *d_delay, float *d_peak, uint8_t *d_locked, float *d_H, float *d_eq,
+                   float *d_llr, uint8_t *d_hard, void *stream) {
+    return ofdm_rx_frames_cfo(pl, d_time, n_samples, first, frame_stride, n_frames, d_delay, d_peak, d_locked, nullptr, d_H,
+                              d_eq, d_llr, d_hard, stream);
 }
 
 int ofdm_bit_recovery(ofdm_plan *pl, const float *d_in, int64_t n, float *d_llr0, float *d_llr1, uint8_t *d_hard,
@@ -585,7 +638,7 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
         if (hi < lo) hi = lo;
         CU(cudaMemcpyAsync(din, h_time + 2 * lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, st), "H2D");
         CU(pl->ks->rx_frames(pl->dev, (const float2 *)din, hi - lo, first + f0 * frame_stride - lo, frame_stride, nf, ddl,
-                             dpk, dlk, nullptr, (float2 *)deq, h_llr ? dll : nullptr, h_hard ? dhd : nullptr, st, pl->sms),
+                             dpk, dlk, nullptr, nullptr, (float2 *)deq, h_llr ? dll : nullptr, h_hard ? dhd : nullptr, st, pl->sms),
            "ofdm_rx_frames_host(kernel)");
         if (h_delay) CU(cudaMemcpyAsync(h_delay + f0, ddl, nf * 4, cudaMemcpyDeviceToHost, st), "D2H");
         if (h_peak) CU(cudaMemcpyAsync(h_peak + f0, dpk, nf * 4, cudaMemcpyDeviceToHost, st), "D2H");

@@ -33,6 +33,13 @@ struct DevParams {
     // comb pilots in data symbols (extension): positions pil_off + i*pil_k of the used-bin list
     int pil_k, pil_off, n_pil, ndd;   // ndd = payload bins per data symbol = ndb - n_pil
     int ls_stride;                    // floats per group of the 64-QAM LLR row staging area (0: none)
+    // frequency-offset hypothesis bank (SynchEstAndFO.py:196): cfo[h][n] = exp(j*2pi*nu_h*n), n = 0..N-1
+    int n_cfo;
+    const float2 *cfo;
+    // extension: continue every hypothesis' phasor from the buffer origin, exp(j*2pi*nu_h*(start+n)), instead of
+    // restarting it at each window like the reference (needed to undo a real carrier offset)
+    int cfo_continuous;
+    const double *cfo_nu;             // [n_cfo] cycles per sample
     const float2 *pilot_tx;   // [N]      pilot value in FFT bin k (0 elsewhere)
 };
 
@@ -124,6 +131,24 @@ __device__ __forceinline__ void load_pts(float2 (&v)[PPT], const float2 *__restr
             v[m] = (i >= 0 && i < n) ? __ldg(x + i) : make_float2(0.f, 0.f);
         }
     }
+}
+
+// CFO de-rotation of the window that opens at absolute sample `start`: sample n times row[n]
+// (window-local, SynchEstAndFO.py:254,:332), times exp(j*2pi*nu*start) in the phase-continuous extension.
+__device__ __forceinline__ float2 cfo_window_phase(const DevParams &P, int h, long long start) {
+    if (!P.cfo_continuous) return make_float2(1.f, 0.f);
+    double t = P.cfo_nu[h] * (double)start;
+    t -= floor(t);
+    double sn, cs;
+    sincospi(2.0 * t, &sn, &cs);
+    return make_float2((float)cs, (float)sn);
+}
+template <int T, int PPT>
+__device__ __forceinline__ void rotate_pts(const DevParams &P, float2 (&v)[PPT], int h, long long start, int j) {
+    const float2 *row = P.cfo + (long long)h * (PPT * T);
+    const float2 ph = cfo_window_phase(P, h, start);
+#pragma unroll
+    for (int m = 0; m < PPT; ++m) v[m] = cmul(v[m], cmul(__ldg(row + j + m * T), ph));
 }
 
 template <int T, int GROUPS>
@@ -702,12 +727,17 @@ template <class C, bool GSM> struct MinBlocksRxF {
     static constexpr int value = C::LOG2N <= 9 ? OFDM_MINB_SMALL : (forced > 0 ? forced : (byregs < 1 ? 1 : byregs));
 };
 
-template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB>
+// CFO: the plan carries a frequency-offset hypothesis bank (SynchEstAndFO.py:196,:247-277,:331-333).  The
+// preamble is then evaluated once per hypothesis (window re-read through L1/L2, de-rotated, transformed,
+// correlated), the hypothesis with the largest peak wins (first on ties) and its phasor row multiplies every
+// data window of the frame before the FFT.
+template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
-                 float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, float2 *__restrict__ H_out,
-                 float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
+                 float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, int *__restrict__ hyp_out,
+                 float2 *__restrict__ H_out, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
+                 uint8_t *__restrict__ hard_out) {
     OFDM_KERNEL_PROLOGUE_(GROUPS, false, PIL, GSM, SB)
     constexpr int N = C::N;
     const int L = N + P.cp, fs = P.m0 + P.d;
@@ -725,6 +755,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
         const long long npos = off0 + fn * frame_stride;
         float2 ys[C::PPT], ydup[2];
         float pw = 0.f;
+        int hyp = 0;
 #pragma unroll
         for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
         ydup[0] = ydup[1] = make_float2(0.f, 0.f);
@@ -733,12 +764,46 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
             take_pts<PPT, S::THREADS>(cur, stage, tid);
             // request the next symbol (the last request of the kernel re-reads a valid window)
             prefetch_pts<T, PPT, S::THREADS>(stage, x, (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos, n_samples, j, tid);
-            fft_group<C, false, GROUPS, SB>(cur, tws, b0, b1, j, gid, pp);
+            if (!CFO || s >= P.m0) {                 // with a CFO bank the preamble is transformed per hypothesis below
+                if (CFO) rotate_pts<T, PPT>(P, cur, hyp, pos + (long long)s * L, j);
+                fft_group<C, false, GROUPS, SB>(cur, tws, b0, b1, j, gid, pp);
+            }
             if (s < P.m0) {
-                sync_accumulate<C>(P, cur, s, j, ys, ydup, pw);
+                if (!CFO) sync_accumulate<C>(P, cur, s, j, ys, ydup, pw);
                 if (s == P.m0 - 1) {
                     float p_est, peak;
                     int delay;
+                    if (CFO) {
+                        p_est = 0.f;
+                        peak = -1.f;
+                        delay = 0;
+                        // pass h < n_cfo scores hypothesis h; the final pass rebuilds the winner's correlation sums
+                        for (int h = 0; h <= P.n_cfo; ++h) {
+                            const int hh = h < P.n_cfo ? h : hyp;
+#pragma unroll
+                            for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
+                            ydup[0] = ydup[1] = make_float2(0.f, 0.f);
+                            pw = 0.f;
+                            for (int s2 = 0; s2 < P.m0; ++s2) {
+                                float2 v[C::PPT];
+                                load_pts<T, PPT>(v, x, pos + (long long)s2 * L, n_samples, j);
+                                rotate_pts<T, PPT>(P, v, hh, pos + (long long)s2 * L, j);
+                                fft_group<C, false, GROUPS, SB>(v, tws, b0, b1, j, gid, pp);
+                                sync_accumulate<C>(P, v, s2, j, ys, ydup, pw);
+                            }
+                            if (h < P.n_cfo) {
+                                float pe, pk;
+                                int dl;
+                                sync_finish<C, GROUPS, SB>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, pe, pk, dl);
+                                if (pk > peak) {
+                                    peak = pk;
+                                    p_est = pe;
+                                    delay = dl;
+                                    hyp = h;
+                                }
+                            }
+                        }
+                    }
                     // the correlation sums are needed again after the delay bank has consumed them: park them
                     // in the gain slots (GSM) or keep a register copy
                     float2 keep[GSM ? 1 : C::PPT];
@@ -746,7 +811,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                     for (int m = 0; m < PPT; ++m) {
                         if (GSM) G.s[m * T] = ys[m]; else keep[GSM ? 0 : m] = ys[m];
                     }
-                    sync_finish<C, GROUPS, SB>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+                    if (!CFO) sync_finish<C, GROUPS, SB>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
                     const float sc = p_est * P.chanest_scale;
 #pragma unroll
                     for (int m = 0; m < PPT; ++m) {
@@ -766,6 +831,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                         delay_out[f] = delay;
                         peak_out[f] = peak;
                         locked_out[f] = peak > P.gate_thresh ? 1 : 0;
+                        if (CFO && hyp_out != nullptr) hyp_out[f] = hyp;
                     }
                 }
             } else if (PIL) {
@@ -789,30 +855,42 @@ template <class C, int GROUPS>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
                       long long stride, long long n_trials, int iters, float *__restrict__ peak_out,
-                      int *__restrict__ delay_out) {
+                      int *__restrict__ delay_out, int *__restrict__ hyp_out) {
     OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
     const int L = N + P.cp;
+    const int n_hyp = P.n_cfo > 0 ? P.n_cfo : 1;                 // with a CFO bank: every hypothesis, best peak wins
     for (int it = 0; it < iters; ++it) {
         long long t = gg + (long long)it * total_groups;
         t = t < n_trials - 1 ? t : n_trials - 1;
         const long long pos = first_start + t * stride;
-        float2 ys[C::PPT], ydup[2];
-        float pw = 0.f, p_est, peak;
-        int delay;
+        float best_peak = -1.f;
+        int best_delay = 0, best_hyp = 0;
+        for (int h = 0; h < n_hyp; ++h) {
+            float2 ys[C::PPT], ydup[2];
+            float pw = 0.f, p_est, peak;
+            int delay;
 #pragma unroll
-        for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
-        ydup[0] = ydup[1] = make_float2(0.f, 0.f);
-        for (int s = 0; s < P.m0; ++s) {
-            float2 v[C::PPT];
-            load_pts<T, PPT>(v, x, pos + (long long)s * L, n_samples, j);
-            fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
-            sync_accumulate<C>(P, v, s, j, ys, ydup, pw);
+            for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
+            ydup[0] = ydup[1] = make_float2(0.f, 0.f);
+            for (int s = 0; s < P.m0; ++s) {
+                float2 v[C::PPT];
+                load_pts<T, PPT>(v, x, pos + (long long)s * L, n_samples, j);
+                if (P.n_cfo > 0) rotate_pts<T, PPT>(P, v, h, pos + (long long)s * L, j);
+                fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
+                sync_accumulate<C>(P, v, s, j, ys, ydup, pw);
+            }
+            sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);   // consumes ys
+            if (peak > best_peak) {                              // first maximum, like np.argmax (SynchEstAndFO.py:274-277)
+                best_peak = peak;
+                best_delay = delay;
+                best_hyp = h;
+            }
         }
-        sync_finish<C, GROUPS>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);   // consumes ys
         if (j == 0) {
-            peak_out[t] = peak;
-            delay_out[t] = delay;
+            peak_out[t] = best_peak;
+            delay_out[t] = best_delay;
+            if (hyp_out != nullptr) hyp_out[t] = best_hyp;
         }
     }
 }
@@ -823,8 +901,9 @@ rx_sync_search_kernel(const DevParams P, const float2 *__restrict__ x, long long
 template <class C, int GROUPS>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
-                  const long long *__restrict__ pos_in, const int *__restrict__ delay_in, long long n_locks, int iters,
-                  float2 *__restrict__ H_out, float2 *__restrict__ htime_out, float2 *__restrict__ synch_eq_out) {
+                  const long long *__restrict__ pos_in, const int *__restrict__ delay_in,
+                  const int *__restrict__ hyp_in, long long n_locks, int iters, float2 *__restrict__ H_out,
+                  float2 *__restrict__ htime_out, float2 *__restrict__ synch_eq_out) {
     OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
     const int L = N + P.cp;
@@ -833,6 +912,7 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
         i = i < n_locks - 1 ? i : n_locks - 1;
         const long long pos = pos_in[i];
         const int delay = delay_in[i];
+        const int hyp = (hyp_in != nullptr && P.n_cfo > 0) ? hyp_in[i] : -1;
         float2 ys[C::PPT], ydup[2], H[C::PPT], G[C::PPT];
         float pw = 0.f, p_est, peak;
         int dfound;
@@ -842,6 +922,7 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
         for (int s = 0; s < P.m0; ++s) {
             float2 v[C::PPT];
             load_pts<T, PPT>(v, x, pos + (long long)s * L, n_samples, j);
+            if (hyp >= 0) rotate_pts<T, PPT>(P, v, hyp, pos + (long long)s * L, j);
             fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
             sync_accumulate<C>(P, v, s, j, ys, ydup, pw);
         }
@@ -866,6 +947,7 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
             for (int s = 0; s < P.m0; ++s) {
                 float2 v[C::PPT];
                 load_pts<T, PPT>(v, x, pos + (long long)s * L, n_samples, j);
+                if (hyp >= 0) rotate_pts<T, PPT>(P, v, hyp, pos + (long long)s * L, j);
                 fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
 #pragma unroll
                 for (int m = 0; m < PPT; ++m) {
@@ -897,7 +979,8 @@ template <class C, int BPS, int GROUPS, bool PIL>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
                 const long long *__restrict__ start_in, const int *__restrict__ delay_in,
-                const int *__restrict__ hrow_in, const float2 *__restrict__ Hmat, long long n_sym, int iters,
+                const int *__restrict__ hrow_in, const int *__restrict__ hyp_in, const float2 *__restrict__ Hmat,
+                long long n_sym, int iters,
                 float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
     OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
@@ -910,6 +993,7 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
         float2 v[C::PPT];
         Gains<C, false> G;
         load_pts<T, PPT>(v, x, start_in[i], n_samples, j);
+        if (hyp_in != nullptr && P.n_cfo > 0) rotate_pts<T, PPT>(P, v, hyp_in[i], start_in[i], j);
 #pragma unroll
         for (int m = 0; m < PPT; ++m) {
             const int k = j + m * T;

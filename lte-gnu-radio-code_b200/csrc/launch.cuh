@@ -62,37 +62,36 @@ static inline cudaError_t plan_launch(int threads, int &smem, int groups, long l
 template <int LOG2N>
 cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_samples, long long first,
                              long long frame_stride, long long n_frames, int *delay, float *peak, uint8_t *locked,
-                             float2 *H, float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
+                             int *hyp, float2 *H, float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
     using C = CfgRxF<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
     constexpr bool GSM = RxFOpts<LOG2N>::GSM, SB = RxFOpts<LOG2N>::SB;
     if (n_frames <= 0) return cudaSuccess;
+    if (P.pil_k && P.n_cfo) return cudaErrorInvalidValue;       // the hypothesis bank is not combined with comb pilots
+#define OFDM_LAUNCH_RXF(PIL, CFO)                                                                                    \
+    {                                                                                                                \
+        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO>;                                           \
+        int SM = Smem<C, G, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : G * P.ls_stride * 4);                           \
+        cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);                                                 \
+        if (e != cudaSuccess) return e;                                                                              \
+        k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, hyp, \
+                                  H, eq, llr, hard);                                                                 \
+    }
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
-        if (P.pil_k) {
-            constexpr auto k = rx_frames_kernel<C, BPS, G, true, GSM, SB>;
-            int SM = Smem<C, G, false, true, GSM, SB>::BYTES;
-            cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
-            if (e != cudaSuccess) return e;
-            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
-                                      eq, llr, hard);
-        } else {
-            constexpr auto k = rx_frames_kernel<C, BPS, G, false, GSM, SB>;
-            int SM = Smem<C, G, false, false, GSM, SB>::BYTES + G * P.ls_stride * 4;
-            cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);
-            if (e != cudaSuccess) return e;
-            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, H,
-                                      eq, llr, hard);
-        }
+        if (P.pil_k) OFDM_LAUNCH_RXF(true, false)
+        else if (P.n_cfo) OFDM_LAUNCH_RXF(false, true)
+        else OFDM_LAUNCH_RXF(false, false)
         count_launch();
     })
+#undef OFDM_LAUNCH_RXF
     return cudaGetLastError();
 }
 
 template <int LOG2N>
 cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_samples, const long long *start,
-                            const int *delay, const int *hrow, const float2 *H, long long n_sym, float2 *eq,
-                            float *llr, uint8_t *hard, cudaStream_t st, int sms) {
+                            const int *delay, const int *hrow, const int *hyp, const float2 *H, long long n_sym,
+                            float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
     using C = CfgRx<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
     int SM = Smem<C, G>::BYTES;
@@ -103,13 +102,13 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
             constexpr auto k = rx_demod_kernel<C, BPS, G, true>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
-            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
+            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard);
         } else {
             constexpr auto k = rx_demod_kernel<C, BPS, G, false>;
             SM += G * P.ls_stride * 4;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
-            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, H, n_sym, d.iters, eq, llr, hard);
+            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard);
         }
         count_launch();
     })
@@ -143,8 +142,8 @@ cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long
 
 template <int LOG2N>
 cudaError_t launch_sync_search(const DevParams &P, const float2 *x, long long n_samples, long long first_start,
-                               long long stride, long long n_trials, float *peak, int *delay, cudaStream_t st,
-                               int sms) {
+                               long long stride, long long n_trials, float *peak, int *delay, int *hyp,
+                               cudaStream_t st, int sms) {
     using C = CfgRx<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
     int SM = Smem<C, G>::BYTES;
@@ -153,15 +152,15 @@ cudaError_t launch_sync_search(const DevParams &P, const float2 *x, long long n_
     LaunchDims d;
     cudaError_t e = plan_launch<k>(TH, SM, G, n_trials, sms, d);
     if (e != cudaSuccess) return e;
-    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first_start, stride, n_trials, d.iters, peak, delay);
+    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first_start, stride, n_trials, d.iters, peak, delay, hyp);
     count_launch();
     return cudaGetLastError();
 }
 
 template <int LOG2N>
 cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samples, const long long *pos,
-                           const int *delay, long long n_locks, float2 *H, float2 *htime, float2 *synch_eq,
-                           cudaStream_t st, int sms) {
+                           const int *delay, const int *hyp, long long n_locks, float2 *H, float2 *htime,
+                           float2 *synch_eq, cudaStream_t st, int sms) {
     using C = CfgRx<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
     int SM = Smem<C, G>::BYTES;
@@ -170,7 +169,7 @@ cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samp
     LaunchDims d;
     cudaError_t e = plan_launch<k>(TH, SM, G, n_locks, sms, d);
     if (e != cudaSuccess) return e;
-    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, pos, delay, n_locks, d.iters, H, htime, synch_eq);
+    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, pos, delay, hyp, n_locks, d.iters, H, htime, synch_eq);
     count_launch();
     return cudaGetLastError();
 }
@@ -178,14 +177,14 @@ cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samp
 // one table of launchers per transform size
 struct KernelSet {
     cudaError_t (*rx_frames)(const DevParams &, const float2 *, long long, long long, long long, long long, int *,
-                             float *, uint8_t *, float2 *, float2 *, float *, uint8_t *, cudaStream_t, int);
+                             float *, uint8_t *, int *, float2 *, float2 *, float *, uint8_t *, cudaStream_t, int);
     cudaError_t (*rx_demod)(const DevParams &, const float2 *, long long, const long long *, const int *, const int *,
-                            const float2 *, long long, float2 *, float *, uint8_t *, cudaStream_t, int);
+                            const int *, const float2 *, long long, float2 *, float *, uint8_t *, cudaStream_t, int);
     cudaError_t (*tx)(const DevParams &, const uint8_t *, float2 *, long long, cudaStream_t, int);
     cudaError_t (*sync_search)(const DevParams &, const float2 *, long long, long long, long long, long long, float *,
-                               int *, cudaStream_t, int);
-    cudaError_t (*chanest)(const DevParams &, const float2 *, long long, const long long *, const int *, long long,
-                           float2 *, float2 *, float2 *, cudaStream_t, int);
+                               int *, int *, cudaStream_t, int);
+    cudaError_t (*chanest)(const DevParams &, const float2 *, long long, const long long *, const int *, const int *,
+                           long long, float2 *, float2 *, float2 *, cudaStream_t, int);
 };
 
 #define OFDM_DEFINE_KERNELSET(LOG2N)                                                               \

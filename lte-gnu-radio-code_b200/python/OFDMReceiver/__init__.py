@@ -1,6 +1,9 @@
-"""OFDMReceiver -- the legacy sink block that turns equalised symbols into soft/hard bits
-(GRC template: OFDMReceiver.BitRecovery(modulation, directory_name, diagnostics),
-GRR/LEGACY/gr-ofdm-rx/grc/OFDMReceiver_BitRecovery.block.yml:24)."""
+"""OFDMReceiver -- the legacy receiver module (GRR/LEGACY/gr-ofdm-rx): the sink block that turns
+equalised symbols into soft/hard bits (GRC template OFDMReceiver.BitRecovery(modulation,
+directory_name, diagnostics), grc/OFDMReceiver_BitRecovery.block.yml:24) and the receiver with a
+frequency-offset hypothesis bank (OFDMReceiver.SynchEstAndFO(case, fo_range, directory_name,
+file_name_cest, diagnostics), grc/OFDMReceiver_SynchEstAndFO.block.yml:33-35)."""
 from .BitRecovery import BitRecovery
+from .SynchEstAndFO import SynchEstAndFO
 
-__all__ = ["BitRecovery"]
+__all__ = ["BitRecovery", "SynchEstAndFO"]

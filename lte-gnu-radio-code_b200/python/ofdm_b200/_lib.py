@@ -38,6 +38,11 @@ SIGNATURES = {
     "ofdm_rx_chanest": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _P]),
     "ofdm_rx_demod": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "ofdm_rx_frames": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ofdm_plan_set_cfo_bank": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    "ofdm_rx_sync_search_cfo": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P]),
+    "ofdm_rx_chanest_cfo": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "ofdm_rx_demod_cfo": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "ofdm_rx_frames_cfo": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ofdm_bit_recovery": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P]),
     "ofdm_counters": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P]),
     "ofdm_channel_awgn": (C.c_int, [_P, _P, _P, _I64, _P, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P]),
@@ -65,7 +70,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.ofdm_abi_version() != 1:
+        if l.ofdm_abi_version() != 2:
             raise OfdmError("libofdm_b200.so ABI version mismatch")
         _lib = l
     return _lib

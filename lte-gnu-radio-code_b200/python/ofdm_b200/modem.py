@@ -133,6 +133,7 @@ class Modem:
         self.cfg = cfg
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._h = C.c_void_p()
+        self.n_cfo = 0
         with torch.cuda.device(self.device):
             s = cfg.to_struct()
             _lib.check(_lib.lib().ofdm_plan_create(C.byref(s), C.byref(self._h)))
@@ -150,6 +151,19 @@ class Modem:
             self.close()
         except Exception:
             pass
+
+    # ---- frequency-offset hypothesis bank ------------------------------------------------------
+    def set_cfo_bank(self, fo_range, fs, phase_continuous=False):
+        """Install (or with an empty list remove) the bank of GRR/LEGACY/gr-ofdm-rx/python/SynchEstAndFO.py:196:
+        hypothesis h multiplies sample n of every FFT window by exp(j*2pi*fo_range[h]/fs*n).  From then on
+        sync_search / rx_frames report the winning hypothesis and chanest / demod accept one per item.
+        phase_continuous=True (extension) continues the phasor from the buffer origin instead of restarting it at
+        every window, which is what a real carrier offset needs."""
+        nu = np.asarray([float(f) / float(fs) for f in fo_range], dtype=np.float64)
+        self.n_cfo = int(nu.size)
+        with _torch().cuda.device(self.device):
+            _lib.check(_lib.lib().ofdm_plan_set_cfo_bank(self._h, C.c_void_p(nu.ctypes.data if nu.size else 0), nu.size,
+                                                         1 if phase_continuous else 0))
 
     # ---- helpers ---------------------------------------------------------------------------
     def _c64(self, x):
@@ -189,9 +203,11 @@ class Modem:
             o["llr"] = self.empty((nd, cfg.payload_bins * cfg.bps), torch.float32) if want_llr else None
             o["hard"] = self.empty((nd, cfg.hard_stride), torch.uint8) if want_hard else None
             o["h"] = self.empty((n_frames, cfg.nfft), torch.complex64) if want_h else None
-        _lib.check(_lib.lib().ofdm_rx_frames(
+            o["hyp"] = self.empty((n_frames,), torch.int32) if self.n_cfo else None
+        _lib.check(_lib.lib().ofdm_rx_frames_cfo(
             self._h, _ptr(rx), rx.numel(), first, fs, n_frames, _ptr(o["delay"]), _ptr(o["peak"]),
-            _ptr(o["locked"]), _ptr(o.get("h")), _ptr(o["eq"]), _ptr(o.get("llr")), _ptr(o.get("hard")), _stream()))
+            _ptr(o["locked"]), _ptr(o.get("hyp")), _ptr(o.get("h")), _ptr(o["eq"]), _ptr(o.get("llr")),
+            _ptr(o.get("hard")), _stream()))
         return o
 
     # ---- RX, modular (what the stream blocks' work() drives) ---------------------------------
@@ -200,11 +216,16 @@ class Modem:
         rx = self._c64(rx)
         peak = self.empty((n_trials,), torch.float32)
         delay = self.empty((n_trials,), torch.int32)
-        _lib.check(_lib.lib().ofdm_rx_sync_search(self._h, _ptr(rx), rx.numel(), first_start, stride, n_trials,
-                                                  _ptr(peak), _ptr(delay), _stream()))
-        return peak, delay
+        if not self.n_cfo:
+            _lib.check(_lib.lib().ofdm_rx_sync_search(self._h, _ptr(rx), rx.numel(), first_start, stride, n_trials,
+                                                      _ptr(peak), _ptr(delay), _stream()))
+            return peak, delay
+        hyp = self.empty((n_trials,), torch.int32)
+        _lib.check(_lib.lib().ofdm_rx_sync_search_cfo(self._h, _ptr(rx), rx.numel(), first_start, stride, n_trials,
+                                                      _ptr(peak), _ptr(delay), _ptr(hyp), _stream()))
+        return peak, delay, hyp
 
-    def chanest(self, rx, pos, delay, want_aux=False):
+    def chanest(self, rx, pos, delay, want_aux=False, hyp=None):
         torch = _torch()
         rx = self._c64(rx)
         n = pos.numel()
@@ -212,11 +233,12 @@ class Modem:
         h = self.empty((n, self.cfg.nfft), torch.complex64)
         ht = self.empty((n, self.cfg.nfft), torch.complex64) if want_aux else None
         se = self.empty((n, self.cfg.mm), torch.complex64) if want_aux else None
-        _lib.check(_lib.lib().ofdm_rx_chanest(self._h, _ptr(rx), rx.numel(), _ptr(pos), _ptr(delay), n, _ptr(h),
-                                              _ptr(ht), _ptr(se), _stream()))
+        assert hyp is None or (hyp.dtype == torch.int32 and hyp.numel() == n)
+        _lib.check(_lib.lib().ofdm_rx_chanest_cfo(self._h, _ptr(rx), rx.numel(), _ptr(pos), _ptr(delay), _ptr(hyp), n,
+                                                  _ptr(h), _ptr(ht), _ptr(se), _stream()))
         return h, ht, se
 
-    def demod(self, rx, start, delay, hrow, h, want_llr=False, want_hard=False):
+    def demod(self, rx, start, delay, hrow, h, want_llr=False, want_hard=False, hyp=None):
         torch = _torch()
         cfg = self.cfg
         rx = self._c64(rx)
@@ -225,8 +247,10 @@ class Modem:
         eq = self.empty((n, cfg.payload_bins), torch.complex64)
         llr = self.empty((n, cfg.payload_bins * cfg.bps), torch.float32) if want_llr else None
         hard = self.empty((n, cfg.hard_stride), torch.uint8) if want_hard else None
-        _lib.check(_lib.lib().ofdm_rx_demod(self._h, _ptr(rx), rx.numel(), _ptr(start), _ptr(delay), _ptr(hrow),
-                                            _ptr(self._c64(h)), n, _ptr(eq), _ptr(llr), _ptr(hard), _stream()))
+        assert hyp is None or (hyp.dtype == torch.int32 and hyp.numel() == n)
+        _lib.check(_lib.lib().ofdm_rx_demod_cfo(self._h, _ptr(rx), rx.numel(), _ptr(start), _ptr(delay), _ptr(hrow),
+                                                _ptr(hyp), _ptr(self._c64(h)), n, _ptr(eq), _ptr(llr), _ptr(hard),
+                                                _stream()))
         return eq, llr, hard
 
     # ---- legacy demapper, counters, test-bench channel ----------------------------------------

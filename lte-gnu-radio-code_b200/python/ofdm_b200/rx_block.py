@@ -72,16 +72,17 @@ class RxBlockBase(gr.sync_block):
         nv = self._n_valid_trials(n)
         if nv == 0:
             return np.zeros(0, np.float32), np.zeros(0, np.int32)
-        peak, delay = self.modem.sync_search(rx, self.cfg.cp_len, self.cfg.stride, nv)
-        return peak.cpu().numpy(), delay.cpu().numpy()
+        res = self.modem.sync_search(rx, self.cfg.cp_len, self.cfg.stride, nv)
+        return tuple(r.cpu().numpy() for r in res)          # (peak, delay) or, with a CFO bank, (peak, delay, hyp)
 
-    def _estimate_into(self, rx, rows, pos, delay):
+    def _estimate_into(self, rx, rows, pos, delay, hyp=None):
         """Channel estimates for new locks -> state rows; aux outputs only when diagnostics ask."""
         torch = self._torch
         dev = self.modem.device
         want_aux = True
         h, ht, se = self.modem.chanest(rx, torch.tensor(pos, dtype=torch.int64, device=dev),
-                                       torch.tensor(delay, dtype=torch.int32, device=dev), want_aux=want_aux)
+                                       torch.tensor(delay, dtype=torch.int32, device=dev), want_aux=want_aux,
+                                       hyp=None if hyp is None else torch.tensor(hyp, dtype=torch.int32, device=dev))
         idx = torch.tensor(rows, dtype=torch.int64, device=dev)
         self._d_H.index_copy_(0, idx, h)
         ht_h, se_h = ht.cpu().numpy(), se.cpu().numpy()
@@ -94,12 +95,13 @@ class RxBlockBase(gr.sync_block):
         with open(path, "wb") as f:
             pickle.dump(np.asarray(chan_est_tim, dtype=complex).reshape(1, -1), f, protocol=2)
 
-    def _demod_into(self, rx, rows, start, delay, hrow):
+    def _demod_into(self, rx, rows, start, delay, hrow, hyp=None):
         if not rows:
             return
         torch = self._torch
         dev = self.modem.device
         eq, _, _ = self.modem.demod(rx, torch.tensor(start, dtype=torch.int64, device=dev),
                                     torch.tensor(delay, dtype=torch.int32, device=dev),
-                                    torch.tensor(hrow, dtype=torch.int32, device=dev), self._d_H)
+                                    torch.tensor(hrow, dtype=torch.int32, device=dev), self._d_H,
+                                    hyp=None if hyp is None else torch.tensor(hyp, dtype=torch.int32, device=dev))
         self.est_data_freq[np.asarray(rows)] = eq.cpu().numpy()

@@ -141,3 +141,96 @@ class RxofdmBlockOracle:
         self.count += 1
         self.cor_obs = 0                                           # :265 (D8)
         return len(out)
+
+
+# numerology tables of the legacy block (GRR/LEGACY/gr-ofdm-rx/python/SynchEstAndFO.py:36-134):
+# case -> (num_ofdm_symb, fs, nfft, synch_dat, num_data_bins); cp_len = nfft/4, num_synch_bins = nfft-2,
+# SNR = 1e8 in every case.  Cases 2 and 9 are listed as shipped; case 2 asks for 180 data bins on a 64-point
+# grid, which no transmitter in the repository produces (the bins alias) -- kept for completeness.
+SYNCH_EST_AND_FO_CASES = {
+    0: (48, 960000, 64, [1, 1], 12),
+    1: (48, 960000, 64, [1, 1], 36),
+    2: (48, 960000, 64, [2, 1], 180),
+    3: (48, 960000, 64, [2, 1], 48),
+    4: (48, 960000, 64, [3, 1], 24),
+    5: (48, 960000, 64, [2, 1], 24),
+    6: (24, 1920000, 128, [3, 1], 24),
+    7: (24, 1920000, 128, [5, 1], 100),
+    8: (12, 3840000, 256, [5, 1], 36),
+    9: (12, 3840000, 256, [2, 1], 180),
+}
+
+
+class SynchEstAndFOOracle:
+    """work() of the legacy receiver with a frequency-offset hypothesis bank
+    (GRR/LEGACY/gr-ofdm-rx/python/SynchEstAndFO.py:31-227 ctor, :230-364 work).
+
+    Same skeleton as gr-RXOFDM (Zadoff-Chu root 37 keyed on the parity of num_synch_bins :172-181,
+    stride CP-1 :200, gate 0.4 :280, snr used as a linear regulariser :298,:324, every lock recorded,
+    first data symbol after each lock only :326-352) plus, per trial, one FFT + delay bank per row of
+    ``cfo`` (:247-272).  Behaviours reproduced as they are written:
+      * the channel estimate of an accepted lock is computed from ``synchdat`` as left behind by the
+        hypothesis loop, i.e. the LAST row of the bank, not the winning one (:262-266 vs :293-296);
+      * loop B de-rotates every data window with ``self.dmax_tmp_ind`` of the last trial evaluated (:274,:332);
+      * ``cp_len = nfft/4`` is a float on Python 3 (:40); made integral here (SURVEY D6 class of defect).
+    """
+
+    def __init__(self, case, fo_range, literal=False, zc_root=None):
+        num_ofdm_symb, fs, nfft, synch_dat, num_data_bins = SYNCH_EST_AND_FO_CASES[case]
+        self.prm = oo.ModemParams(nfft=nfft, cp_len=nfft // 4, num_synch_bins=nfft - 2, num_data_bins=num_data_bins,
+                                  m0=synch_dat[0], d=synch_dat[1], snr=100000000, compat="rxofdm", zc_root=zc_root)
+        self.num_ofdm_symb = num_ofdm_symb
+        self.fs = fs
+        self.fo_range = list(fo_range)
+        self.literal = literal
+        p = self.prm
+        self.zc = oo.zc_for(p)
+        self.bank = oo.delay_bank(p)
+        self.cfo = oo.cfo_bank(self.fo_range, fs, nfft)                      # :196
+        self.max_num_corr = 100
+        self.cor_obs = -1
+        self.dmax_tmp_ind = 0                                      # the reference leaves it undefined until the first trial
+        self.time_synch_ref = np.zeros((self.max_num_corr, 3))
+        self.est_chan_time = np.zeros((self.max_num_corr, nfft), dtype=complex)
+        self.est_synch_freq = np.zeros((self.max_num_corr, p.mm), dtype=complex)
+        self.est_chan_freq_P = np.zeros((self.max_num_corr, nfft), dtype=complex)
+        self.est_data_freq = np.zeros((self.max_num_corr, num_data_bins), dtype=complex)
+        self.count = 0
+        self.last_written = 0
+
+    def work(self, in0, out):
+        p = self.prm
+        N, CP, L = p.nfft, p.cp_len, p.sym_len
+        n_trials = int(np.around(len(in0) / p.stride))                       # :233
+        for P in range(n_trials):
+            if p.m0 * L + P * p.stride + N + CP < len(in0):                  # :236
+                start = P * p.stride + CP
+                fo_ind, d_i, d_v, res = oo.sync_trial_cfo(in0, start, p, self.cfo, self.zc, self.bank, self.literal)
+                self.dmax_tmp_ind = fo_ind                                   # :274
+                if d_v > 0.4 * p.mm:                                         # :280
+                    prev = self.time_synch_ref[max(self.cor_obs, 0)][0]
+                    if (start - prev > 2 * CP + N) or self.cor_obs == -1:    # :282-283
+                        self.cor_obs += 1
+                        r = self.cor_obs
+                        self.time_synch_ref[r] = (start, d_i, int(d_v))
+                        sd_last = res[-1][2]                                 # synchdat of the last hypothesis (:262-266)
+                        ce, ce1, dr = oo.chan_est(sd_last, d_i, p, self.zc, self.bank, self.literal)
+                        self.est_chan_freq_P[r] = ce1
+                        tim, esf = oo.chan_est_aux(ce, ce1, dr, p)
+                        self.est_chan_time[r] = tim
+                        self.est_synch_freq[r] = esf
+        for r in range(self.cor_obs + 1):                                    # :326-352
+            pos = self.time_synch_ref[r][0]
+            if pos + p.m0 * L + N - 1 <= len(in0):
+                ptr = int(pos + p.m0 * L)
+                self.est_data_freq[r] = oo.demod_symbol(in0, ptr, self.time_synch_ref[r][1], self.est_chan_freq_P[r], p,
+                                                        self.literal, rot=self.cfo[self.dmax_tmp_ind])
+        corr_size = int(self.num_ofdm_symb / p.frame_syms)                   # :356
+        data_out = np.reshape(self.est_data_freq[0:corr_size], (1, corr_size * p.num_data_bins))
+        self.last_written = 0
+        if self.count > 0:
+            out[0:data_out.shape[1]] = data_out[0]
+            self.last_written = data_out.shape[1]
+        self.count += 1
+        self.cor_obs = 0
+        return len(out)

@@ -330,22 +330,46 @@ def delay_bank(prm: ModemParams):
     return np.tile(e, (1, prm.m0))
 
 
-def sync_window(in0, start, prm: ModemParams):
+def cfo_bank(fo_range, fs, nfft):
+    """cfo[F x N] = exp(j*2pi*(1/fs)*fo*n): one window-local de-rotation phasor per frequency-offset
+    hypothesis.  GRR/LEGACY/gr-ofdm-rx/python/SynchEstAndFO.py:196."""
+    return np.exp(1j * 2 * np.pi * (1 / fs) * (np.outer(np.asarray(fo_range, dtype=float), list(range(nfft)))))
+
+
+def _window(in0, a, N, rot=None, nu=None):
+    """N samples from ``a`` (zero-padded past the end, like np.fft.fft(x, N)), times the CFO phasor.
+
+    ``rot`` is one row of cfo_bank(): the reference restarts the phasor at every window (SynchEstAndFO.py:254,
+    :332), so windows L samples apart keep a relative phase of 2*pi*nu*L.  EXTENSION (our definition):
+    with ``nu`` (the row's frequency in cycles per sample) the phasor is continued from the buffer origin,
+    exp(j*2pi*nu*(a+n)), which is what undoing a real carrier offset needs."""
+    w = np.zeros(N, dtype=complex)
+    seg = np.asarray(in0[a:a + N], dtype=complex)
+    w[:len(seg)] = seg
+    if rot is not None:
+        w = w * rot
+    if nu is not None:
+        w = w * np.exp(2j * np.pi * ((nu * a) % 1.0))
+    return w
+
+
+def sync_window(in0, start, prm: ModemParams, rot=None, nu=None):
     """Gather the M0 FFT windows that start at ``start`` and pick the synch bins.
 
-    SynchAndChanEst.py:145-154.  Returns the un-normalised M0*nsb vector.
+    SynchAndChanEst.py:145-154; with ``rot`` each window is first multiplied by one row of the CFO
+    bank (SynchEstAndFO.py:252-256).  Returns the un-normalised M0*nsb vector.
     """
     N, L = prm.nfft, prm.sym_len
     sb = bins_used(prm.num_synch_bins, N)
     out = np.zeros(prm.mm, dtype=complex)
     for ll in range(prm.m0):
         a = L * ll + start
-        spec = np.fft.fft(np.asarray(in0[a:a + N], dtype=complex), N)
+        spec = np.fft.fft(_window(in0, a, N, rot, nu), N)
         out[ll * prm.num_synch_bins:(ll + 1) * prm.num_synch_bins] = spec[sb]
     return out
 
 
-def sync_trial(in0, start, prm: ModemParams, zc=None, bank=None, literal=False):
+def sync_trial(in0, start, prm: ModemParams, zc=None, bank=None, literal=False, rot=None, nu=None):
     """One trial of the sliding search at FFT-window start sample ``start``.
 
     Returns (dmax_ind, dmax_val, synchdat) where synchdat is the unit-power synch-bin vector.
@@ -353,7 +377,7 @@ def sync_trial(in0, start, prm: ModemParams, zc=None, bank=None, literal=False):
     """
     zc = zc_for(prm) if zc is None else zc
     bank = delay_bank(prm) if bank is None else bank
-    sd0 = sync_window(in0, start, prm)
+    sd0 = sync_window(in0, start, prm, rot, nu)
     if literal:
         p_est = np.sqrt(len(sd0) / sum(np.multiply(sd0, np.conj(sd0))))
         sd = p_est * sd0
@@ -364,6 +388,19 @@ def sync_trial(in0, start, prm: ModemParams, zc=None, bank=None, literal=False):
         del_mat = bank @ (sd * np.conj(zc))
     mag = np.abs(del_mat)
     return int(np.argmax(mag)), float(np.max(mag)), sd
+
+
+def sync_trial_cfo(in0, start, prm: ModemParams, cfo, zc=None, bank=None, literal=False, nus=None):
+    """The trial repeated for every row of the CFO bank; the hypothesis with the largest peak wins
+    (first one on ties, np.argmax).  SynchEstAndFO.py:247-277.
+
+    Returns (fo_ind, dmax_ind, dmax_val, per-hypothesis list of (dmax_ind, dmax_val, synchdat)).
+    """
+    res = [sync_trial(in0, start, prm, zc, bank, literal, rot=cfo[h], nu=None if nus is None else nus[h])
+           for h in range(len(cfo))]
+    vals = np.array([r[1] for r in res])
+    fo_ind = int(np.argmax(vals))
+    return fo_ind, res[fo_ind][0], float(np.max(vals)), res
 
 
 # --------------------------------------------------------------------------------------------
@@ -402,7 +439,7 @@ def chan_est_aux(ce, ce1, data_recov, prm: ModemParams):
 # --------------------------------------------------------------------------------------------
 # a14-a16  one data symbol
 # --------------------------------------------------------------------------------------------
-def demod_symbol(in0, ptr, delay, h_full, prm: ModemParams, literal=False):
+def demod_symbol(in0, ptr, delay, h_full, prm: ModemParams, literal=False, rot=None, nu=None):
     """FFT (CP skipped by the start pointer) -> data bins -> unit power -> de-rotate -> one-tap MMSE.
 
     SynchAndChanEst.py:226-248 / synch_and_chan_est.py:230-250.  A window that runs past the end
@@ -410,7 +447,7 @@ def demod_symbol(in0, ptr, delay, h_full, prm: ModemParams, literal=False):
     """
     N = prm.nfft
     db = bins_used(prm.num_data_bins, N)
-    spec = np.fft.fft(np.asarray(in0[ptr:ptr + N], dtype=complex), N)
+    spec = np.fft.fft(_window(in0, ptr, N, rot, nu), N)    # rot: SynchEstAndFO.py:331-333
     fd = spec[db]
     p0 = np.sqrt(len(fd) / np.dot(fd, np.conj(fd)))
     fd = fd * p0
@@ -441,14 +478,17 @@ def demod_symbol(in0, ptr, delay, h_full, prm: ModemParams, literal=False):
 # --------------------------------------------------------------------------------------------
 # framed receiver: one trial per frame at the nominal position (throughput mode)
 # --------------------------------------------------------------------------------------------
-def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, literal=False):
+def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, literal=False, cfo=None, nus=None):
     """Loop-A body once per frame + loop-B body for all D data symbols of that frame.
 
     Frame f's synch FFT window opens at  first + f*frame_stride + CP - sync_advance ; data symbol n
     opens at that position + M0*L + n*L.  This is the reference's per-lock arithmetic
     (SynchAndChanEst.py:143-219 then :221-248) applied with one candidate per frame, which is how
     a receiver with known framing runs it.  Returns dict(delay, peak, locked, h[N], eq[D,ndb]) per
-    frame stacked on axis 0.
+    frame stacked on axis 0.  With a CFO bank (``cfo``, rows from cfo_bank()) every frame picks its own
+    hypothesis on the preamble (SynchEstAndFO.py:247-277) and de-rotates its data windows with it
+    (:331-333); ``hyp`` is added to the result.  ``nus`` (cycles per sample of each row) switches to the
+    phase-continuous extension described at _window().
     """
     fs = prm.frame_len if frame_stride is None else frame_stride
     zc, bank = zc_for(prm), delay_bank(prm)
@@ -458,15 +498,26 @@ def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, litera
     locked = np.zeros(n_frames, dtype=np.uint8)
     h = np.zeros((n_frames, prm.nfft), dtype=complex)
     eq = np.zeros((n_frames, prm.d, prm.n_payload_bins), dtype=complex)
+    hyp = np.zeros(n_frames, dtype=np.int32)
     for f in range(n_frames):
         pos = first + f * fs + prm.cp_len - prm.sync_advance
-        d_i, d_v, sd = sync_trial(rx, pos, prm, zc, bank, literal)
+        rot = nu = None
+        if cfo is None:
+            d_i, d_v, sd = sync_trial(rx, pos, prm, zc, bank, literal)
+        else:
+            hyp[f], d_i, d_v, res = sync_trial_cfo(rx, pos, prm, cfo, zc, bank, literal, nus)
+            sd = res[hyp[f]][2]
+            rot = cfo[hyp[f]]
+            nu = None if nus is None else nus[hyp[f]]
         delay[f], peak[f] = d_i, d_v
         locked[f] = 1 if d_v > prm.gate * prm.mm else 0
         _, h[f], _ = chan_est(sd, d_i, prm, zc, bank, literal)
         for n in range(prm.d):
-            eq[f, n] = demod_symbol(rx, pos + prm.m0 * L + n * L, d_i, h[f], prm, literal)
-    return dict(delay=delay, peak=peak, locked=locked, h=h, eq=eq)
+            eq[f, n] = demod_symbol(rx, pos + prm.m0 * L + n * L, d_i, h[f], prm, literal, rot=rot, nu=nu)
+    out = dict(delay=delay, peak=peak, locked=locked, h=h, eq=eq)
+    if cfo is not None:
+        out["hyp"] = hyp
+    return out
 
 
 # --------------------------------------------------------------------------------------------

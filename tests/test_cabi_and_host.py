@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export: " + n
     assert set(_lib.SIGNATURES) == set(names)
     lib.ofdm_abi_version.restype = ctypes.c_int
-    assert lib.ofdm_abi_version() == 1
+    assert lib.ofdm_abi_version() == 2
 
 
 def test_params_struct_matches_header():
