@@ -11,11 +11,13 @@ Workloads (BASELINE.json configs):
   rx_n64_16qam_1m  (default, configs[1]) N=64, CP=16, 62 ZC bins, 60 data bins, frames of 1 synch + 3
                    data symbols, 16-QAM, 333 334 frames = 1 000 002 data symbols, reference 5-tap
                    channel + AWGN, per-frame ZC-preamble ("pilot") equalisation.
-  rx_lte20_64qam   (configs[2]/[3]) N=2048, CP=144, 2046 ZC bins, 1200 data bins, 1+13 symbols, 64-QAM,
-                   4096 frames.
-Multi-GPU (torchrun, one rank per GPU): every rank receives its own independent batch of the same
-size (weak scaling, no data-path collective); BER/EVM counters are all-reduced over NCCL once per
-measurement window.
+  rx_lte20_64qam   (configs[2]) N=2048, CP=144, 2046 ZC bins, 1200 data bins, 1+13 symbols, 64-QAM,
+                   4096 frames, an independent random 5-tap multipath channel per frame + AWGN.
+  rx_lte20_streams (configs[3]) the same numerology as 4096 independent streams x 10 frames, the STREAMS
+                   dealt round-robin over the ranks (strong scaling: the total is fixed).
+Multi-GPU (torchrun, one rank per GPU): every rank receives its own independent batch (weak scaling
+unless the workload says otherwise, no data-path collective); BER/EVM counters are all-reduced over
+NCCL once per measurement window.
 """
 import argparse
 import json
@@ -34,8 +36,20 @@ WORKLOADS = {
     "rx_n64_16qam_1m": dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4,
                             n_frames=333334, noise_sigma=0.02),
     "rx_lte20_64qam": dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6,
-                           n_frames=4096, noise_sigma=0.01),
+                           n_frames=4096, noise_sigma=0.0224, multipath=True),          # Es/N0 = 30 dB
+    "rx_lte20_streams": dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6,
+                             n_streams=4096, frames_per_stream=10, noise_sigma=0.0224, multipath=True),
 }
+# power delay profile of the per-frame random channel, shaped after the reference taps (MultiAntennaSystem.py:64)
+MULTIPATH_PDP = np.array([0.16, 0.79, 0.04, 0.01, 0.002])
+
+
+def frames_for_rank(w, rank, world):
+    """(frames this rank processes, frames of the whole job, scaling)"""
+    if "n_streams" in w:
+        mine = len(range(rank, w["n_streams"], world)) * w["frames_per_stream"]      # shard.my_streams
+        return mine, w["n_streams"] * w["frames_per_stream"], "strong"
+    return w["n_frames"], w["n_frames"] * world, "weak"
 REF_TAPS = np.array([0.3977, 0.7954 - 0.3977j, -0.1988, 0.0994, -0.0398])     # MultiAntennaSystem.py:64
 
 
@@ -60,10 +74,9 @@ def profiled_traffic(workload):
     return None
 
 
-def algorithmic_bytes(w):
-    """Bytes one launch must move: every input sample once, every output once."""
+def algorithmic_bytes(w, fr):
+    """Bytes one launch over `fr` frames must move: every input sample once, every output once."""
     L = w["nfft"] + w["cp_len"]
-    fr = w["n_frames"]
     nsym = fr * w["d"]
     read = fr * (w["m0"] + w["d"]) * L * 8
     hs = (w["num_data_bins"] * w["bps"] + 7) // 8
@@ -208,7 +221,7 @@ def run_ours(args, rank, world, local_rank):
                       num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100.0, gate=0.5,
                       noise_var=2 * w["noise_sigma"] ** 2)
     m = Modem(cfg)
-    nf = w["n_frames"]
+    nf, nf_total, scaling = frames_for_rank(w, rank, world)
     nsym = nf * cfg.d
 
     # synthetic batch, generated on the device (not timed): payload -> CUDA TX -> 5-tap channel + AWGN
@@ -216,7 +229,13 @@ def run_ours(args, rank, world, local_rank):
     g.manual_seed(2024 + rank)
     bits = torch.randint(0, 256, (nsym * cfg.hard_stride,), dtype=torch.uint8, device=dev, generator=g)
     tx = m.tx_modulate(bits, nf)
-    taps = torch.tensor(REF_TAPS / np.linalg.norm(REF_TAPS), dtype=torch.complex64, device=dev)
+    if w.get("multipath"):
+        gt = torch.Generator(device=dev)
+        gt.manual_seed(7 + rank)
+        taps = torch.randn((nf, len(MULTIPATH_PDP)), dtype=torch.complex64, device=dev, generator=gt)
+        taps = (taps * torch.tensor(np.sqrt(MULTIPATH_PDP), dtype=torch.float32, device=dev)).contiguous()
+    else:
+        taps = torch.tensor(REF_TAPS / np.linalg.norm(REF_TAPS), dtype=torch.complex64, device=dev)
     rx = m.channel_awgn(tx, nf, taps, w["noise_sigma"], 2024 + rank)
     out = m.rx_frames(rx, nf)
     torch.cuda.synchronize()
@@ -248,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * nsym / (ms_per_step * 1e-3)
+    value = nf_total * cfg.d / (ms_per_step * 1e-3)
 
     # ---- TX throughput, same batch (reported beside it) -------------------------------------------
     for _ in range(3):
@@ -303,7 +322,7 @@ def run_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    rd, wr = algorithmic_bytes(w)
+    rd, wr = algorithmic_bytes(w, nf)
     peak, peak_src = measured_peak_gbs()
     k_ms = float(np.mean(per_launch_ms))
     achieved = (rd + wr) / (k_ms * 1e-3) / 1e9
@@ -312,10 +331,12 @@ def run_ours(args, rank, world, local_rank):
     res = {
         "metric": "rx_ofdm_data_symbols_per_s", "value": value, "unit": "symbols/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wname, "nfft": cfg.nfft, "cp_len": cfg.cp_len, "num_synch_bins": cfg.num_synch_bins,
                    "num_data_bins": cfg.num_data_bins, "synch_dat": [cfg.m0, cfg.d], "bps": cfg.bps,
-                   "frames_per_gpu": nf, "data_symbols_per_gpu": nsym, "outputs": "eq c64 + llr f32 + packed hard bits",
+                   "frames_per_gpu": nf, "data_symbols_per_gpu": nsym, "frames_total": nf_total,
+                   "channel": "independent random 5-tap multipath per frame + AWGN" if w.get("multipath")
+                   else "reference 5-tap channel + AWGN", "outputs": "eq c64 + llr f32 + packed hard bits",
                    "cache": "inputs+outputs per step = %.2f GB per GPU, far larger than the 126 MB L2" % ((rd + wr) / 1e9),
                    "parallelism": "frames sharded by rank, no data-path collective"},
         "msamples_per_s": value * L * cfg.frame_syms / cfg.d / 1e6,
@@ -323,14 +344,14 @@ def run_ours(args, rank, world, local_rank):
                      "traffic": profiled_traffic(wname), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": rd + wr, "kernel": "rx_frames_kernel",
                      "kernel_ms": k_ms, "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": world * nsym / e2e_s, "unit": "symbols/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": nf_total * cfg.d / e2e_s, "unit": "symbols/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
                 "api": "Modem.rx_frames_host -> ofdm_rx_frames_host (pinned host buffers, chunked double-buffered "
                        "copies inside the call)", "timer": "host perf_counter around synchronous calls",
                 "matches_device_path": same},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "tx": {"value": world * nsym / (tx_ms * 1e-3), "unit": "symbols/s", "ms_per_step": tx_ms,
+        "tx": {"value": nf_total * cfg.d / (tx_ms * 1e-3), "unit": "symbols/s", "ms_per_step": tx_ms,
                "achieved_GBs": tx_bytes / (tx_ms * 1e-3) / 1e9, "frac": tx_bytes / (tx_ms * 1e-3) / 1e9 / peak},
         "quality": {"ber": cnt[0] / max(cnt[1], 1.0), "bits": cnt[1], "evm_rms": float(np.sqrt(cnt[2] / max(cnt[3], 1e-30))),
                     "frames_locked": cnt[4], "frames": cnt[5], "reduced_over": "NCCL all_reduce(sum)" if world > 1 else "1 GPU"},

@@ -381,6 +381,8 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     // rounded so that neighbouring groups start 16 banks apart.  Only for transforms up to
     // OFDM_LLR_STAGE_MAX_N points (environment override for A/B runs; 0 disables): from N = 128 on the extra
     // shared-memory traffic costs more than the partial-sector stores it removes (B200, 64-QAM: N=64 0.53 -> 0.39 ms, N=128 0.37 -> 0.42 ms, N=2048 0.76 -> 0.81 ms).
+    // (Staging the equalised-symbol rows and the LLR rows of the other modulations as well was tried: 7-12 % slower
+    // at every size, and even the dormant run-time switch cost the fast path 2-7 %, so it is not in the code.)
     {
         const char *env = getenv("OFDM_LLR_STAGE_MAX_N");
         const int max_n = env ? atoi(env) : 64;
