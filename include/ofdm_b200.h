@@ -165,6 +165,13 @@ int ofdm_rx_frames_cfo(ofdm_plan *plan, const float *d_time, int64_t n_samples, 
 int ofdm_bit_recovery(ofdm_plan *plan, const float *d_in, int64_t n, float *d_llr0, float *d_llr1,
                       uint8_t *d_hard, double *d_ws, void *stream);
 
+/* DSSS despreading of equalised rows (legacy receiver): every group of sf consecutive data bins of a row is
+ * multiplied by conj(code) and averaged; bins past the last whole group are ignored.
+ * d_eq: n_rows x row_len complex64, d_code: sf complex64, d_out: n_rows x (row_len / sf) complex64.
+ * Replaces GRR/LEGACY/gr-ofdm-rx/python/SynchEstFOAndDSSS.py:392-397 (code: :253-261). */
+int ofdm_dsss_despread(ofdm_plan *plan, const float *d_eq, int64_t n_rows, int32_t row_len, const float *d_code,
+                       int32_t sf, float *d_out, void *stream);
+
 /* BER/EVM counters, ACCUMULATED into d_cnt[8] (double): [0] bit errors, [1] bits compared,
  * [2] sum|eq-ref|^2, [3] sum|ref|^2, [4] frames locked, [5] frames; [6],[7] spare.
  * ref symbols are rebuilt from d_bits_tx.  d_locked nullable.  This vector is the only thing

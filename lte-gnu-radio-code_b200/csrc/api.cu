@@ -154,6 +154,22 @@ __global__ void counters_kernel(const DevParams P, const uint8_t *__restrict__ r
     }
 }
 
+// DSSS despreading of equalised rows: out[r][g] = mean_i eq[r][g*sf + i] * conj(code[i]).
+// SynchEstFOAndDSSS.py:392-397.  One thread per output; a warp's reads sweep one contiguous stretch of the row.
+__global__ void dsss_despread_kernel(const float2 *__restrict__ eq, long long n_rows, int row_len, int n_groups,
+                                     const float2 *__restrict__ code, int sf, float2 *__restrict__ out) {
+    const long long total = n_rows * n_groups;
+    const float inv = 1.f / (float)sf;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n_groups;
+        const int g = (int)(i - r * n_groups);
+        const float2 *src = eq + r * row_len + (long long)g * sf;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int c = 0; c < sf; ++c) acc = cadd(acc, cmulc(__ldg(src + c), __ldg(code + c)));
+        out[i] = cscale(acc, inv);
+    }
+}
+
 // Philox4x32-10 counter-based generator (Salmon et al., SC'11), one call = 4 x 32 random bits.
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -538,6 +554,22 @@ int ofdm_bit_recovery(ofdm_plan *pl, const float *d_in, int64_t n, float *d_llr0
     bitrec_llr_kernel<<<(int)blocks, 256, 0, st>>>((const float2 *)d_in, n, d_ws, d_llr0, d_llr1, d_hard);
     count_launch();
     CU(cudaGetLastError(), "ofdm_bit_recovery");
+    return OFDM_OK;
+}
+
+int ofdm_dsss_despread(ofdm_plan *pl, const float *d_eq, int64_t n_rows, int32_t row_len, const float *d_code, int32_t sf,
+                       float *d_out, void *stream) {
+    if (pl && n_rows == 0) return OFDM_OK;
+    if (!pl || !d_eq || !d_code || !d_out || n_rows < 0 || sf < 1 || row_len < sf)
+        return fail(OFDM_EINVAL, "ofdm_dsss_despread: bad argument%s");
+    const int n_groups = row_len / sf;
+    long long blocks = (n_rows * n_groups + 255) / 256;
+    const long long cap = (long long)pl->sms * 16;
+    if (blocks > cap) blocks = cap;
+    dsss_despread_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float2 *)d_eq, n_rows, row_len, n_groups,
+                                                                        (const float2 *)d_code, sf, (float2 *)d_out);
+    count_launch();
+    CU(cudaGetLastError(), "ofdm_dsss_despread");
     return OFDM_OK;
 }
 

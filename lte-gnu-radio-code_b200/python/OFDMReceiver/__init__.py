@@ -2,8 +2,10 @@
 equalised symbols into soft/hard bits (GRC template OFDMReceiver.BitRecovery(modulation,
 directory_name, diagnostics), grc/OFDMReceiver_BitRecovery.block.yml:24) and the receiver with a
 frequency-offset hypothesis bank (OFDMReceiver.SynchEstAndFO(case, fo_range, directory_name,
-file_name_cest, diagnostics), grc/OFDMReceiver_SynchEstAndFO.block.yml:33-35)."""
+file_name_cest, diagnostics), grc/OFDMReceiver_SynchEstAndFO.block.yml:33-35) and its variant that also
+despreads DSSS-coded data bins (OFDMReceiver.SynchEstFOAndDSSS, same arguments)."""
 from .BitRecovery import BitRecovery
 from .SynchEstAndFO import SynchEstAndFO
+from .SynchEstFOAndDSSS import SynchEstFOAndDSSS
 
-__all__ = ["BitRecovery", "SynchEstAndFO"]
+__all__ = ["BitRecovery", "SynchEstAndFO", "SynchEstFOAndDSSS"]

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ofdm_rx_chanest_cfo": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "ofdm_rx_demod_cfo": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "ofdm_rx_frames_cfo": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ofdm_dsss_despread": (C.c_int, [_P, _P, _I64, C.c_int32, _P, C.c_int32, _P, _P]),
     "ofdm_bit_recovery": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P]),
     "ofdm_counters": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _P]),
     "ofdm_channel_awgn": (C.c_int, [_P, _P, _P, _I64, _P, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P]),

@@ -253,6 +253,19 @@ class Modem:
                                                 _stream()))
         return eq, llr, hard
 
+    # ---- DSSS despreading (legacy receiver) ------------------------------------------------------
+    def dsss_despread(self, eq, code):
+        """eq: complex64 [n_rows, row_len]; code: complex64 [sf] -> [n_rows, row_len // sf]
+        (GRR/LEGACY/gr-ofdm-rx/python/SynchEstFOAndDSSS.py:392-397)."""
+        torch = _torch()
+        eq = self._c64(eq)
+        code = self._c64(code)
+        n_rows, row_len = eq.shape
+        sf = code.numel()
+        out = self.empty((n_rows, row_len // sf), torch.complex64)
+        _lib.check(_lib.lib().ofdm_dsss_despread(self._h, _ptr(eq), n_rows, row_len, _ptr(code), sf, _ptr(out), _stream()))
+        return out
+
     # ---- legacy demapper, counters, test-bench channel ----------------------------------------
     def bit_recovery(self, x):
         torch = _torch()

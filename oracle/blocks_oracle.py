@@ -234,3 +234,75 @@ class SynchEstAndFOOracle:
         self.count += 1
         self.cor_obs = 0
         return len(out)
+
+
+# case -> (num_ofdm_symb, fs, nfft, synch_dat, num_data_bins, DSSS)
+# GRR/LEGACY/gr-ofdm-rx/python/SynchEstFOAndDSSS.py:37-157
+SYNCH_EST_FO_AND_DSSS_CASES = {
+    0: (48, 960000, 64, [2, 1], 12, 1),
+    1: (48, 960000, 64, [3, 1], 36, 6),
+    2: (45, 960000, 64, [4, 1], 48, 6),
+    3: (45, 960000, 64, [4, 1], 48, 12),
+    4: (24, 1920000, 128, [3, 1], 32, 8),
+    5: (20, 1920000, 128, [4, 1], 84, 12),
+    6: (20, 1920000, 128, [4, 1], 96, 16),
+    7: (24, 1920000, 128, [5, 1], 120, 24),
+    8: (12, 3840000, 256, [3, 1], 168, 12),
+    9: (10, 3840000, 256, [4, 1], 192, 16),
+    10: (10, 3840000, 256, [4, 1], 240, 24),
+}
+
+
+class SynchEstFOAndDSSSOracle(SynchEstAndFOOracle):
+    """work() of GRR/LEGACY/gr-ofdm-rx/python/SynchEstFOAndDSSS.py (:268-410): SynchEstAndFO plus despreading of
+    the equalised data bins with a length-DSSS Zadoff-Chu code (:253-261, :392-397).  As written there:
+      * the despreading sits inside the per-lock loop but OUTSIDE the window guard (:366 vs :392), so a lock whose
+        data window does not fit first receives a copy of the most recent demodulated row (:392), then is despread;
+      * the despread rows are written on every call, the first included (:404-406, the count guard is commented out).
+    """
+
+    def __init__(self, case, fo_range, literal=False, zc_root=None):
+        num_ofdm_symb, fs, nfft, synch_dat, num_data_bins, dsss = SYNCH_EST_FO_AND_DSSS_CASES[case]
+        SYNCH_EST_AND_FO_CASES[("dsss", case)] = (num_ofdm_symb, fs, nfft, synch_dat, num_data_bins)
+        super().__init__(("dsss", case), fo_range, literal, zc_root)
+        self.DSSS = dsss
+        self.SC = oo.dsss_code(dsss, self.prm.zc_root)             # :253-261 (same root self.p as the preamble)
+        self.est_data_freq_d = np.zeros((self.max_num_corr, num_data_bins // dsss), dtype=complex)
+
+    def work(self, in0, out):
+        p = self.prm
+        N, CP, L = p.nfft, p.cp_len, p.sym_len
+        n_trials = int(np.around(len(in0) / p.stride))
+        for P in range(n_trials):                                            # loop A: identical to SynchEstAndFO
+            if p.m0 * L + P * p.stride + N + CP < len(in0):
+                start = P * p.stride + CP
+                fo_ind, d_i, d_v, res = oo.sync_trial_cfo(in0, start, p, self.cfo, self.zc, self.bank, self.literal)
+                self.dmax_tmp_ind = fo_ind
+                if d_v > 0.4 * p.mm:
+                    prev = self.time_synch_ref[max(self.cor_obs, 0)][0]
+                    if (start - prev > 2 * CP + N) or self.cor_obs == -1:
+                        self.cor_obs += 1
+                        r = self.cor_obs
+                        self.time_synch_ref[r] = (start, d_i, int(d_v))
+                        ce, ce1, dr = oo.chan_est(res[-1][2], d_i, p, self.zc, self.bank, self.literal)
+                        self.est_chan_freq_P[r] = ce1
+                        tim, esf = oo.chan_est_aux(ce, ce1, dr, p)
+                        self.est_chan_time[r] = tim
+                        self.est_synch_freq[r] = esf
+        last = None
+        for r in range(self.cor_obs + 1):                                    # :360-397
+            pos = self.time_synch_ref[r][0]
+            if pos + p.m0 * L + N - 1 <= len(in0):
+                ptr = int(pos + p.m0 * L)
+                last = oo.demod_symbol(in0, ptr, self.time_synch_ref[r][1], self.est_chan_freq_P[r], p, self.literal,
+                                       rot=self.cfo[self.dmax_tmp_ind])
+            if last is not None:                                             # :392 (NameError in the reference otherwise)
+                self.est_data_freq[r] = last
+            self.est_data_freq_d[r] = oo.dsss_despread(self.est_data_freq[r], self.SC)
+        corr_size = int(self.num_ofdm_symb / p.frame_syms)
+        data_out = np.reshape(self.est_data_freq_d[0:corr_size], (1, corr_size * self.est_data_freq_d.shape[1]))
+        out[0:data_out.shape[1]] = data_out[0]                               # :406, no count guard
+        self.last_written = data_out.shape[1]
+        self.count += 1
+        self.cor_obs = 0
+        return len(out)

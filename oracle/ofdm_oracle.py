@@ -521,6 +521,33 @@ def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, litera
 
 
 # --------------------------------------------------------------------------------------------
+# DSSS despreading of the equalised data bins (legacy receiver)
+# --------------------------------------------------------------------------------------------
+def dsss_code(sf, root=37):
+    """Spreading code SC: a Zadoff-Chu sequence of length ``sf`` (k^2 for even, k(k+1) for odd lengths).
+    GRR/LEGACY/gr-ofdm-rx/python/SynchEstFOAndDSSS.py:253-261 (root = self.p = 37, :195)."""
+    k = np.arange(sf)
+    xx = k * k if sf % 2 == 0 else k * (k + 1)
+    return np.exp((-1j * (TWO_PI / sf) * root / 2.0) * xx)
+
+
+def dsss_despread(rows, code):
+    """rows[..., ndb] -> [..., ndb // sf]: each group of sf consecutive data bins times conj(code), averaged.
+    SynchEstFOAndDSSS.py:392-397 (bins past the last whole group are ignored, :358)."""
+    rows = np.asarray(rows)
+    sf = len(code)
+    ng = rows.shape[-1] // sf
+    g = rows[..., :ng * sf].reshape(rows.shape[:-1] + (ng, sf))
+    return np.mean(g * np.conj(code), axis=-1)
+
+
+def dsss_spread(symbols, code):
+    """Transmit-side counterpart (our definition; the spreading transmitter is not in the reference tree): every
+    symbol occupies sf consecutive data bins, multiplied by the code chips."""
+    return (np.asarray(symbols)[..., None] * code).reshape(np.asarray(symbols).shape[:-1] + (-1,))
+
+
+# --------------------------------------------------------------------------------------------
 # a18  demapping
 # --------------------------------------------------------------------------------------------
 def bit_recovery(data_in):

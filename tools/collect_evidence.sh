@@ -1,0 +1,18 @@
+#!/bin/bash
+# Run on the GPU box (gpurun): bench lines, launch list and full ncu captures for profiles/.
+# Every ncu command is preceded by the same command without ncu exiting 0.
+set -u
+cd "$(dirname "$0")/.."
+O=gpurun_out/ev
+mkdir -p $O
+python bench.py --steps 50 --warmup 5 > $O/bench_n64.json 2> $O/bench_n64.err || { echo "bench failed"; tail -5 $O/bench_n64.err; exit 1; }
+python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err || echo "reference arm failed"
+python bench.py --steps 3 --warmup 3 --no-cpu > $O/bench_short.json 2> $O/bench_short.err && \
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_n64.csv \
+      python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu_launches.log 2>&1
+python tools/prof_cases.py n64 lte > $O/prof_plain.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:"rx_frames_kernel|tx_kernel" -s 2 -c 12 -o $O/prof_final -f \
+      python tools/prof_cases.py n64 lte > $O/prof_ncu.log 2>&1
+python tools/sweep_nfft.py > $O/sweep_nfft.jsonl 2> $O/sweep_nfft.err
+python bench.py --workload rx_lte20_64qam --steps 20 --warmup 3 --no-cpu > $O/bench_lte.json 2> $O/bench_lte.err
+ls -la $O
