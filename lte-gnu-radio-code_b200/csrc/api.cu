@@ -403,6 +403,22 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
         const char *env = getenv("OFDM_LLR_STAGE_MAX_N");
         const int max_n = env ? atoi(env) : 64;
         D.ls_stride = (p->bps == 6 && pk == 0 && N <= max_n) ? (((ndb * 6 + 31) & ~31) + 16) : 0;
+        D.es_stride = 0;
+        D.bulk_rows = 0;
+        // Bulk-store variant of the framed receiver (kernels.cuh, data_epilogue_bulk): rows of eq and LLR leave shared
+        // memory as cp.async.bulk copies.  Used for 64-QAM (whose per-lane LLR stores write every sector three times)
+        // from OFDM_BULK_MIN_N points on, when the rows fit next to the transform without costing a resident CTA
+        // (checked at launch).  B200, LTE 20 MHz numerology: 0.760 -> 0.708 ms.  At N <= 512 the per-row copies are too
+        // small to pay for the extra barrier (N=64: 0.45 -> 0.49 ms), and 16-QAM / QPSK rows are already stored with
+        // full sectors (N=2048, 1920 bins, 16-QAM: 0.353 -> 0.367 ms), so only the 64-QAM kernels have this variant.
+        // Environment override for A/B runs: OFDM_BULK_MIN_N (a value above 4096 disables it).
+        const char *eb = getenv("OFDM_BULK_MIN_N");
+        const int bulk_min = eb ? atoi(eb) : 1024;
+        if (pk == 0 && N >= bulk_min && p->bps == 6 && ((ndb * p->bps) & 3) == 0 && (ndb & 1) == 0) {
+            D.bulk_rows = 1;
+            D.ls_stride = ((ndb * p->bps + 31) & ~31) + 16;
+            D.es_stride = ((ndb + 15) & ~15) + 8;
+        }
     }
     D.dup_bin = dup_bin;
     D.equalizer = p->equalizer;

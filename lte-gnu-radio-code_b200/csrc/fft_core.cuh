@@ -132,13 +132,17 @@ template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value>;
 #ifndef OFDM_SB_MIN_LOG2N
 #define OFDM_SB_MIN_LOG2N 13
 #endif
+// ... and up to this size as well (0 = none).  For groups inside one warp the second barrier is a __syncwarp.
+#ifndef OFDM_SB_SMALL_MAX_LOG2N
+#define OFDM_SB_SMALL_MAX_LOG2N 0
+#endif
 template <int LOG2N> struct PptRxF {
     static constexpr int value = LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RXF_1024 : (LOG2N == 11 ? OFDM_PPT_RXF_2048 : OFDM_PPT_RXF_4096));
 };
 template <int LOG2N> using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N)>;
 template <int LOG2N> struct RxFOpts {
     static constexpr bool GSM = LOG2N >= OFDM_GSM_MIN_LOG2N;
-    static constexpr bool SB = LOG2N >= OFDM_SB_MIN_LOG2N;
+    static constexpr bool SB = LOG2N >= OFDM_SB_MIN_LOG2N || LOG2N <= OFDM_SB_SMALL_MAX_LOG2N;
 };
 template <int LOG2N> using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_TX_MIN_LOG2N)>;
 

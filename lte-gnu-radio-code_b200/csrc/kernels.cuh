@@ -32,7 +32,9 @@ struct DevParams {
     const float2 *zc_tx;      // [M0][N]  ZC value the transmitter puts in bin k of synch symbol m (0 if unused)
     // comb pilots in data symbols (extension): positions pil_off + i*pil_k of the used-bin list
     int pil_k, pil_off, n_pil, ndd;   // ndd = payload bins per data symbol = ndb - n_pil
-    int ls_stride;                    // floats per group of the 64-QAM LLR row staging area (0: none)
+    int ls_stride;                    // floats per group of the LLR row staging area (0: none)
+    int es_stride;                    // float2 per group of the equalised-symbol row staging area (bulk-store variant)
+    int bulk_rows;                    // 1: the plan asks for the bulk-store variant of the framed receiver
     // frequency-offset hypothesis bank (SynchEstAndFO.py:196): cfo[h][n] = exp(j*2pi*nu_h*n), n = 0..N-1
     int n_cfo;
     const float2 *cfo;
@@ -119,6 +121,21 @@ template <int T, int PPT> __device__ __forceinline__ int bin_out(const BinMap &b
 template <bool CS = true, class V> __device__ __forceinline__ void st_out(V *p, V v) {
     if (CS) __stcs(p, v); else *p = v;
 }
+
+// Bulk (TMA) row stores: a finished output row is assembled in shared memory and handed to the async proxy as
+// ONE shared->global copy (cp.async.bulk), so the LSU sees 16-byte shared-memory stores instead of global stores
+// and no register stays pinned behind a store queue.  Sizes and both addresses must be multiples of 16 bytes.
+__device__ __forceinline__ void bulk_store_row(void *gdst, const void *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all earlier bulk copies of this thread have finished READING shared memory (the rows may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed altogether (their global writes are done)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make this thread's shared-memory writes visible to the async proxy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float2 ld_stream(const float2 *p) {      // read-once data: do not allocate in L1
     float2 r;
@@ -619,6 +636,63 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
         pack_bits<BPS, T, GROUPS>(hb, reinterpret_cast<unsigned *>(hb + C::N + 16), hard_out + row * P.hard_stride, P.hard_stride, j, gid);
 }
 
+// Bulk-store variant of data_epilogue: equalised symbols and LLRs go to the group's shared-memory rows (es, ls)
+// and leave as two cp.async.bulk copies issued by lane 0 of the group.  The row buffers are reused every symbol:
+// lane 0 first waits until the previous copies have read them, and the power reduction that follows is the
+// group-wide synchronisation that keeps every other lane behind that wait.
+template <class C, int BPS, int GROUPS, bool GSM>
+__device__ __forceinline__ void data_epilogue_bulk(const DevParams &P, const DataCtx<C, BPS> &D, const float2 (&v)[C::PPT],
+                                                   const Gains<C, GSM> &G, long long row, float *redf, uint8_t *hb,
+                                                   float *ls, float2 *es, int j, int gid, float2 *__restrict__ eq_out,
+                                                   float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
+    constexpr int T = C::T, PPT = C::PPT;
+    const unsigned mask = D.map.mask;
+    if (j == 0) bulk_wait_read();
+    float pw = 0.f;
+#pragma unroll
+    for (int m = 0; m < PPT; ++m)
+        if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
+    pw = group_sum<T, GROUPS>(pw, redf, j, gid);
+    const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
+    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
+    float2 *eqp = es + D.map.base_p, *eqn = es + (D.map.base_n - (PPT / 2) * T);
+    float *lp = ls + D.map.base_p * BPS, *ln = ls + (D.map.base_n - (PPT / 2) * T) * BPS;
+    uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - (PPT / 2) * T);
+#pragma unroll
+    for (int m = 0; m < PPT; ++m) {
+        if (mask & (1u << m)) {
+            const float2 z = cscale(cmul(G.get(m), v[m]), p0);
+            (m < PPT / 2 ? eqp : eqn)[m * T] = z;
+            if (soft || hard) {
+                float Lb[BPS];
+                unsigned bits;
+                D.dem.run(z, Lb, bits);
+                if (soft) {
+                    float *q = (m < PPT / 2 ? lp : ln) + m * T * BPS;
+                    if (BPS == 1) {
+                        *q = Lb[0];
+                    } else if (BPS == 4) {
+                        *reinterpret_cast<float4 *>(q) = make_float4(Lb[0], Lb[1], Lb[2], Lb[3]);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b + 1 < BPS; b += 2) *reinterpret_cast<float2 *>(q + b) = make_float2(Lb[b], Lb[b + 1]);
+                    }
+                }
+                if (hard) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
+            }
+        }
+    }
+    fence_async_smem();
+    group_sync<T, GROUPS>(gid);
+    if (j == 0) {
+        bulk_store_row(eq_out + row * P.ndb, es, (unsigned)P.ndb * 8u);
+        if (soft) bulk_store_row(llr_out + row * P.ndb * BPS, ls, (unsigned)(P.ndb * BPS) * 4u);
+        bulk_commit();
+    }
+    if (hard)
+        pack_bits<BPS, T, GROUPS>(hb, reinterpret_cast<unsigned *>(hb + C::N + 16), hard_out + row * P.hard_stride, P.hard_stride, j, gid);
+}
+
 // Pilot mode (extension): G[] holds the de-rotation only.  Each data symbol is equalised with the LS
 // estimate on its own comb pilots, linearly interpolated across the used-bin list and held constant
 // outside the outermost pilots (the oracle's np.interp).  Off the fast path: positions are recomputed
@@ -692,7 +766,8 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
     uint8_t *hb = S::hb(smem_raw, gid);                                                \
     float2 *hp = S::hp(smem_raw, gid);                                                 \
     float *ls = P.ls_stride ? reinterpret_cast<float *>(smem_raw + S::BYTES) + gid * P.ls_stride : nullptr; \
-    (void)redu; (void)redf; (void)stage; (void)hp; (void)ls;                           \
+    float2 *es = reinterpret_cast<float2 *>(smem_raw + S::BYTES + GROUPS * P.ls_stride * 4) + gid * P.es_stride; \
+    (void)redu; (void)redf; (void)stage; (void)hp; (void)ls; (void)es;                 \
     for (int i = j; i < S::HB_STRIDE; i += T) hb[i] = 0;                               \
     fill_twiddles<C>(S::tws(smem_raw), P.tw, tid, S::THREADS);                              \
     __syncthreads();                                                                   \
@@ -749,7 +824,7 @@ template <class C, bool GSM> struct MinBlocksRxF {
 // preamble is then evaluated once per hypothesis (window re-read through L1/L2, de-rotated, transformed,
 // correlated), the hypothesis with the largest peak wins (first on ties) and its phasor row multiplies every
 // data window of the frame before the FFT.
-template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO>
+template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO, bool BULK = false>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
@@ -881,6 +956,9 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
             } else if (PIL) {
                 data_epilogue_pilot<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, hp, j, gid, eq_out,
                                                         llr_out, hard_out);
+            } else if (BULK) {
+                data_epilogue_bulk<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, es, j, gid, eq_out,
+                                                       llr_out, hard_out);
             } else {
                 data_epilogue<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, j, gid, eq_out, llr_out,
                                                   hard_out);
@@ -890,6 +968,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
         pos = npos;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (BULK && j == 0) bulk_wait_all();             // the last rows must have left shared memory before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------

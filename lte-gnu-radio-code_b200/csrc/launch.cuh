@@ -13,7 +13,7 @@ template <class C> struct GroupsFor {
 };
 
 struct LaunchDims {
-    int grid, iters;
+    int grid, iters, ctas_per_sm;
 };
 
 void count_launch();
@@ -47,6 +47,7 @@ static inline cudaError_t plan_launch(int threads, int &smem, int groups, long l
     if (grid < 1) grid = 1;
     dims.grid = (int)grid;
     dims.iters = (int)((work + grid * groups - 1) / (grid * groups));
+    dims.ctas_per_sm = cached_bps;
     return cudaSuccess;
 }
 
@@ -68,20 +69,42 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     constexpr bool GSM = RxFOpts<LOG2N>::GSM, SB = RxFOpts<LOG2N>::SB;
     if (n_frames <= 0) return cudaSuccess;
     if (P.pil_k && P.n_cfo) return cudaErrorInvalidValue;       // the hypothesis bank is not combined with comb pilots
-#define OFDM_LAUNCH_RXF(PIL, CFO)                                                                                    \
+#define OFDM_LAUNCH_RXF(PIL, CFO, BULK, Q)                                                                           \
     {                                                                                                                \
-        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO>;                                           \
-        int SM = Smem<C, G, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : G * P.ls_stride * 4);                           \
+        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO, BULK>;                                     \
+        int SM = Smem<C, G, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : G * (Q.ls_stride * 4 + Q.es_stride * 8));       \
         cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);                                                 \
         if (e != cudaSuccess) return e;                                                                              \
-        k<<<d.grid, TH, SM, st>>>(P, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, hyp, \
+        k<<<d.grid, TH, SM, st>>>(Q, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, hyp, \
                                   H, eq, llr, hard);                                                                 \
     }
+    // The per-lane variant only knows the 64-QAM LLR staging of small transforms (api.cu); the bulk-store variant
+    // (64-QAM only, see data_epilogue_bulk) needs 16-byte aligned rows and must not cost a resident CTA.
+    DevParams Qp = P;
+    Qp.es_stride = 0;
+    if (P.bulk_rows && !(P.bps == 6 && LOG2N <= 6)) Qp.ls_stride = 0;
+    const bool bulk_ok = P.bulk_rows && !P.pil_k && !P.n_cfo && ((reinterpret_cast<unsigned long long>(eq) & 15ull) == 0) &&
+                         ((reinterpret_cast<unsigned long long>(llr) & 15ull) == 0);
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
-        if (P.pil_k) OFDM_LAUNCH_RXF(true, false)
-        else if (P.n_cfo) OFDM_LAUNCH_RXF(false, true)
-        else OFDM_LAUNCH_RXF(false, false)
+        if (P.pil_k) OFDM_LAUNCH_RXF(true, false, false, Qp)
+        else if (P.n_cfo) OFDM_LAUNCH_RXF(false, true, false, Qp)
+        else {
+            bool bulk = false;
+            if constexpr (BPS == 6) {
+                if (bulk_ok) {
+                    LaunchDims db, dp;
+                    int smb = Smem<C, G, false, false, GSM, SB>::BYTES + G * (P.ls_stride * 4 + P.es_stride * 8);
+                    int smp = Smem<C, G, false, false, GSM, SB>::BYTES + G * Qp.ls_stride * 4;
+                    const cudaError_t eb = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, true>>(TH, smb, G, n_frames, sms, db);
+                    const cudaError_t ep = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, false>>(TH, smp, G, n_frames, sms, dp);
+                    if (eb != cudaSuccess) cudaGetLastError();              // rows do not fit next to the transform: not an error
+                    bulk = eb == cudaSuccess && ep == cudaSuccess && db.ctas_per_sm >= dp.ctas_per_sm;
+                }
+                if (bulk) OFDM_LAUNCH_RXF(false, false, true, P)
+            }
+            if (!bulk) OFDM_LAUNCH_RXF(false, false, false, Qp)
+        }
         count_launch();
     })
 #undef OFDM_LAUNCH_RXF
@@ -105,10 +128,13 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
             k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard);
         } else {
             constexpr auto k = rx_demod_kernel<C, BPS, G, false>;
-            SM += G * P.ls_stride * 4;
+            DevParams Q = P;
+            Q.es_stride = 0;
+            if (P.bulk_rows && !(P.bps == 6 && LOG2N <= 6)) Q.ls_stride = 0;
+            SM += G * Q.ls_stride * 4;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
-            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard);
+            k<<<d.grid, TH, SM, st>>>(Q, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard);
         }
         count_launch();
     })
