@@ -274,6 +274,22 @@ __device__ __forceinline__ void fill_twiddles(float2 *tws, const float2 *__restr
     }
 }
 
+// number of last-pass twiddles a thread owns, and their load from the CTA's table (call after fill_twiddles + barrier)
+template <class C> struct LastPassTw {
+    static constexpr int P = C::NPASS - 1, R = C::radix(P), Ns = C::ns(P), B = C::PPT / R;
+    static constexpr int COUNT = P > 0 ? B * (R - 1) : 1;
+    static __device__ __forceinline__ void load(float2 (&w)[COUNT], const float2 *tws, int j) {
+        static_assert(!C::CH, "register twiddles are taken from the full table");
+        if (P > 0) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) w[b * (R - 1) + q - 1] = tws[C::tw_off(P) + (q - 1) * Ns + ((j + b * C::T) & (Ns - 1))];
+            }
+        }
+    }
+};
+
 template <bool INV> __device__ __forceinline__ float2 twmul(float2 a, float2 w) {
     return INV ? cmulc(a, w) : cmul(a, w);
 }
@@ -298,11 +314,19 @@ template <bool INV, int R, int B, int PPT> __device__ __forceinline__ void bfly_
 
 // One pass P of the transform, fully unrolled through template recursion.  Butterfly b of a thread
 // works on registers b + q*B (B = PPT/R butterflies per thread), i.e. on elements j + b*T + q*N/R.
-template <class C, bool INV, int GROUPS, int P, bool SB = false> struct Pass {
+// TWR: the twiddles of the LAST pass depend only on the thread (its element j + b*T never leaves the first Ns of the
+// pass), so a kernel with registers to spare keeps them in twreg[b*(R-1) + q-1] instead of reading the table.
+template <class C, bool INV, int GROUPS, int P, bool SB = false, bool TWR = false> struct Pass {
     static __device__ __forceinline__ void run(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1,
-                                               int j, int gid, int &pp) {
+                                               int j, int gid, int &pp, const float2 *twreg = nullptr) {
         constexpr int R = C::radix(P), Ns = C::ns(P), B = C::PPT / R;
-        if (P > 0) {
+        if (P > 0 && TWR && P == C::NPASS - 1) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], twreg[b * (R - 1) + q - 1]);
+            }
+        } else if (P > 0) {
             constexpr int off = C::tw_off(P);
 #pragma unroll
             for (int b = 0; b < B; ++b) {
@@ -340,20 +364,21 @@ template <class C, bool INV, int GROUPS, int P, bool SB = false> struct Pass {
 #pragma unroll
             for (int m = 0; m < C::PPT; ++m) v[m] = buf[lay<C, P>(j + m * C::T)];
             if (SB) group_sync<C::T, GROUPS>(gid);
-            Pass<C, INV, GROUPS, P + 1, SB>::run(v, tws, buf0, buf1, j, gid, pp);
+            Pass<C, INV, GROUPS, P + 1, SB, TWR>::run(v, tws, buf0, buf1, j, gid, pp, twreg);
         }
     }
 };
-template <class C, bool INV, int GROUPS, bool SB> struct Pass<C, INV, GROUPS, 4, SB> {
-    static __device__ __forceinline__ void run(float2 (&)[C::PPT], const float2 *, float2 *, float2 *, int, int, int &) {}
+template <class C, bool INV, int GROUPS, bool SB, bool TWR> struct Pass<C, INV, GROUPS, 4, SB, TWR> {
+    static __device__ __forceinline__ void run(float2 (&)[C::PPT], const float2 *, float2 *, float2 *, int, int, int &,
+                                               const float2 * = nullptr) {}
 };
 
 // In-place transform of the group's symbol.  pp is the running ping-pong selector (kept across
 // calls so that consecutive transforms never need a second barrier per exchange).
-template <class C, bool INV, int GROUPS, bool SB = false>
+template <class C, bool INV, int GROUPS, bool SB = false, bool TWR = false>
 __device__ __forceinline__ void fft_group(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1, int j,
-                                          int gid, int &pp) {
-    Pass<C, INV, GROUPS, 0, SB>::run(v, tws, buf0, buf1, j, gid, pp);
+                                          int gid, int &pp, const float2 *twreg = nullptr) {
+    Pass<C, INV, GROUPS, 0, SB, TWR>::run(v, tws, buf0, buf1, j, gid, pp, twreg);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -846,6 +846,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
     constexpr int DEPTH = OFDM_PF_DEPTH, SLOT = S::THREADS * PPT;
     long long pf_pos = pos;
     int pf_s = 0, pf_it = 0, pf_slot = 0, slot = 0;
+    (void)slot;
     auto request = [&]() {
         prefetch_pts<T, PPT, S::THREADS>(stage + pf_slot * SLOT, x, pf_pos + (long long)pf_s * L, n_samples, j, tid);
         pf_slot = pf_slot + 1 == DEPTH ? 0 : pf_slot + 1;
@@ -1151,6 +1152,9 @@ __device__ __forceinline__ unsigned ld_word_guarded(const uint8_t *__restrict__ 
     return w;
 }
 
+#ifndef OFDM_TX_TWREG_MAX_LOG2N
+#define OFDM_TX_TWREG_MAX_LOG2N 7      // B200: +3 % at N=64, +1.5 % at N=128, nothing from N=256 on
+#endif
 template <class C, int BPS, int GROUPS, bool PIL>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksTx<C>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
@@ -1166,6 +1170,10 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     float2 *lut = S::lut(smem_raw);
     for (int i = tid; i <= ZERO; i += S::THREADS) lut[i] = i < (1 << BPS) ? map_bits<BPS>((unsigned)i) : make_float2(0.f, 0.f);
     __syncthreads();
+    // the last pass' twiddles live in registers where the transmitter has them to spare (N <= OFDM_TX_TWREG_MAX_LOG2N)
+    constexpr bool TWR = C::LOG2N <= OFDM_TX_TWREG_MAX_LOG2N && !C::CH;
+    float2 twreg[LastPassTw<C>::COUNT];
+    if constexpr (TWR) LastPassTw<C>::load(twreg, tws, j);
     const BinMap map = make_bin_map<T, PPT>(P.ndb, j);
     // bit position of this thread's first bin of each spectrum half inside a payload row; the other
     // bins of the half are T*BPS bits (a whole number of bytes) further on
@@ -1252,7 +1260,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                 for (int m = 0; m < PPT; ++m) v[m] = __ldg(z + m * T);
             }
         }
-        fft_group<C, true, GROUPS>(v, tws, b0, b1, j, gid, pp);
+        fft_group<C, true, GROUPS, false, TWR>(v, tws, b0, b1, j, gid, pp, twreg);
         float3 acc = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < PPT; ++m) {

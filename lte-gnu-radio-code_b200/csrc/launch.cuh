@@ -2,6 +2,7 @@
 // translation units compile in parallel.
 #pragma once
 #include <cstdlib>
+#include <mutex>
 
 #include "kernels.cuh"
 
@@ -23,6 +24,8 @@ void count_launch();
 template <auto kernel>
 static inline cudaError_t plan_launch(int threads, int &smem, int groups, long long work, int sms, LaunchDims &dims) {
     static int cached_dev = -1, cached_bps = 0, cached_smem = -1, max_smem = -1;
+    static std::mutex mu;                      // blocks of one flowgraph call work() from their own threads
+    std::lock_guard<std::mutex> lock(mu);
     // tuning aid: OFDM_SMEM_PAD=<bytes> inflates the dynamic shared-memory request to lower occupancy
     static const int pad = getenv("OFDM_SMEM_PAD") ? atoi(getenv("OFDM_SMEM_PAD")) : 0;
     smem += pad;
