@@ -215,3 +215,26 @@ def test_full_size_round_trip_properties():
     m3 = make(dict(REF, bps=2, snr=100, gate=0.5, noise_var=0.5))
     got3 = m3.rx_frames(rx2, 1000)
     assert torch.allclose(got3["llr"], got2["llr"][:3000] * 2.0, rtol=1e-5, atol=1e-6)
+
+
+def test_on_device_loopback_counts_match_oracle_counters():
+    """TX -> channel -> RX -> counters without leaving the device (ofdm_b200.loopback); the counter vector equals
+    the one the oracle computes from the same tensors copied back."""
+    from ofdm_b200 import ModemConfig
+    from ofdm_b200.loopback import Loopback
+    lb = Loopback(ModemConfig(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4, snr=100, gate=0.5,
+                              noise_var=0.02))
+    n_frames = 50
+    r = lb.run(n_frames, seed=5, noise_sigma=0.1)
+    s = r["summary"]
+    assert s["frames"] == n_frames and s["frames_locked"] == n_frames and s["bits"] == n_frames * 3 * 240
+    tx_bits = np.unpackbits(r["bits"].cpu().numpy().reshape(n_frames * 3, 30), axis=1).reshape(-1)
+    rx_bits = np.unpackbits(r["out"]["hard"].cpu().numpy(), axis=1).reshape(-1)
+    eq = r["out"]["eq"].cpu().numpy().reshape(-1)
+    ref = oo.counters(rx_bits, tx_bits, eq, oo.bits_to_symbols(tx_bits, 4))
+    assert s["bit_errors"] == ref[0] and 0 < s["ber"] < 0.2
+    assert abs(s["evm_rms"] - np.sqrt(ref[2] / ref[3])) < 1e-4
+    # noiseless reference channel: error free, and per-frame random taps are accepted
+    assert lb.run(n_frames, seed=6)["summary"]["bit_errors"] == 0
+    taps = lb.taps_random(n_frames, [0.2, 0.7, 0.1], 3)
+    assert lb.run(n_frames, seed=7, taps=taps, noise_sigma=0.01)["summary"]["frames"] == n_frames
