@@ -133,3 +133,50 @@ def test_headless_ofdm_chain_loopback():
     assert rel_err(res["rx_out"][:n], out[:n]) < 1e-4
     res = mod.run_loopback(num_ofdm_symb=24, n_calls=2, seed=1234, variant="rxofdm")
     assert res["bit_errors"] == 0 and res["bits"] == 6 * 120
+
+
+def test_blocks_accept_short_and_empty_buffers(golden):
+    """Scheduler buffers shorter than one frame, and empty ones: no trial passes the window guard
+    (synch_and_chan_est.py:147), state rows survive, the written prefix follows the count rule.  The gr-RXOFDM
+    family is compared with its oracles; the utsa block's reference raises ValueError whenever the buffer does not
+    hold exactly num_ofdm_symb symbols (SynchAndChanEst.py:253) -- the drop-in clamps instead, which is checked here."""
+    import utsa_ofdm
+    import RXOFDM
+    import OFDMReceiver
+    from oracle.blocks_oracle import SynchEstAndFOOracle, SynchEstFOAndDSSSOracle
+    rx = golden["rx_offline"][0].astype(np.complex64)
+    pairs = [
+        (RXOFDM.synch_and_chan_est(24, 64, 16, 62, [1, 3], 60, 100, "/tmp/", "o", 0, 0, zc_root=23), RxofdmBlockOracle(24, 64, 16, 62, [1, 3], 60, 100, zc_root=23)),
+        (OFDMReceiver.SynchEstAndFO(1, [0.0, 500.0], "/tmp/", "c", 0), SynchEstAndFOOracle(1, [0.0, 500.0])),
+        (OFDMReceiver.SynchEstFOAndDSSS(1, [0.0], "/tmp/", "c", 0), SynchEstFOAndDSSSOracle(1, [0.0])),
+    ]
+    lengths = (2000, 100, 0, 33, 1500)
+    for blk, ora in pairs:
+        for n_in in lengths:
+            buf = rx[:n_in]
+            out_b = np.zeros(4096, np.complex64)
+            out_o = np.zeros(4096, np.complex64)
+            assert blk.work([buf], [out_b]) == len(out_b)
+            assert ora.work(buf, out_o) == len(out_o)
+            assert np.array_equal(np.asarray(blk.time_synch_ref), np.asarray(ora.time_synch_ref)), (type(blk).__name__, n_in)
+            assert blk.last_written == ora.last_written
+            n = ora.last_written
+            if n:
+                assert rel_err(out_b[:n], out_o[:n]) < 1e-4
+    blk = utsa_ofdm.SynchAndChanEst(24, 64, 16, 62, [1, 3], 60, 100, 0.7, "/tmp/", "c.pckl", 0, 0)
+    ora = UtsaBlockOracle(24, 64, 16, 62, [1, 3], 60, 100, 0.7)
+    out_b = np.zeros(4096, np.complex64)
+    out_o = np.zeros(4096, np.complex64)
+    for n_in in (1920, 100, 0, 33, 1999):
+        buf = rx[:n_in]
+        assert blk.work([buf], [out_b]) == len(out_b)
+        if n_in >= 1920:                                   # the only lengths the reference accepts for num_ofdm_symb = 24
+            assert ora.work(buf, out_o) == len(out_o)
+            assert tuple(blk.time_synch_ref) == tuple(ora.time_synch_ref)
+            assert blk.last_written == ora.last_written
+            if ora.last_written:
+                assert rel_err(out_b[:ora.last_written], out_o[:ora.last_written]) < 1e-4
+        else:
+            with pytest.raises(ValueError):
+                UtsaBlockOracle(24, 64, 16, 62, [1, 3], 60, 100, 0.7).work(buf, out_o)
+            assert blk.last_written <= (n_in // 80) * 60
