@@ -154,6 +154,24 @@ def _cpu_chunk(args):
     return dt, int(hard.sum())
 
 
+def cpu_tx_rate(wname, target_seconds):
+    """data symbols/s of the oracle transmitter (bits -> waveform) on one host core."""
+    from oracle import ofdm_oracle as oo
+    w = WORKLOADS[wname]
+    prm = oo.ModemParams(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
+                         num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100, gate=0.5)
+    rng = np.random.default_rng(5)
+    nf, done, t_used = 4, 0, 0.0
+    while t_used < target_seconds:
+        bits = rng.integers(0, 2, nf * w["d"] * w["num_data_bins"] * w["bps"])
+        t0 = time.perf_counter()
+        oo.tx_modulate(bits, prm, nf)
+        t_used += time.perf_counter() - t0
+        done += nf * w["d"]
+        nf = min(nf * 2, 4096)
+    return done / t_used
+
+
 def cpu_reference_rate(wname, target_seconds, literal=True, cores=None):
     """data symbols/s of the oracle port over all host cores on a bounded sample."""
     import multiprocessing as mp
@@ -359,10 +377,14 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu:
         v, info = cpu_reference_rate(wname, args.cpu_seconds / 2.0, literal=True)
         v2, info2 = cpu_reference_rate(wname, args.cpu_seconds / 4.0, literal=False)
+        v0, _ = cpu_reference_rate(wname, 2.0, literal=True, cores=1)
+        v1, _ = cpu_reference_rate(wname, 2.0, literal=False, cores=1)
+        vt = cpu_tx_rate(wname, 2.0)
         res["cpu_baseline"] = {"value": v, "unit": "symbols/s", "cores": info["cores"], "kind": "port",
                                "sample": "%d frames (%d data symbols) of the same workload, literal NumPy restatement "
                                          "of the reference arithmetic, one process per core, %.1f s"
                                          % (info["frames"], info["data_symbols"], info["seconds"]),
+                               "literal_1core": v0, "vectorised_1core": v1, "tx_1core": vt,
                                "vectorised_value": v2,
                                "vectorised_note": "same arithmetic with the dense diag matmuls replaced by element-wise "
                                                   "products (not what the reference executes)"}
