@@ -225,12 +225,14 @@ struct ofdm_plan {
     void *d_tables;                // one allocation holding every table
     void *d_cfo;                   // frequency-offset hypothesis bank (optional)
     // staging for the host-buffer entry points (grown on demand, freed with the plan)
-    static const int NSLOT = 2;
+    static const int NSLOT = 3;
     cudaStream_t st[NSLOT];
     cudaEvent_t ev[NSLOT];
     bool streams_made;
     void *stage[NSLOT];
     size_t stage_bytes[NSLOT];
+    void *small;                   // per-frame results of the host-buffer receiver (delay, peak, locked)
+    size_t small_bytes;
 };
 
 static const KernelSet *kset_for(int log2n) {
@@ -435,6 +437,7 @@ int ofdm_plan_destroy(ofdm_plan *pl) {
     if (!pl) return OFDM_OK;
     cudaFree(pl->d_tables);
     if (pl->d_cfo) cudaFree(pl->d_cfo);
+    if (pl->small) cudaFree(pl->small);
     for (int i = 0; i < ofdm_plan::NSLOT; ++i) {
         if (pl->stage[i]) cudaFree(pl->stage[i]);
         if (pl->streams_made) {
@@ -465,6 +468,7 @@ int ofdm_plan_set_cfo_bank(ofdm_plan *pl, const double *cycles_per_sample, int32
         return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: bad argument (0..64 hypotheses)%s");
     if (n_hyp > 0 && pl->prm.pilot_spacing) return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: not available with comb pilots%s");
     if (pl->d_cfo) cudaFree(pl->d_cfo);
+    if (pl->small) cudaFree(pl->small);
     pl->d_cfo = nullptr;
     pl->dev.n_cfo = 0;
     pl->dev.cfo = nullptr;
@@ -656,30 +660,50 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
     const ofdm_params &p = pl->prm;
     const int64_t L = p.nfft + p.cp_len, fl = (int64_t)(p.m0 + p.d) * L;
     const int64_t ndb = pl->dev.ndd, hs = pl->dev.hard_stride;
-    // chunk size: ~32 MiB of input per slot so copies and kernels of adjacent chunks overlap
-    int64_t per = (32ll << 20) / (frame_stride * 8);
-    if (per < 1) per = 1;
-    if (per > n_frames) per = n_frames;
+    // Chunk schedule: the link back to the host is the bottleneck (D2H bytes > H2D bytes).  The first chunk is small
+    // so that the first D2H starts early, and chunks then grow by 1.5x (slower than the D2H : H2D byte ratio, so the
+    // upload of chunk i+1 always hides behind the download of chunk i) up to the steady size.
+    // OFDM_HOST_CHUNK_MB / OFDM_HOST_FIRST_MB (environment) override the two sizes.
+    static const int big_mb = getenv("OFDM_HOST_CHUNK_MB") ? atoi(getenv("OFDM_HOST_CHUNK_MB")) : 32;
+    static const int first_mb = getenv("OFDM_HOST_FIRST_MB") ? atoi(getenv("OFDM_HOST_FIRST_MB")) : 4;
+    auto frames_for = [&](int mb) {
+        int64_t n = ((int64_t)(mb > 0 ? mb : 1) << 20) / (frame_stride * 8);
+        if (n < 1) n = 1;
+        return n < n_frames ? n : n_frames;
+    };
+    const int64_t per_big = frames_for(big_mb), per_first = frames_for(first_mb < big_mb ? first_mb : big_mb);
+    const int64_t per = per_big;
     const size_t b_in = al256((size_t)((per - 1) * frame_stride + fl + 2 * p.cp_len) * 8);
-    const size_t b_dl = al256(per * 4), b_pk = al256(per * 4), b_lk = al256(per);
     const size_t b_eq = al256(per * p.d * ndb * 8), b_ll = al256(per * p.d * ndb * p.bps * 4), b_hd = al256(per * p.d * hs);
-    const size_t tot = b_in + b_dl + b_pk + b_lk + b_eq + b_ll + b_hd;
+    const size_t tot = b_in + b_eq + b_ll + b_hd;
     for (int s = 0; s < ofdm_plan::NSLOT; ++s) {
         rc = ensure_stage(pl, s, tot);
         if (rc) return rc;
     }
+    // per-frame results (9 bytes per frame) are kept for the whole call and copied back once at the end
+    const size_t b_dl = al256(n_frames * 4), b_pk = al256(n_frames * 4), b_lk = al256(n_frames);
+    if (pl->small_bytes < b_dl + b_pk + b_lk) {
+        if (pl->small) cudaFree(pl->small);
+        pl->small = nullptr;
+        pl->small_bytes = 0;
+        CU(cudaMalloc(&pl->small, b_dl + b_pk + b_lk), "per-frame staging cudaMalloc");
+        pl->small_bytes = b_dl + b_pk + b_lk;
+    }
+    int32_t *ddl = (int32_t *)pl->small;
+    float *dpk = (float *)((char *)pl->small + b_dl);
+    uint8_t *dlk = (uint8_t *)((char *)pl->small + b_dl + b_pk);
     int slot = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += per, slot ^= 1) {
-        const int64_t nf = (n_frames - f0 < per) ? (n_frames - f0) : per;
+    int64_t want = per_first;
+    for (int64_t f0 = 0; f0 < n_frames; slot = (slot + 1) % ofdm_plan::NSLOT) {
+        const int64_t nf = (n_frames - f0 < want) ? (n_frames - f0) : want;
+        want = want + want / 2 + 1;
+        if (want > per_big) want = per_big;
         cudaStream_t st = pl->st[slot];
         char *b = (char *)pl->stage[slot];
         float *din = (float *)b;
-        int32_t *ddl = (int32_t *)(b + b_in);
-        float *dpk = (float *)(b + b_in + b_dl);
-        uint8_t *dlk = (uint8_t *)(b + b_in + b_dl + b_pk);
-        float *deq = (float *)(b + b_in + b_dl + b_pk + b_lk);
-        float *dll = (float *)(b + b_in + b_dl + b_pk + b_lk + b_eq);
-        uint8_t *dhd = (uint8_t *)(b + b_in + b_dl + b_pk + b_lk + b_eq + b_ll);
+        float *deq = (float *)(b + b_in);
+        float *dll = (float *)(b + b_in + b_eq);
+        uint8_t *dhd = (uint8_t *)(b + b_in + b_eq + b_ll);
         // samples needed by this chunk: [lo, hi)
         int64_t lo = first + f0 * frame_stride - p.sync_advance;
         if (lo < 0) lo = 0;
@@ -687,18 +711,20 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
         if (hi > n_samples) hi = n_samples;
         if (hi < lo) hi = lo;
         CU(cudaMemcpyAsync(din, h_time + 2 * lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, st), "H2D");
-        CU(pl->ks->rx_frames(pl->dev, (const float2 *)din, hi - lo, first + f0 * frame_stride - lo, frame_stride, nf, ddl,
-                             dpk, dlk, nullptr, nullptr, (float2 *)deq, h_llr ? dll : nullptr, h_hard ? dhd : nullptr, st, pl->sms),
+        CU(pl->ks->rx_frames(pl->dev, (const float2 *)din, hi - lo, first + f0 * frame_stride - lo, frame_stride, nf, ddl + f0,
+                             dpk + f0, dlk + f0, nullptr, nullptr, (float2 *)deq, h_llr ? dll : nullptr, h_hard ? dhd : nullptr, st, pl->sms),
            "ofdm_rx_frames_host(kernel)");
-        if (h_delay) CU(cudaMemcpyAsync(h_delay + f0, ddl, nf * 4, cudaMemcpyDeviceToHost, st), "D2H");
-        if (h_peak) CU(cudaMemcpyAsync(h_peak + f0, dpk, nf * 4, cudaMemcpyDeviceToHost, st), "D2H");
-        if (h_locked) CU(cudaMemcpyAsync(h_locked + f0, dlk, nf, cudaMemcpyDeviceToHost, st), "D2H");
-        CU(cudaMemcpyAsync(h_eq + 2 * f0 * p.d * ndb, deq, (size_t)nf * p.d * ndb * 8, cudaMemcpyDeviceToHost, st), "D2H");
         if (h_llr)
             CU(cudaMemcpyAsync(h_llr + f0 * p.d * ndb * p.bps, dll, (size_t)nf * p.d * ndb * p.bps * 4, cudaMemcpyDeviceToHost, st), "D2H");
+        CU(cudaMemcpyAsync(h_eq + 2 * f0 * p.d * ndb, deq, (size_t)nf * p.d * ndb * 8, cudaMemcpyDeviceToHost, st), "D2H");
         if (h_hard) CU(cudaMemcpyAsync(h_hard + f0 * p.d * hs, dhd, (size_t)nf * p.d * hs, cudaMemcpyDeviceToHost, st), "D2H");
+        f0 += nf;
     }
     for (int s = 0; s < ofdm_plan::NSLOT; ++s) CU(cudaStreamSynchronize(pl->st[s]), "ofdm_rx_frames_host(sync)");
+    if (h_delay) CU(cudaMemcpyAsync(h_delay, ddl, n_frames * 4, cudaMemcpyDeviceToHost, pl->st[0]), "D2H");
+    if (h_peak) CU(cudaMemcpyAsync(h_peak, dpk, n_frames * 4, cudaMemcpyDeviceToHost, pl->st[0]), "D2H");
+    if (h_locked) CU(cudaMemcpyAsync(h_locked, dlk, n_frames, cudaMemcpyDeviceToHost, pl->st[0]), "D2H");
+    CU(cudaStreamSynchronize(pl->st[0]), "ofdm_rx_frames_host(sync)");
     return OFDM_OK;
 }
 
@@ -719,7 +745,7 @@ int ofdm_tx_modulate_host(ofdm_plan *pl, const uint8_t *h_bits, float *h_time, i
         if (rc) return rc;
     }
     int slot = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += per, slot ^= 1) {
+    for (int64_t f0 = 0; f0 < n_frames; f0 += per, slot = (slot + 1) % ofdm_plan::NSLOT) {
         const int64_t nf = (n_frames - f0 < per) ? (n_frames - f0) : per;
         cudaStream_t st = pl->st[slot];
         char *b = (char *)pl->stage[slot];
