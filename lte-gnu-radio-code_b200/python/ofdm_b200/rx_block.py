@@ -91,6 +91,39 @@ class RxBlockBase(gr.sync_block):
             self.est_synch_freq[r] = se_h[i]
         return ht_h
 
+    # ---- throughput API (additive): device-resident, no scheduler buffers ---------------
+    def process_batch(self, rx, first=0, want_llr=True, want_hard=True):
+        """Framed receiver over a batch of independent streams that stay in device memory.
+
+        rx: complex64 CUDA tensor [B, T] (B streams) or [T]; every stream holds whole frames of M0 synch + D data
+        symbols starting at sample `first`.  Per frame this is the arithmetic of one accepted lock of work() --
+        loop A's body at the frame's nominal position, the LS channel estimate, and loop B for the frame's D data
+        symbols -- in one fused kernel.  Returns a dict of device tensors: delay / peak / locked [B, F],
+        eq [B, F*D, ndb] (+ llr [B, F*D, ndb*bps], hard [B, F*D, hard_stride])."""
+        c = self.cfg
+        flat = rx.reshape(-1) if rx.dim() == 2 else rx
+        B = rx.shape[0] if rx.dim() == 2 else 1
+        T = flat.numel() // B
+        F = (T - first) // c.frame_len
+        if F <= 0:
+            raise ValueError("streams of %d samples hold no whole frame of %d samples" % (T, c.frame_len))
+        if B == 1 or T == F * c.frame_len + first and first == 0:
+            out = self.modem.rx_frames(flat, B * F, first=first, want_llr=want_llr, want_hard=want_hard)
+            parts = [out]
+        else:                                    # ragged streams: one launch per stream, each with its own origin
+            parts = [self.modem.rx_frames(flat, F, first=b * T + first, want_llr=want_llr, want_hard=want_hard)
+                     for b in range(B)]
+        torch = self._torch
+        res = {}
+        for k in ("delay", "peak", "locked", "eq", "llr", "hard"):
+            vals = [p_[k] for p_ in parts]
+            if vals[0] is None:
+                res[k] = None
+                continue
+            v = vals[0] if len(vals) == 1 else torch.cat(vals)
+            res[k] = v.reshape((B, F) if k in ("delay", "peak", "locked") else (B, F * c.d, -1))
+        return res
+
     def _dump_chan(self, chan_est_tim, path):
         with open(path, "wb") as f:
             pickle.dump(np.asarray(chan_est_tim, dtype=complex).reshape(1, -1), f, protocol=2)

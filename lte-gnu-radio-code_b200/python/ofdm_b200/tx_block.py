@@ -52,6 +52,26 @@ class TxReplayBase(gr.sync_block):
         out = m.tx_modulate(torch.from_numpy(packed).to(m.device), n_frames)
         return out.cpu().numpy().reshape(1, -1)
 
+    # ---- throughput API (additive) ---------------------------------------------------------
+    @staticmethod
+    def modulate_batch(bits, config, n_frames=None, device=None):
+        """bits -> waveform on the GPU, device tensors in and out: packed payload rows (uint8 CUDA tensor,
+        n_frames*D rows of config.hard_stride bytes, MSB first) -> complex64 [n_frames*frame_len].  The arithmetic
+        of MultiAntennaSystem.multi_ant_binary_map + multi_ant_symb_gen (MultiAntennaSystem.py:113-219), which is
+        what produced the pickles the work() path replays."""
+        from .modem import Modem
+        key = (id(config), str(device))
+        cache = TxReplayBase._modems
+        if key not in cache:
+            cache.clear()
+            cache[key] = Modem(config, device=device)
+        m = cache[key]
+        if n_frames is None:
+            n_frames = bits.numel() // (config.d * config.hard_stride)
+        return m.tx_modulate(bits.reshape(-1), n_frames)
+
+    _modems = {}
+
     def work(self, input_items, output_items):
         """Streams the stored waveform, wrapping around at its end.  The reference copies the whole
         array to out[0:T] on every call (and fails when T exceeds the buffer); the first
