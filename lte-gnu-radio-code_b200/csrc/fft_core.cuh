@@ -57,9 +57,9 @@ __host__ __device__ constexpr int fft_tw_off(int log2n, int ppt, int p, bool ch 
     return o;
 }
 
-template <int LOG2N_, int PPT_, bool CH_ = false> struct FftCfg {
+template <int LOG2N_, int PPT_, bool CH_ = false, bool PAD_ = false> struct FftCfg {
     static constexpr int LOG2N = LOG2N_, PPT = PPT_;
-    static constexpr bool CH = CH_;
+    static constexpr bool CH = CH_, PAD = PAD_;
     static constexpr int N = 1 << LOG2N;
     static constexpr int T = N / PPT;                     // threads per symbol group
     static constexpr int LP = fft_lp(PPT);
@@ -69,7 +69,8 @@ template <int LOG2N_, int PPT_, bool CH_ = false> struct FftCfg {
     static constexpr int NEXCH = NPASS - 1;               // shared-memory exchanges per transform
     static constexpr int TW_ENTRIES = fft_tw_off(LOG2N, PPT, NPASS, CH);
     // padded buffer length in complex slots; N == 64 uses a pad-per-8 layout (see lay())
-    static constexpr int BUF = (LOG2N == 6) ? 72 : N;
+    // (PAD: one pad slot per 16, resp. 8 per 64, instead of XOR swizzles -- see lay())
+    static constexpr int BUF = (LOG2N == 6) ? 72 : (PAD ? (PPT == 16 ? N + N / 16 : N + N / 8) : N);
     __host__ __device__ static constexpr int radix(int p) { return fft_radix(LOG2N, PPT, p); }
     __host__ __device__ static constexpr int ns(int p) { return fft_ns(LOG2N, PPT, p); }
     __host__ __device__ static constexpr int tw_off(int p) { return fft_tw_off(LOG2N, PPT, p, CH); }
@@ -77,7 +78,7 @@ template <int LOG2N_, int PPT_, bool CH_ = false> struct FftCfg {
 
 // Points per thread for each transform size and kernel family (overridable for A/B runs, e.g.
 // -DOFDM_PPT_RX_4096=8).  Measured on B200 (tools/sweep_minb.sh): 16 points per thread speed the
-// transmitter up by 11-28 % at N >= 512 and the receiver by 14 % at N = 4096; at N = 1024/2048 the
+// transmitter up by 11-28 % at N >= 256 and the receiver by 14 % at N = 4096; at N = 1024/2048 the
 // receiver also carries 16 equaliser gains per thread and is faster with 8.
 #ifndef OFDM_PPT_TX_LARGE
 #define OFDM_PPT_TX_LARGE 16
@@ -95,7 +96,7 @@ template <int LOG2N> struct PptRx {
     static constexpr int value = LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RX_1024 : (LOG2N == 11 ? OFDM_PPT_RX_2048 : OFDM_PPT_RX_4096));
 };
 #ifndef OFDM_PPT_TX_MIN_LOG2N
-#define OFDM_PPT_TX_MIN_LOG2N 9
+#define OFDM_PPT_TX_MIN_LOG2N 8           // B200: N=256 +11 % with 16 points per thread (one exchange), N=128 -3 %
 #endif
 template <int LOG2N> struct PptTx {
     static constexpr int value = LOG2N >= OFDM_PPT_TX_MIN_LOG2N ? OFDM_PPT_TX_LARGE : 8;
@@ -108,7 +109,13 @@ template <int LOG2N> struct PptTx {
 #ifndef OFDM_TW_CHAIN_RXF_MIN_LOG2N
 #define OFDM_TW_CHAIN_RXF_MIN_LOG2N 10
 #endif
-template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value>;
+#ifndef OFDM_TX_LAY_PAD
+#define OFDM_TX_LAY_PAD 1
+#endif
+#ifndef OFDM_RX_LAY_PAD
+#define OFDM_RX_LAY_PAD 0
+#endif
+template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value, false, OFDM_RX_LAY_PAD != 0>;
 
 // The fused framed receiver (rx_frames_kernel) has its own knobs, because it is the one kernel that
 // keeps per-frame state (the equaliser gains) alive across symbols:
@@ -139,12 +146,14 @@ template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value>;
 template <int LOG2N> struct PptRxF {
     static constexpr int value = LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RXF_1024 : (LOG2N == 11 ? OFDM_PPT_RXF_2048 : OFDM_PPT_RXF_4096));
 };
-template <int LOG2N> using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N)>;
+template <int LOG2N>
+using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N), OFDM_RX_LAY_PAD != 0>;
 template <int LOG2N> struct RxFOpts {
     static constexpr bool GSM = LOG2N >= OFDM_GSM_MIN_LOG2N;
     static constexpr bool SB = LOG2N >= OFDM_SB_MIN_LOG2N || LOG2N <= OFDM_SB_SMALL_MAX_LOG2N;
 };
-template <int LOG2N> using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_TX_MIN_LOG2N)>;
+template <int LOG2N>
+using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_TX_MIN_LOG2N), OFDM_TX_LAY_PAD != 0>;
 
 // Exchange layout for the buffer written by pass P (Ns = PPT^P), chosen so that the scattered write
 // out[(j/Ns)*Ns*R + j%Ns + q*Ns] and the contiguous read in[j + m*T] both hit 16 distinct 8-byte
@@ -154,8 +163,17 @@ template <int LOG2N> using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value, (LOG2N >= 
 //   PPT 8,  P == 1     : i ^ ((i >> 3) & 8)       bit 6 folded into bit 3
 //   PPT 16, P == 0     : i ^ ((i >> 4) & 15)      stride-16 scatter
 //   otherwise          : identity (writes are already lane-contiguous)
+// C::PAD replaces the XOR swizzles by padding -- P == 0: i + (i >> 4), PPT 8 P == 1: i + 8 * (i >> 6) -- which is
+// conflict-free on both sides as well and makes every scattered write `thread base + constant` (77 fewer
+// instructions per 2048-point transmit symbol), at the price of N/16 (N/8) more slots per buffer.  Measured on B200:
+// transmitter +1..2 %, framed receiver 0..-1 % -> transmitter only (OFDM_TX_LAY_PAD / OFDM_RX_LAY_PAD).
 template <class C, int P> __device__ __forceinline__ int lay(int i) {
     if (C::LOG2N == 6) return i + (i >> 3);
+    if (C::PAD) {
+        if (P == 0) return i + (i >> 4);
+        if (P == 1 && C::PPT == 8) return i + ((i >> 6) << 3);
+        return i;
+    }
     if (C::PPT == 16) return P == 0 ? (i ^ ((i >> 4) & 15)) : i;
     if (P == 0) return i ^ ((i >> 4) & 7);
     if (P == 1) return i ^ ((i >> 3) & 8);

@@ -15,6 +15,7 @@
 //     before the current one is transformed, so DRAM latency overlaps the arithmetic without
 //     holding registers.
 #pragma once
+#include <cuda_fp16.h>
 #include "fft_core.cuh"
 
 namespace ofdm {
@@ -110,6 +111,18 @@ template <int T, int PPT> __device__ __forceinline__ BinMap make_bin_map(int n, 
 template <int T, int PPT> __device__ __forceinline__ int bin_out(const BinMap &b, int m) {
     return (m < PPT / 2 ? b.base_p : b.base_n - (PPT / 2) * T) + m * T;
 }
+
+// The framed receiver's epilogue is branch-free (see data_epilogue, DENSE) when at least this many 64ths of the FFT bins
+// carry data; 65 = never.  B200: +3..10 % at a 94 % fill for every size, slower at the LTE fill of 59 %.
+#ifndef OFDM_EPI_CHUNK_SPARSE
+#define OFDM_EPI_CHUNK_SPARSE 0
+#endif
+#ifndef OFDM_EPI_CHUNK_BULK
+#define OFDM_EPI_CHUNK_BULK 0
+#endif
+#ifndef OFDM_DENSE_MIN_FILL64
+#define OFDM_DENSE_MIN_FILL64 48
+#endif
 
 // Output stores: every output byte is written once and never read again by the kernel.  CS selects
 // st.global.cs (streaming, evict first) over a plain write-back store.  Measured on B200: streaming stores are
@@ -573,18 +586,23 @@ template <class C, int BPS> struct DataCtx {
 };
 
 // equalise + demap + store one data symbol held in v[] (FFT output).  SynchAndChanEst.py:232-248.
-template <class C, int BPS, int GROUPS, bool GSM>
+template <class C, int BPS, int GROUPS, bool GSM, bool DENSE = false>
 __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<C, BPS> &D, const float2 (&v)[C::PPT],
                                               const Gains<C, GSM> &G, long long row, float *redf, uint8_t *hb, float *ls,
                                               int j, int gid, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                                               uint8_t *__restrict__ hard_out) {
     constexpr int T = C::T, PPT = C::PPT;
     constexpr bool CS = C::LOG2N >= OFDM_RX_CS_MIN_LOG2N;
+    // DENSE: every bin is equalised and demapped unconditionally and only the stores are predicated, so the PPT
+    // per-bin dependency chains are one basic block the scheduler can interleave.  For grids where most bins are used
+    // (chosen at launch from the fill ratio, launch_rx_frames).
     const unsigned mask = D.map.mask;
     float pw = 0.f;
 #pragma unroll
-    for (int m = 0; m < PPT; ++m)
-        if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
+    for (int m = 0; m < PPT; ++m) {
+        if (DENSE) pw += (mask & (1u << m)) ? cabs2(v[m]) : 0.f;
+        else if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
+    }
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
@@ -597,9 +615,45 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     float *lp = (staged ? ls : llr_out + row * P.ndb * BPS) + D.map.base_p * BPS;
     float *ln = (staged ? ls : llr_out + row * P.ndb * BPS) + (D.map.base_n - (PPT / 2) * T) * BPS;
     uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - (PPT / 2) * T);
+    // CH bins at a time: the chunk is skipped when no lane of the warp uses any of its bins (a warp-uniform vote, so no
+    // divergence), otherwise all CH bins are computed branch-free and only the stores are predicated.  CH = PPT is the
+    // fully dense form; CH = 0 keeps the per-lane branches of the loop further down.
+    constexpr int CH = DENSE ? PPT : OFDM_EPI_CHUNK_SPARSE;
+    if (CH > 0) {
+#pragma unroll
+        for (int c = 0; c < PPT; c += (CH > 0 ? CH : PPT)) {
+            if (CH == PPT || __any_sync(0xffffffffu, ((mask >> c) & ((1u << CH) - 1u)) != 0u)) {
+#pragma unroll
+                for (int m = c; m < c + CH; ++m) {
+                    const bool used = (mask & (1u << m)) != 0;
+                    const float2 z = cscale(cmul(G.get(m), v[m]), p0);
+                    if (used) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
+                    float Lb[BPS];
+                    unsigned bits;
+                    D.dem.run(z, Lb, bits);
+                    float *q = (m < PPT / 2 ? lp : ln) + m * T * BPS;
+                    if (used && soft) {
+                        if (BPS == 1) {
+                            st_out<CS>(q, Lb[0]);
+                        } else if (BPS == 4) {
+                            st_out<CS>(reinterpret_cast<float4 *>(q), make_float4(Lb[0], Lb[1], Lb[2], Lb[3]));
+                        } else if (staged) {
+#pragma unroll
+                            for (int b = 0; b + 1 < BPS; b += 2) *reinterpret_cast<float2 *>(q + b) = make_float2(Lb[b], Lb[b + 1]);
+                        } else {
+#pragma unroll
+                            for (int b = 0; b + 1 < BPS; b += 2)
+                                st_out<CS>(reinterpret_cast<float2 *>(q + b), make_float2(Lb[b], Lb[b + 1]));
+                        }
+                    }
+                    if (used && hard) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
-        if (mask & (1u << m)) {
+        if (CH == 0 && (mask & (1u << m))) {
             const float2 z = cscale(cmul(G.get(m), v[m]), p0);
             st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
             if (soft || hard) {
@@ -658,9 +712,38 @@ __device__ __forceinline__ void data_epilogue_bulk(const DevParams &P, const Dat
     float2 *eqp = es + D.map.base_p, *eqn = es + (D.map.base_n - (PPT / 2) * T);
     float *lp = ls + D.map.base_p * BPS, *ln = ls + (D.map.base_n - (PPT / 2) * T) * BPS;
     uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - (PPT / 2) * T);
+    constexpr int CH = OFDM_EPI_CHUNK_BULK;                 // as in data_epilogue
+    if (CH > 0) {
+#pragma unroll
+        for (int c = 0; c < PPT; c += (CH > 0 ? CH : PPT)) {
+            if (CH == PPT || __any_sync(0xffffffffu, ((mask >> c) & ((1u << CH) - 1u)) != 0u)) {
+#pragma unroll
+                for (int m = c; m < c + CH; ++m) {
+                    const bool used = (mask & (1u << m)) != 0;
+                    const float2 z = cscale(cmul(G.get(m), v[m]), p0);
+                    if (used) (m < PPT / 2 ? eqp : eqn)[m * T] = z;
+                    float Lb[BPS];
+                    unsigned bits;
+                    D.dem.run(z, Lb, bits);
+                    float *q = (m < PPT / 2 ? lp : ln) + m * T * BPS;
+                    if (used && soft) {
+                        if (BPS == 1) {
+                            *q = Lb[0];
+                        } else if (BPS == 4) {
+                            *reinterpret_cast<float4 *>(q) = make_float4(Lb[0], Lb[1], Lb[2], Lb[3]);
+                        } else {
+#pragma unroll
+                            for (int b = 0; b + 1 < BPS; b += 2) *reinterpret_cast<float2 *>(q + b) = make_float2(Lb[b], Lb[b + 1]);
+                        }
+                    }
+                    if (used && hard) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
-        if (mask & (1u << m)) {
+        if (CH == 0 && (mask & (1u << m))) {
             const float2 z = cscale(cmul(G.get(m), v[m]), p0);
             (m < PPT / 2 ? eqp : eqn)[m * T] = z;
             if (soft || hard) {
@@ -824,7 +907,10 @@ template <class C, bool GSM> struct MinBlocksRxF {
 // preamble is then evaluated once per hypothesis (window re-read through L1/L2, de-rotated, transformed,
 // correlated), the hypothesis with the largest peak wins (first on ties) and its phasor row multiplies every
 // data window of the frame before the FFT.
-template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO, bool BULK = false>
+// EPI selects the data-symbol epilogue: EPI_SPARSE per-lane stores with unused bins skipped, EPI_BULK rows through the
+// async proxy (data_epilogue_bulk), EPI_DENSE per-lane stores with branch-free arithmetic (data_epilogue, DENSE).
+enum { EPI_SPARSE = 0, EPI_BULK = 1, EPI_DENSE = 2 };
+template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO, int EPI = EPI_SPARSE>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
@@ -957,19 +1043,19 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
             } else if (PIL) {
                 data_epilogue_pilot<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, hp, j, gid, eq_out,
                                                         llr_out, hard_out);
-            } else if (BULK) {
+            } else if (EPI == EPI_BULK) {
                 data_epilogue_bulk<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, es, j, gid, eq_out,
                                                        llr_out, hard_out);
             } else {
-                data_epilogue<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, j, gid, eq_out, llr_out,
-                                                  hard_out);
+                data_epilogue<C, BPS, GROUPS, GSM, EPI == EPI_DENSE>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, j, gid,
+                                                                     eq_out, llr_out, hard_out);
             }
         }
         f = fn;
         pos = npos;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (BULK && j == 0) bulk_wait_all();             // the last rows must have left shared memory before the CTA retires
+    if (EPI == EPI_BULK && j == 0) bulk_wait_all();             // the last rows must have left shared memory before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1152,6 +1238,9 @@ __device__ __forceinline__ unsigned ld_word_guarded(const uint8_t *__restrict__ 
     return w;
 }
 
+#ifndef OFDM_TX_LUT32
+#define OFDM_TX_LUT32 1                   // B200: +2 % at N=64, +2.5 % at N=2048 (0 = float2 entries)
+#endif
 #ifndef OFDM_TX_TWREG_MAX_LOG2N
 #define OFDM_TX_TWREG_MAX_LOG2N 7      // B200: +3 % at N=64, +1.5 % at N=128, nothing from N=256 on
 #endif
@@ -1168,8 +1257,29 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     // (bank-private copies of the table were tried: the 2-way conflicts of random lookups cost less than the
     // larger table's index arithmetic -- 2-3 % slower at every size, B200)
     float2 *lut = S::lut(smem_raw);
-    for (int i = tid; i <= ZERO; i += S::THREADS) lut[i] = i < (1 << BPS) ? map_bits<BPS>((unsigned)i) : make_float2(0.f, 0.f);
+    // LUT32: entries are the integer levels (+-1, +-3, ..) as two halves -- 4 bytes per lookup instead of 8, so a warp's
+    // lookup is one shared-memory wavefront less.  The levels are exact in fp16 and the common amplitude cancels in the
+    // symbol's power normalisation; only the comb-pilot variant, whose pilots come at true scale, multiplies it back.
+    constexpr bool LUT32 = OFDM_TX_LUT32 != 0;
+    constexpr float AMP = BPS == 1 ? 1.f : (BPS == 2 ? 0.70710678118654752440f
+                                                     : (BPS == 4 ? 0.31622776601683793320f : 0.15430334996209191026f));
+    unsigned *lut32 = reinterpret_cast<unsigned *>(lut);
+    for (int i = tid; i <= ZERO; i += S::THREADS) {
+        const float2 c = i < (1 << BPS) ? map_bits<BPS>((unsigned)i) : make_float2(0.f, 0.f);
+        if (LUT32) {
+            const __half2 h = __floats2half2_rn(rintf(c.x / AMP), rintf(c.y / AMP));
+            lut32[i] = *reinterpret_cast<const unsigned *>(&h);
+        } else {
+            lut[i] = c;
+        }
+    }
     __syncthreads();
+    auto look = [&](unsigned idx) -> float2 {
+        if (!LUT32) return lut[idx];
+        const unsigned e = lut32[idx];
+        const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&e));
+        return PIL ? cscale(c, AMP) : c;
+    };
     // the last pass' twiddles live in registers where the transmitter has them to spare (N <= OFDM_TX_TWREG_MAX_LOG2N)
     constexpr bool TWR = C::LOG2N <= OFDM_TX_TWREG_MAX_LOG2N && !C::CH;
     float2 twreg[LastPassTw<C>::COUNT];
@@ -1241,7 +1351,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                     unsigned w = (unsigned)q[0] << 8;
                     if (BPS == 6) w |= (unsigned)q[1];
                     const unsigned val = (w >> (16 - (bo & 7) - BPS)) & ((1u << BPS) - 1u);
-                    v[m] = !used ? make_float2(0.f, 0.f) : (pq.is_pilot ? __ldg(P.pilot_tx + j + m * T) : lut[val]);
+                    v[m] = !used ? make_float2(0.f, 0.f) : (pq.is_pilot ? __ldg(P.pilot_tx + j + m * T) : look(val));
                 }
             } else {
 #pragma unroll
@@ -1252,7 +1362,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                     unsigned w = (unsigned)q[0] << 8;
                     if (BPS == 6) w |= (unsigned)q[1];
                     const unsigned val = (w >> (m < PPT / 2 ? shp : shn)) & ((1u << BPS) - 1u);
-                    v[m] = lut[(map.mask & (1u << m)) ? val : ZERO];
+                    v[m] = look((map.mask & (1u << m)) ? val : ZERO);
                 }
             }
             if (s < P.m0) {

@@ -72,9 +72,9 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     constexpr bool GSM = RxFOpts<LOG2N>::GSM, SB = RxFOpts<LOG2N>::SB;
     if (n_frames <= 0) return cudaSuccess;
     if (P.pil_k && P.n_cfo) return cudaErrorInvalidValue;       // the hypothesis bank is not combined with comb pilots
-#define OFDM_LAUNCH_RXF(PIL, CFO, BULK, Q)                                                                           \
+#define OFDM_LAUNCH_RXF(PIL, CFO, EPI, Q)                                                                            \
     {                                                                                                                \
-        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO, BULK>;                                     \
+        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO, EPI>;                                      \
         int SM = Smem<C, G, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : G * (Q.ls_stride * 4 + Q.es_stride * 8));       \
         cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);                                                 \
         if (e != cudaSuccess) return e;                                                                              \
@@ -88,10 +88,11 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     if (P.bulk_rows && !(P.bps == 6 && LOG2N <= 6)) Qp.ls_stride = 0;
     const bool bulk_ok = P.bulk_rows && !P.pil_k && !P.n_cfo && ((reinterpret_cast<unsigned long long>(eq) & 15ull) == 0) &&
                          ((reinterpret_cast<unsigned long long>(llr) & 15ull) == 0);
+    const bool dense = (long long)P.ndb * 64 >= (long long)OFDM_DENSE_MIN_FILL64 * C::N;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
-        if (P.pil_k) OFDM_LAUNCH_RXF(true, false, false, Qp)
-        else if (P.n_cfo) OFDM_LAUNCH_RXF(false, true, false, Qp)
+        if (P.pil_k) OFDM_LAUNCH_RXF(true, false, EPI_SPARSE, Qp)
+        else if (P.n_cfo) OFDM_LAUNCH_RXF(false, true, EPI_SPARSE, Qp)
         else {
             bool bulk = false;
             if constexpr (BPS == 6) {
@@ -99,14 +100,16 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
                     LaunchDims db, dp;
                     int smb = Smem<C, G, false, false, GSM, SB>::BYTES + G * (P.ls_stride * 4 + P.es_stride * 8);
                     int smp = Smem<C, G, false, false, GSM, SB>::BYTES + G * Qp.ls_stride * 4;
-                    const cudaError_t eb = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, true>>(TH, smb, G, n_frames, sms, db);
-                    const cudaError_t ep = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, false>>(TH, smp, G, n_frames, sms, dp);
+                    const cudaError_t eb = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, EPI_BULK>>(TH, smb, G, n_frames, sms, db);
+                    const cudaError_t ep = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, EPI_SPARSE>>(TH, smp, G, n_frames, sms, dp);
                     if (eb != cudaSuccess) cudaGetLastError();              // rows do not fit next to the transform: not an error
                     bulk = eb == cudaSuccess && ep == cudaSuccess && db.ctas_per_sm >= dp.ctas_per_sm;
                 }
-                if (bulk) OFDM_LAUNCH_RXF(false, false, true, P)
+                if (bulk) OFDM_LAUNCH_RXF(false, false, EPI_BULK, P)
             }
-            if (!bulk) OFDM_LAUNCH_RXF(false, false, false, Qp)
+            // densely filled grids take the branch-free epilogue (same shared-memory footprint as the sparse one)
+            if (!bulk && dense) OFDM_LAUNCH_RXF(false, false, EPI_DENSE, Qp)
+            else if (!bulk) OFDM_LAUNCH_RXF(false, false, EPI_SPARSE, Qp)
         }
         count_launch();
     })

@@ -86,6 +86,14 @@ if __name__ == "__main__":
     if which in ("all", "lte"):
         run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
                                      bps=6, snr=100, noise_var=0.01), 4096)
+    if which in ("ltex",):                                  # LTE grid (59 % of the bins used) on the per-lane epilogues
+        for bps, nm in ((2, "qpsk"), (4, "16qam")):
+            run("LTE_" + nm, ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
+                                         bps=bps, snr=100, noise_var=0.01), 4096)
+        run("N2048_16qam", ModemConfig(nfft=2048, cp_len=512, num_synch_bins=2046, num_data_bins=1920, m0=1, d=3,
+                                       bps=4, snr=100, noise_var=0.01), 6553)
+        run("N2048_qpsk", ModemConfig(nfft=2048, cp_len=512, num_synch_bins=2046, num_data_bins=1920, m0=1, d=3,
+                                      bps=2, snr=100, noise_var=0.01), 6553)
     if which in ("all", "sweep"):
         for n in (128, 256, 512, 1024, 4096):
             ndb = int(0.9375 * n) // 4 * 4
