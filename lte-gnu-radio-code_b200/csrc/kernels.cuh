@@ -422,7 +422,8 @@ template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = fal
     static constexpr int STAGE_BYTES = TXK ? 0 : OFDM_PF_DEPTH * THREADS * C::PPT * 8;   // symbols in flight: PPT samples per thread each (RX)
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
     static constexpr int PK_BYTES = TXK ? 0 : 3 * C::N / 4 + 16;                    // packed row staged for aligned stores
-    static constexpr int HB_STRIDE = C::N + 16 + PK_BYTES;                          // +16: zero pad, keeps 16-byte alignment
+    static constexpr int TX_ROW_BYTES = 3 * C::N / 4 + 16;                          // one packed payload row at any byte phase (TX)
+    static constexpr int HB_STRIDE = TXK ? 2 * TX_ROW_BYTES : C::N + 16 + PK_BYTES; // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
     static constexpr int LUT_BYTES = TXK ? 72 * 8 : 0;                              // constellation table (TX), entry 64 = 0
     static constexpr int HP_BYTES = (TXK || !PIL) ? 0 : GROUPS * (C::N / 2) * 8;    // per-symbol pilot estimates (RX, pilot mode)
@@ -1228,16 +1229,6 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
 // Both normalisations are scale factors derived from two sums over the L = N+CP output samples
 // (CP samples count twice), so the symbol is written to HBM once, already normalised.
 // ------------------------------------------------------------------------------------------------
-// aligned 32-bit word `w` of the byte string that starts at p (p 4-byte aligned); bytes at or past
-// `limit` (relative to p) read as zero so nothing outside the caller's buffer is touched
-__device__ __forceinline__ unsigned ld_word_guarded(const uint8_t *__restrict__ p, long long off, long long limit) {
-    if (off + 4 <= limit) return __ldg(reinterpret_cast<const unsigned *>(p + off));
-    unsigned w = 0;
-    for (int i = 0; i < 4; ++i)
-        if (off + i < limit) w |= (unsigned)__ldg(p + off + i) << (8 * i);
-    return w;
-}
-
 #ifndef OFDM_TX_LUT32
 #define OFDM_TX_LUT32 1                   // B200: +2 % at N=64, +2.5 % at N=2048 (0 = float2 entries)
 #endif
@@ -1250,7 +1241,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
           int iters) {
     OFDM_KERNEL_PROLOGUE_(GROUPS, true, false)
     constexpr int N = C::N;
-    constexpr int WPT = PPT / 4;                             // a payload row spans at most PPT/4 packed words per thread
+    constexpr int CPT = (3 * N / 4 + 14 + 8 * T - 1) / (8 * T);   // 8-byte chunks of a payload row per thread, at most
     constexpr int ZERO = 64;                                 // LUT entry that maps unused bins to 0
     const int L = N + P.cp, fs = P.m0 + P.d;
     // constellation table in shared memory: one LDS per bin instead of arithmetic on the bits
@@ -1295,52 +1286,73 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     for (int m = 0; m < PPT; ++m) cpmask |= (j + m * T >= N - P.cp) ? (1u << m) : 0u;
     const float sqrtL = sqrtf((float)L), invL = 1.f / (float)L;
     const float emin = 1e-30f * (float)N * (float)N;
-    // the payload buffer, viewed from its 4-byte-aligned base
-    const long long mis = (long long)(reinterpret_cast<unsigned long long>(bits) & 3ull);
+    // The payload buffer, viewed from its 4-byte-aligned base.  A symbol's packed row is copied word by word into one
+    // of the group's two row buffers with cp.async while the previous symbol is built: no registers and no scoreboard
+    // are held across the iteration (the register version stalled 12 % of the kernel on a false dependency between
+    // the staging store and the next row's loads), and the copy's src-size zero-fills the bytes past the caller's
+    // buffer, so nothing outside it is touched (8-byte chunks from the buffer's 8-byte-aligned base).
+    const long long mis = (long long)(reinterpret_cast<unsigned long long>(bits) & 7ull);
     const uint8_t *abits = bits - mis;
     const long long limit = mis + (n_sym_total / fs) * P.d * (long long)P.hard_stride;
-    const int nwords = (P.hard_stride + 3 + 3) / 4;          // words that can hold a row at any byte phase
-    // (frame, symbol-in-frame) of the group's work item, advanced without 64-bit divisions
-    const long long step_f = total_groups / fs;
-    const int step_s = (int)(total_groups - step_f * fs);
-    long long f = gg / fs;
-    int s = (int)(gg - f * fs);
-    const long long last = n_sym_total - 1, last_f = last / fs;
-    const int last_s = (int)(last - last_f * fs);
-    auto row_start = [&](long long ff, int ss) -> long long {   // byte offset of the symbol's payload row, or -1
-        return ss >= P.m0 ? mis + (ff * P.d + (ss - P.m0)) * (long long)P.hard_stride : -1;
+    const int nchunks = (P.hard_stride + 7 + 7) / 8;         // 8-byte chunks that can hold a row at any byte phase
+    constexpr int RB = S::TX_ROW_BYTES;
+    const unsigned hb_s = (unsigned)__cvta_generic_to_shared(hb);
+    // The group's work items are the symbols q = gg, gg + TG, ... (q counts symbols over all frames; items past the end
+    // repeat the last symbol).  Symbol type s = q mod fs, payload row offset r = mis + (q - (f+1)*m0) * hard_stride and
+    // the output offset are advanced incrementally: no 64-bit multiply or divide inside the loop.
+    const long long TG = total_groups, last = n_sym_total - 1;
+    const int step_s = (int)(TG % fs);
+    const long long dr = (long long)P.hard_stride * (TG - (TG / fs) * P.m0), dr_wrap = (long long)P.hard_stride * P.m0;
+    const long long dout = TG * L;
+    auto locate = [&](long long qq, int &ss, long long &rr) {
+        const long long ff = qq / fs;
+        ss = (int)(qq - ff * fs);
+        rr = mis + (qq - (ff + 1) * P.m0) * (long long)P.hard_stride;
     };
-    auto clampfs = [&](long long &ff, int &ss) {
-        if (ff > last_f || (ff == last_f && ss > last_s)) { ff = last_f; ss = last_s; }
-    };
-    auto fetch = [&](unsigned (&w)[WPT], long long r) {
+    int s_last;
+    long long r_last;
+    locate(last, s_last, r_last);
+    long long q = gg < last ? gg : last, r;
+    int s;
+    locate(q, s, r);
+    long long oo = q * L + P.cp + j;                          // first useful sample of the symbol in `out`
+    auto request = [&](long long r, int buf) {               // synch symbols (r < 0) carry no payload: nothing to copy
+        if (r >= 0) {
+            const long long base = r & ~7ll, left = limit - base;             // left > 0: the row starts inside the buffer
+            const int room = left < (1 << 30) ? (int)left : (1 << 30);          // bytes from the row's first chunk to the end
+            const uint8_t *src = abits + base;
+            const unsigned dst = hb_s + buf * RB + 8 * j;
 #pragma unroll
-        for (int i = 0; i < WPT; ++i)
-            w[i] = (r >= 0 && j + i * T < nwords) ? ld_word_guarded(abits, (r & ~3ll) + 4 * (j + i * T), limit) : 0u;
+            for (int i = 0; i < CPT; ++i) {
+                const int wo = 8 * (j + i * T);
+                if (wo < 8 * nchunks) {
+                    const int sz = min(max(room - wo, 0), 8);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8 * i * T),
+                                 "l"(src + (sz ? wo : 0)), "r"(sz) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    clampfs(f, s);
-    long long rcur = row_start(f, s);
-    unsigned wcur[WPT], wnxt[WPT];
-    fetch(wcur, rcur);
+    int cb = 0;
+    request(s >= P.m0 ? r : -1, 0);
     for (int it = 0; it < iters; ++it) {
-        // next work item and its payload words (in flight while this symbol is built)
-        long long fn = f + step_f;
+        // next work item; its payload row is requested as soon as the current one has landed
+        long long qn = q + TG, rn = r + dr, on = oo + dout;
         int sn = s + step_s;
-        if (sn >= fs) { sn -= fs; ++fn; }
-        clampfs(fn, sn);
-        const long long rnxt = row_start(fn, sn);
-        fetch(wnxt, rnxt);
+        if (sn >= fs) { sn -= fs; rn -= dr_wrap; }
+        if (qn > last) { qn = last; sn = s_last; rn = r_last; on = last * L + P.cp + j; }
         float2 v[C::PPT];
         {
-            // Stage the row's packed words, then every thread picks the bits of its own bins.  Groups that
-            // share a warp can be on different symbol types, so the barrier is executed unconditionally
-            // and synch symbols simply overwrite the (all-zero) result with their Zadoff-Chu bins.
-            unsigned *hw = reinterpret_cast<unsigned *>(hb);
-#pragma unroll
-            for (int i = 0; i < WPT; ++i)
-                if (j + i * T < nwords) hw[j + i * T] = wcur[i];
+            // Every thread picks the bits of its own bins from the staged row.  Groups that share a warp can be on
+            // different symbol types, so the barrier is executed unconditionally and synch symbols simply overwrite
+            // the result with their Zadoff-Chu bins.  The barrier also orders the previous symbol's reads of the
+            // other row buffer before the copies that refill it.
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             group_sync<T, GROUPS>(gid);
-            const uint8_t *rp = hb + (int)(rcur & 3);
+            request(sn >= P.m0 ? rn : -1, cb ^ 1);
+            const uint8_t *rp = hb + cb * RB + (int)(r & 7);
+            cb ^= 1;
             if (PIL) {
 #pragma unroll
                 for (int m = 0; m < PPT; ++m) {
@@ -1359,9 +1371,13 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                     // (skipping the fetch + lookup for guard bins was tried, per thread and per row with a branch on kernel
                     // parameters only: 4-19 % slower either way -- the straight-line form lets all loads issue together)
                     const uint8_t *q = rp + (m < PPT / 2 ? byp : byn) + m * (T * BPS / 8);
-                    unsigned w = (unsigned)q[0] << 8;
-                    if (BPS == 6) w |= (unsigned)q[1];
-                    const unsigned val = (w >> (m < PPT / 2 ? shp : shn)) & ((1u << BPS) - 1u);
+                    unsigned val;
+                    if (BPS == 6) {                              // a 6-bit field can straddle two bytes
+                        const unsigned w = ((unsigned)q[0] << 8) | (unsigned)q[1];
+                        val = (w >> (m < PPT / 2 ? shp : shn)) & 63u;
+                    } else {
+                        val = ((unsigned)q[0] >> ((m < PPT / 2 ? shp : shn) - 8)) & ((1u << BPS) - 1u);
+                    }
                     v[m] = look((map.mask & (1u << m)) ? val : ZERO);
                 }
             }
@@ -1387,7 +1403,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
         const float mx = s1 * acc.y * invL, my = s1 * acc.z * invL;
         const float var = s1 * s1 * acc.x * invL - (mx * mx + my * my);
         const float g = var > 0.f ? s1 * rsqrtf(var) : 0.f;
-        float2 *o = out + (f * fs + s) * L + P.cp + j;
+        float2 *o = out + oo;
         float2 *ocp = o - N;                                  // sample n >= N-CP is also output n - (N-CP)
 #pragma unroll
         for (int m = 0; m < PPT; ++m) {
@@ -1395,12 +1411,12 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             st_out(o + m * T, z);
             if (cpmask & (1u << m)) st_out(ocp + m * T, z);
         }
-        f = fn;
+        q = qn;
         s = sn;
-        rcur = rnxt;
-#pragma unroll
-        for (int i = 0; i < WPT; ++i) wcur[i] = wnxt[i];
+        r = rn;
+        oo = on;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace ofdm
