@@ -16,6 +16,7 @@
 //     holding registers.
 #pragma once
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "fft_core.cuh"
 
 namespace ofdm {
@@ -422,7 +423,8 @@ template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = fal
     static constexpr int STAGE_BYTES = TXK ? 0 : OFDM_PF_DEPTH * THREADS * C::PPT * 8;   // symbols in flight: PPT samples per thread each (RX)
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
     static constexpr int PK_BYTES = TXK ? 0 : 3 * C::N / 4 + 16;                    // packed row staged for aligned stores
-    static constexpr int TX_ROW_BYTES = 3 * C::N / 4 + 16;                          // one packed payload row at any byte phase (TX)
+    static constexpr int TX_ROW_BYTES = 3 * C::N / 4 + 16;                          // one packed payload row at any 16-byte phase (TX)
+    static_assert((3 * C::N / 4 + 30) / 16 <= C::T, "one 16-byte chunk per thread must cover a payload row");
     static constexpr int HB_STRIDE = TXK ? 2 * TX_ROW_BYTES : C::N + 16 + PK_BYTES; // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
     static constexpr int LUT_BYTES = TXK ? 72 * 8 : 0;                              // constellation table (TX), entry 64 = 0
@@ -437,6 +439,7 @@ template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = fal
     static constexpr int OFF_GS = OFF_HP + HP_BYTES;
     static constexpr int BYTES = OFF_GS + GS_BYTES;
     static_assert(BYTES % 16 == 0, "the dynamic tail (LLR row staging) needs 16-byte alignment");
+    static_assert(!TXK || (OFF_HB % 16 == 0 && HB_STRIDE % 16 == 0), "cp.async row buffers need 16-byte alignment");
     __device__ static float2 *buf0(unsigned char *s, int gid) { return reinterpret_cast<float2 *>(s) + gid * GSTRIDE; }
     __device__ static float2 *tws(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_TW); }
     // slot m of thread t: stage[m * THREADS + t] -> lanes hit consecutive 8-byte words
@@ -1241,7 +1244,6 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
           int iters) {
     OFDM_KERNEL_PROLOGUE_(GROUPS, true, false)
     constexpr int N = C::N;
-    constexpr int CPT = (3 * N / 4 + 14 + 8 * T - 1) / (8 * T);   // 8-byte chunks of a payload row per thread, at most
     constexpr int ZERO = 64;                                 // LUT entry that maps unused bins to 0
     const int L = N + P.cp, fs = P.m0 + P.d;
     // constellation table in shared memory: one LDS per bin instead of arithmetic on the bits
@@ -1281,20 +1283,20 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     const int bop = map.base_p * BPS, bon = (map.base_n - (PPT / 2) * T) * BPS;
     const int byp = bop >> 3, shp = 16 - (bop & 7) - BPS, byn = bon >> 3, shn = 16 - (bon & 7) - BPS;
     // this thread's samples n = j + m*T that also go into the cyclic prefix (n >= N - CP)
-    unsigned cpmask = 0;
-#pragma unroll
-    for (int m = 0; m < PPT; ++m) cpmask |= (j + m * T >= N - P.cp) ? (1u << m) : 0u;
+    // (tested as j >= ncp0 - m*T where it is needed: one compare against a uniform value per sample; a per-thread bit
+    // mask made the compiler keep sixteen flag registers and rebuild the mask every symbol)
+    const int ncp0 = N - P.cp;
     const float sqrtL = sqrtf((float)L), invL = 1.f / (float)L;
     const float emin = 1e-30f * (float)N * (float)N;
     // The payload buffer, viewed from its 4-byte-aligned base.  A symbol's packed row is copied word by word into one
     // of the group's two row buffers with cp.async while the previous symbol is built: no registers and no scoreboard
     // are held across the iteration (the register version stalled 12 % of the kernel on a false dependency between
     // the staging store and the next row's loads), and the copy's src-size zero-fills the bytes past the caller's
-    // buffer, so nothing outside it is touched (8-byte chunks from the buffer's 8-byte-aligned base).
-    const long long mis = (long long)(reinterpret_cast<unsigned long long>(bits) & 7ull);
+    // buffer, so nothing outside it is touched (16-byte chunks from the buffer's 16-byte-aligned base, one per thread).
+    const long long mis = (long long)(reinterpret_cast<unsigned long long>(bits) & 15ull);
     const uint8_t *abits = bits - mis;
     const long long limit = mis + (n_sym_total / fs) * P.d * (long long)P.hard_stride;
-    const int nchunks = (P.hard_stride + 7 + 7) / 8;         // 8-byte chunks that can hold a row at any byte phase
+    const int nchunks = (P.hard_stride + 15 + 15) / 16;      // 16-byte chunks that can hold a row at any byte phase (<= T)
     constexpr int RB = S::TX_ROW_BYTES;
     const unsigned hb_s = (unsigned)__cvta_generic_to_shared(hb);
     // The group's work items are the symbols q = gg, gg + TG, ... (q counts symbols over all frames; items past the end
@@ -1318,18 +1320,12 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     long long oo = q * L + P.cp + j;                          // first useful sample of the symbol in `out`
     auto request = [&](long long r, int buf) {               // synch symbols (r < 0) carry no payload: nothing to copy
         if (r >= 0) {
-            const long long base = r & ~7ll, left = limit - base;             // left > 0: the row starts inside the buffer
+            const long long base = r & ~15ll, left = limit - base;            // left > 0: the row starts inside the buffer
             const int room = left < (1 << 30) ? (int)left : (1 << 30);          // bytes from the row's first chunk to the end
-            const uint8_t *src = abits + base;
-            const unsigned dst = hb_s + buf * RB + 8 * j;
-#pragma unroll
-            for (int i = 0; i < CPT; ++i) {
-                const int wo = 8 * (j + i * T);
-                if (wo < 8 * nchunks) {
-                    const int sz = min(max(room - wo, 0), 8);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8 * i * T),
-                                 "l"(src + (sz ? wo : 0)), "r"(sz) : "memory");
-                }
+            if (j < nchunks) {                                                  // one chunk per thread covers any row
+                const int sz = min(max(room - 16 * j, 0), 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(hb_s + buf * RB + 16 * j),
+                             "l"(abits + base + (sz ? 16 * j : 0)), "r"(sz) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1351,7 +1347,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             group_sync<T, GROUPS>(gid);
             request(sn >= P.m0 ? rn : -1, cb ^ 1);
-            const uint8_t *rp = hb + cb * RB + (int)(r & 7);
+            const uint8_t *rp = hb + cb * RB + (int)(r & 15);
             cb ^= 1;
             if (PIL) {
 #pragma unroll
@@ -1388,29 +1384,43 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             }
         }
         fft_group<C, true, GROUPS, false, TWR>(v, tws, b0, b1, j, gid, pp, twreg);
-        float3 acc = make_float3(0.f, 0.f, 0.f);
+        // Power / mean sums with the CP samples counted twice, one scale, stores with the CP copy.  With CP <= N/4 (every
+        // numerology in use) only the last quarter of a thread's samples can repeat in the prefix, so the common case
+        // is compiled without the per-sample compare, weight select and predicated second store for the other three
+        // quarters; the branch is on a kernel parameter, hence uniform.
+        auto finish = [&](auto quarter) {
+            constexpr int MCP = decltype(quarter)::value ? 3 * PPT / 4 : 0;      // first m whose sample can be in the CP
+            float3 acc = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
-        for (int m = 0; m < PPT; ++m) {
-            const float w = (cpmask & (1u << m)) ? 2.f : 1.f;
-            acc.x = fmaf(w, cabs2(v[m]), acc.x);
-            acc.y = fmaf(w, v[m].x, acc.y);
-            acc.z = fmaf(w, v[m].y, acc.z);
-        }
-        acc = group_sum3<T, GROUPS>(acc, redf, j, gid);
-        // v holds N*ifft(X) = N*t.  Reference: t -> t*sqrt(L/sum|t|^2) -> /sqrt(var); with the first
-        // factor applied the mean power is 1, so var = 1 - |mean|^2 and both steps are one scale g.
-        const float s1 = acc.x > emin ? sqrtL * rsqrtf(acc.x) : 1.f / (float)N;
-        const float mx = s1 * acc.y * invL, my = s1 * acc.z * invL;
-        const float var = s1 * s1 * acc.x * invL - (mx * mx + my * my);
-        const float g = var > 0.f ? s1 * rsqrtf(var) : 0.f;
-        float2 *o = out + oo;
-        float2 *ocp = o - N;                                  // sample n >= N-CP is also output n - (N-CP)
+            for (int m = 0; m < PPT; ++m) {
+                if (m < MCP) {
+                    acc.x += cabs2(v[m]);
+                    acc.y += v[m].x;
+                    acc.z += v[m].y;
+                } else {
+                    const float w = (j >= ncp0 - m * T) ? 2.f : 1.f;
+                    acc.x = fmaf(w, cabs2(v[m]), acc.x);
+                    acc.y = fmaf(w, v[m].x, acc.y);
+                    acc.z = fmaf(w, v[m].y, acc.z);
+                }
+            }
+            acc = group_sum3<T, GROUPS>(acc, redf, j, gid);
+            // v holds N*ifft(X) = N*t.  Reference: t -> t*sqrt(L/sum|t|^2) -> /sqrt(var); with the first
+            // factor applied the mean power is 1, so var = 1 - |mean|^2 and both steps are one scale g.
+            const float s1 = acc.x > emin ? sqrtL * rsqrtf(acc.x) : 1.f / (float)N;
+            const float mx = s1 * acc.y * invL, my = s1 * acc.z * invL;
+            const float var = s1 * s1 * acc.x * invL - (mx * mx + my * my);
+            const float g = var > 0.f ? s1 * rsqrtf(var) : 0.f;
+            float2 *o = out + oo;
+            float2 *ocp = o - N;                              // sample n >= N-CP is also output n - (N-CP)
 #pragma unroll
-        for (int m = 0; m < PPT; ++m) {
-            const float2 z = cscale(v[m], g);
-            st_out(o + m * T, z);
-            if (cpmask & (1u << m)) st_out(ocp + m * T, z);
-        }
+            for (int m = 0; m < PPT; ++m) {
+                const float2 z = cscale(v[m], g);
+                st_out(o + m * T, z);
+                if (m >= MCP && j >= ncp0 - m * T) st_out(ocp + m * T, z);
+            }
+        };
+        if (4 * P.cp <= N) finish(std::true_type{}); else finish(std::false_type{});
         q = qn;
         s = sn;
         r = rn;
