@@ -11,7 +11,8 @@ Workloads (BASELINE.json configs):
   rx_n64_16qam_1m  (default, configs[1]) N=64, CP=16, 62 ZC bins, 60 data bins, frames of 1 synch + 3
                    data symbols, 16-QAM, 333 334 frames = 1 000 002 data symbols, reference 5-tap
                    channel + AWGN, per-frame ZC-preamble ("pilot") equalisation.
-  rx_lte20_64qam   (configs[2]) N=2048, CP=144, 2046 ZC bins, 1200 data bins, 1+13 symbols, 64-QAM,
+  rx_lte20_64qam   (configs[2]) N=2048, normal CP (160 samples on the first symbol of each 7-symbol slot, 144 on the
+                   others: 30 720 samples per 14-symbol frame), 2046 ZC bins, 1200 data bins, 1+13 symbols, 64-QAM,
                    4096 frames, an independent random 5-tap multipath channel per frame + AWGN.
   rx_lte20_streams (configs[3]) the same numerology as 4096 independent streams x 10 frames, the STREAMS
                    dealt round-robin over the ranks (strong scaling: the total is fixed).
@@ -35,10 +36,10 @@ sys.path.insert(0, os.path.join(ROOT, "lte-gnu-radio-code_b200", "python"))
 WORKLOADS = {
     "rx_n64_16qam_1m": dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4,
                             n_frames=333334, noise_sigma=0.02),
-    "rx_lte20_64qam": dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6,
-                           n_frames=4096, noise_sigma=0.0224, multipath=True),          # Es/N0 = 30 dB
-    "rx_lte20_streams": dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6,
-                             n_streams=4096, frames_per_stream=10, noise_sigma=0.0224, multipath=True),
+    "rx_lte20_64qam": dict(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200,
+                           m0=1, d=13, bps=6, n_frames=4096, noise_sigma=0.0224, multipath=True),   # Es/N0 = 30 dB
+    "rx_lte20_streams": dict(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200,
+                             m0=1, d=13, bps=6, n_streams=4096, frames_per_stream=10, noise_sigma=0.0224, multipath=True),
 }
 # power delay profile of the per-frame random channel, shaped after the reference taps (MultiAntennaSystem.py:64)
 MULTIPATH_PDP = np.array([0.16, 0.79, 0.04, 0.01, 0.002])
@@ -74,11 +75,19 @@ def profiled_traffic(workload):
     return None
 
 
+def frame_len(w):
+    """samples per frame: (M0+D) symbols of nfft + cp_len, plus the longer first prefix of every slot (CP pattern)"""
+    fs = w["m0"] + w["d"]
+    n = fs * (w["nfft"] + w["cp_len"])
+    if w.get("cp_first"):
+        n += (w["cp_first"] - w["cp_len"]) * ((fs + w["slot_syms"] - 1) // w["slot_syms"])
+    return n
+
+
 def algorithmic_bytes(w, fr):
     """Bytes one launch over `fr` frames must move: every input sample once, every output once."""
-    L = w["nfft"] + w["cp_len"]
     nsym = fr * w["d"]
-    read = fr * (w["m0"] + w["d"]) * L * 8
+    read = fr * frame_len(w) * 8
     hs = (w["num_data_bins"] * w["bps"] + 7) // 8
     write = nsym * w["num_data_bins"] * 8 + nsym * w["num_data_bins"] * w["bps"] * 4 + nsym * hs + fr * 9
     return read, write
@@ -139,7 +148,8 @@ def _cpu_chunk(args):
     from oracle import ofdm_oracle as oo
     w = WORKLOADS[wname]
     prm = oo.ModemParams(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
-                         num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100, gate=0.5)
+                         num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100, gate=0.5,
+                         cp_first=w.get("cp_first", 0), slot_syms=w.get("slot_syms", 0))
     rng = np.random.default_rng(seed)
     bits = rng.integers(0, 2, n_frames * w["d"] * w["num_data_bins"] * w["bps"])
     tx = oo.tx_modulate(bits, prm, n_frames)
@@ -159,7 +169,8 @@ def cpu_tx_rate(wname, target_seconds):
     from oracle import ofdm_oracle as oo
     w = WORKLOADS[wname]
     prm = oo.ModemParams(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
-                         num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100, gate=0.5)
+                         num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100, gate=0.5,
+                         cp_first=w.get("cp_first", 0), slot_syms=w.get("slot_syms", 0))
     rng = np.random.default_rng(5)
     nf, done, t_used = 4, 0, 0.0
     while t_used < target_seconds:
@@ -211,7 +222,7 @@ def run_reference(args, rank, world):
            "ms_per_step": 1e3 * info["seconds"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": wname, **{k: w[k] for k in ("nfft", "cp_len", "num_data_bins", "bps", "m0", "d")}},
-           "msamples_per_s": v * L * (w["m0"] + w["d"]) / w["d"] / 1e6,
+           "msamples_per_s": v * frame_len(w) / w["d"] / 1e6,
            "cpu_baseline": {"value": v, "unit": "symbols/s", "cores": info["cores"], "kind": "port",
                             "sample": "%d frames (%d data symbols) per step: literal NumPy restatement of the "
                                       "reference block arithmetic (dense diag matmuls kept), one process per core; "
@@ -237,7 +248,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     cfg = ModemConfig(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
                       num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100.0, gate=0.5,
-                      noise_var=2 * w["noise_sigma"] ** 2)
+                      noise_var=2 * w["noise_sigma"] ** 2, cp_first=w.get("cp_first", 0), slot_syms=w.get("slot_syms", 0))
     m = Modem(cfg)
     nf, nf_total, scaling = frames_for_rank(w, rank, world)
     nsym = nf * cfg.d
@@ -350,14 +361,15 @@ def run_ours(args, rank, world, local_rank):
         "metric": "rx_ofdm_data_symbols_per_s", "value": value, "unit": "symbols/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wname, "nfft": cfg.nfft, "cp_len": cfg.cp_len, "num_synch_bins": cfg.num_synch_bins,
+        "config": {"workload": wname, "nfft": cfg.nfft, "cp_len": cfg.cp_len,
+                   "cp_pattern": [cfg.cp_first, cfg.slot_syms] if cfg.cp_pattern else None, "num_synch_bins": cfg.num_synch_bins,
                    "num_data_bins": cfg.num_data_bins, "synch_dat": [cfg.m0, cfg.d], "bps": cfg.bps,
                    "frames_per_gpu": nf, "data_symbols_per_gpu": nsym, "frames_total": nf_total,
                    "channel": "independent random 5-tap multipath per frame + AWGN" if w.get("multipath")
                    else "reference 5-tap channel + AWGN", "outputs": "eq c64 + llr f32 + packed hard bits",
                    "cache": "inputs+outputs per step = %.2f GB per GPU, far larger than the 126 MB L2" % ((rd + wr) / 1e9),
                    "parallelism": "frames sharded by rank, no data-path collective"},
-        "msamples_per_s": value * L * cfg.frame_syms / cfg.d / 1e6,
+        "msamples_per_s": value * cfg.frame_len / cfg.d / 1e6,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": profiled_traffic(wname), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": rd + wr, "kernel": "rx_frames_kernel",

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OFDM_B200_ABI_VERSION 2
+#define OFDM_B200_ABI_VERSION 3
 
 enum {
     OFDM_OK = 0,
@@ -71,7 +71,17 @@ typedef struct ofdm_params {
     int32_t pilot_spacing;
     int32_t pilot_offset;
     int32_t pilot_root;
-    int32_t reserved[5];     /* must be zero */
+    /* LTE "normal CP" pattern (extension; the reference assumes one prefix length, rx_b_len = nfft + cp_len,
+     * GRR/gr-utsa_ofdm/python/SynchAndChanEst.py:79).  With cp_first > cp_len and slot_syms >= 1, symbol k of a frame
+     * carries a prefix of cp_first samples when k % slot_syms == 0 and of cp_len samples otherwise (TS 36.211 5.6:
+     * 160 / 144 samples at nfft 2048, 7 symbols per slot), each symbol is normalised over its own length, and
+     * ofdm_plan_frame_len() is the sum of the symbol lengths.  Requires m0 == 1; not combined with comb pilots or the
+     * frequency-offset bank.  The delay bank still spans
+     * 0..cp_len.  cp_first = 0 (or == cp_len) means a uniform prefix.  The symbol-list entry points
+     * (ofdm_rx_sync_search / chanest / demod) take explicit window positions and are unaffected. */
+    int32_t cp_first;
+    int32_t slot_syms;
+    int32_t reserved[3];     /* must be zero */
 } ofdm_params;
 
 typedef struct ofdm_plan ofdm_plan;
@@ -84,7 +94,7 @@ const char *ofdm_last_error(void);
 int ofdm_plan_create(const ofdm_params *params, ofdm_plan **plan_out);
 int ofdm_plan_destroy(ofdm_plan *plan);
 int ofdm_plan_hard_stride(const ofdm_plan *plan);          /* bytes of packed bits per data symbol */
-int ofdm_plan_frame_len(const ofdm_plan *plan);            /* (M0+D)*(nfft+cp_len) samples */
+int ofdm_plan_frame_len(const ofdm_plan *plan);            /* (M0+D)*(nfft+cp_len) samples (+ the longer prefixes of a CP pattern) */
 int ofdm_plan_payload_bins(const ofdm_plan *plan);         /* payload bins per data symbol */
 
 /* TX: bits -> QAM + Zadoff-Chu/resource-element insertion -> IFFT -> CP add -> power normalise.
@@ -120,7 +130,8 @@ int ofdm_rx_demod(ofdm_plan *plan, const float *d_time, int64_t n_samples, const
 
 /* RX framed mode (throughput path): loop A body once per frame at the nominal position plus
  * loop B for the frame's D data symbols, fused in one kernel -- the channel estimate never
- * leaves the SM.  Frame f's synch window opens at first + f*frame_stride + cp_len - sync_advance.
+ * leaves the SM.  Frame f's synch window opens at first + f*frame_stride + cp_len - sync_advance
+ * (cp_first instead of cp_len with a CP pattern).
  * Outputs per frame: d_delay, d_peak, d_locked (peak > gate*M0*nsb); d_H nullable (nfft per frame).
  * Per data symbol (n_frames*D rows): d_eq, d_llr (nullable), d_hard (nullable). */
 int ofdm_rx_frames(ofdm_plan *plan, const float *d_time, int64_t n_samples, int64_t first,

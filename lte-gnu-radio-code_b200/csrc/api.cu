@@ -269,8 +269,11 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     if (p->m0 < 1 || p->m0 > 16 || p->d < 0) return fail(OFDM_EINVAL, "synch_dat out of range%s");
     if (p->bps != 1 && p->bps != 2 && p->bps != 4 && p->bps != 6) return fail(OFDM_EINVAL, "bps must be 1, 2, 4 or 6%s");
     if (p->sync_advance < 0 || p->sync_advance > p->cp_len) return fail(OFDM_EINVAL, "sync_advance must be in 0..cp_len%s");
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 3; ++i)
         if (p->reserved[i] != 0) return fail(OFDM_EINVAL, "reserved fields must be zero%s");
+    const bool cp_pattern = p->cp_first != 0 && p->cp_first != p->cp_len;
+    if (cp_pattern && (p->cp_first < p->cp_len || p->cp_first >= N || p->slot_syms < 1 || p->m0 != 1 || p->pilot_spacing))
+        return fail(OFDM_EINVAL, "CP pattern needs cp_len < cp_first < nfft, slot_syms >= 1, m0 == 1 and no comb pilots%s");
     if (p->pilot_spacing < 0 || p->pilot_spacing == 1 || p->pilot_spacing > p->num_data_bins / 2)
         return fail(OFDM_EINVAL, "pilot_spacing must be 0 or in 2..num_data_bins/2%s");
     if (p->pilot_spacing && (p->pilot_offset < 0 || p->pilot_offset >= p->pilot_spacing))
@@ -383,6 +386,8 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     }
     D.nfft = N;
     D.cp = p->cp_len;
+    D.cp_extra = cp_pattern ? p->cp_first - p->cp_len : 0;
+    D.slot = cp_pattern ? p->slot_syms : 0x7fffffff;           // a slot that never ends: the uniform prefix
     D.nsb = nsb;
     D.ndb = p->num_data_bins;
     D.m0 = m0;
@@ -452,7 +457,11 @@ int ofdm_plan_destroy(ofdm_plan *pl) {
 int ofdm_plan_hard_stride(const ofdm_plan *pl) { return pl ? pl->dev.hard_stride : OFDM_EINVAL; }
 int ofdm_plan_payload_bins(const ofdm_plan *pl) { return pl ? pl->dev.ndd : OFDM_EINVAL; }
 int ofdm_plan_frame_len(const ofdm_plan *pl) {
-    return pl ? (pl->prm.m0 + pl->prm.d) * (pl->prm.nfft + pl->prm.cp_len) : OFDM_EINVAL;
+    if (!pl) return OFDM_EINVAL;
+    const int fs = pl->prm.m0 + pl->prm.d;
+    int n = fs * (pl->prm.nfft + pl->prm.cp_len);
+    if (pl->dev.cp_extra) n += pl->dev.cp_extra * ((fs + pl->dev.slot - 1) / pl->dev.slot);   // one longer prefix per slot
+    return n;
 }
 
 int ofdm_tx_modulate(ofdm_plan *pl, const uint8_t *d_bits, float *d_time, int64_t n_frames, void *stream) {
@@ -467,6 +476,7 @@ int ofdm_plan_set_cfo_bank(ofdm_plan *pl, const double *cycles_per_sample, int32
     if (!pl || n_hyp < 0 || n_hyp > 64 || (n_hyp > 0 && !cycles_per_sample))
         return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: bad argument (0..64 hypotheses)%s");
     if (n_hyp > 0 && pl->prm.pilot_spacing) return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: not available with comb pilots%s");
+    if (n_hyp > 0 && pl->dev.cp_extra) return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: not available with a CP pattern%s");
     if (pl->d_cfo) cudaFree(pl->d_cfo);
     if (pl->small) cudaFree(pl->small);
     pl->d_cfo = nullptr;
@@ -658,7 +668,7 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
     int rc = ensure_streams(pl);
     if (rc) return rc;
     const ofdm_params &p = pl->prm;
-    const int64_t L = p.nfft + p.cp_len, fl = (int64_t)(p.m0 + p.d) * L;
+    const int64_t fl = ofdm_plan_frame_len(pl), cpmax = p.cp_len + pl->dev.cp_extra;
     const int64_t ndb = pl->dev.ndd, hs = pl->dev.hard_stride;
     // Chunk schedule: the link back to the host is the bottleneck (D2H bytes > H2D bytes).  The first chunk is small
     // so that the first D2H starts early, and chunks then grow by 1.5x (slower than the D2H : H2D byte ratio, so the
@@ -673,7 +683,7 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
     };
     const int64_t per_big = frames_for(big_mb), per_first = frames_for(first_mb < big_mb ? first_mb : big_mb);
     const int64_t per = per_big;
-    const size_t b_in = al256((size_t)((per - 1) * frame_stride + fl + 2 * p.cp_len) * 8);
+    const size_t b_in = al256((size_t)((per - 1) * frame_stride + fl + 2 * cpmax) * 8);
     const size_t b_eq = al256(per * p.d * ndb * 8), b_ll = al256(per * p.d * ndb * p.bps * 4), b_hd = al256(per * p.d * hs);
     const size_t tot = b_in + b_eq + b_ll + b_hd;
     for (int s = 0; s < ofdm_plan::NSLOT; ++s) {
@@ -707,7 +717,7 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
         // samples needed by this chunk: [lo, hi)
         int64_t lo = first + f0 * frame_stride - p.sync_advance;
         if (lo < 0) lo = 0;
-        int64_t hi = first + (f0 + nf - 1) * frame_stride + fl + p.cp_len;
+        int64_t hi = first + (f0 + nf - 1) * frame_stride + fl + cpmax;
         if (hi > n_samples) hi = n_samples;
         if (hi < lo) hi = lo;
         CU(cudaMemcpyAsync(din, h_time + 2 * lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, st), "H2D");

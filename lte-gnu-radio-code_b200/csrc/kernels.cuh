@@ -23,6 +23,9 @@ namespace ofdm {
 
 struct DevParams {
     int nfft, cp, nsb, ndb, m0, d, bps, mm;
+    // CP pattern (extension): symbols k % slot == 0 of a frame carry cp + cp_extra prefix samples; cp_extra = 0 and
+    // slot = INT_MAX for the reference's uniform prefix, so the counters below never fire
+    int cp_extra, slot;
     int sync_advance, hard_stride, dup_bin, equalizer;
     float gate_thresh;        // gate * M0*nsb
     float chanest_scale;      // 1 / ((1 + inv_reg_chanest) * M0)
@@ -914,7 +917,9 @@ template <class C, bool GSM> struct MinBlocksRxF {
 // EPI selects the data-symbol epilogue: EPI_SPARSE per-lane stores with unused bins skipped, EPI_BULK rows through the
 // async proxy (data_epilogue_bulk), EPI_DENSE per-lane stores with branch-free arithmetic (data_epilogue, DENSE).
 enum { EPI_SPARSE = 0, EPI_BULK = 1, EPI_DENSE = 2 };
-template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO, int EPI = EPI_SPARSE>
+// CPP: the plan has a CP pattern (DevParams::cp_extra); instantiated without comb pilots and hypothesis bank only, so
+// that the reference's uniform prefix pays nothing for it.
+template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO, int EPI = EPI_SPARSE, bool CPP = false>
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
@@ -928,20 +933,27 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
     Gains<C, GSM> G;
     G.s = S::gs(smem_raw, gid) + j;
     const long long last_frame = n_frames - 1;
-    const long long off0 = first + P.cp - P.sync_advance;
+    const long long off0 = first + P.cp + (CPP ? P.cp_extra : 0) - P.sync_advance;   // symbol 0 opens a slot: the longer prefix
     long long f = gg < last_frame ? gg : last_frame;
     long long pos = off0 + f * frame_stride;
     // request cursor: runs OFDM_PF_DEPTH symbols ahead of the symbol being processed, through the same
     // (frame, symbol) sequence; frames past the end of the list repeat the last one (valid windows)
     constexpr int DEPTH = OFDM_PF_DEPTH, SLOT = S::THREADS * PPT;
+    // Window of symbol s relative to the frame's first window: s*L, plus cp_extra for every slot boundary crossed (CP
+    // pattern).  Kept as running offsets (wo: symbol in hand, pf_wo: request cursor) with a position-in-slot counter.
     long long pf_pos = pos;
-    int pf_s = 0, pf_it = 0, pf_slot = 0, slot = 0;
+    int pf_s = 0, pf_it = 0, pf_slot = 0, slot = 0, pf_wo = 0, pf_k = 0;
     (void)slot;
     auto request = [&]() {
-        prefetch_pts<T, PPT, S::THREADS>(stage + pf_slot * SLOT, x, pf_pos + (long long)pf_s * L, n_samples, j, tid);
+        prefetch_pts<T, PPT, S::THREADS>(stage + pf_slot * SLOT, x, pf_pos + (CPP ? (long long)pf_wo : (long long)pf_s * L),
+                                         n_samples, j, tid);
         pf_slot = pf_slot + 1 == DEPTH ? 0 : pf_slot + 1;
+        if (CPP) {
+            pf_wo += L;
+            if (++pf_k == P.slot) { pf_k = 0; pf_wo += P.cp_extra; }
+        }
         if (++pf_s == fs) {
-            pf_s = 0;
+            pf_s = pf_wo = pf_k = 0;
             long long fq = gg + (long long)(++pf_it) * total_groups;
             fq = fq < last_frame ? fq : last_frame;
             pf_pos = off0 + fq * frame_stride;
@@ -963,19 +975,27 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
 #pragma unroll
         for (int m = 0; m < PPT; ++m) ys[m] = make_float2(0.f, 0.f);
         ydup[0] = ydup[1] = make_float2(0.f, 0.f);
+        int wo = 0, kslot = 0;
+        (void)kslot;
         for (int s = 0; s < fs; ++s) {
             float2 cur[C::PPT];
+            const long long wcur = CPP ? (long long)wo : (long long)s * L;
+            if (CPP) {
+                wo += L;
+                if (++kslot == P.slot) { kslot = 0; wo += P.cp_extra; }
+            }
             if constexpr (DEPTH == 1) {
                 take_pts<PPT, S::THREADS>(cur, stage, tid);
                 // request the next symbol (the last request of the kernel re-reads a valid window)
-                prefetch_pts<T, PPT, S::THREADS>(stage, x, (s + 1 < fs) ? pos + (long long)(s + 1) * L : npos, n_samples, j, tid);
+                prefetch_pts<T, PPT, S::THREADS>(stage, x, (s + 1 < fs) ? pos + (CPP ? (long long)wo : (long long)(s + 1) * L) : npos,
+                                                 n_samples, j, tid);
             } else {
                 take_pts<PPT, S::THREADS, DEPTH - 1>(cur, stage + slot * SLOT, tid);
                 slot = slot + 1 == DEPTH ? 0 : slot + 1;
                 request();                               // refills the slot just emptied
             }
             if (!CFO || s >= P.m0) {                 // with a CFO bank the preamble is transformed per hypothesis below
-                if (CFO) rotate_pts<T, PPT>(P, cur, hyp, pos + (long long)s * L, j);
+                if (CFO) rotate_pts<T, PPT>(P, cur, hyp, pos + wcur, j);
                 fft_group<C, false, GROUPS, SB>(cur, tws, b0, b1, j, gid, pp);
             }
             if (s < P.m0) {
@@ -1238,7 +1258,7 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
 #ifndef OFDM_TX_TWREG_MAX_LOG2N
 #define OFDM_TX_TWREG_MAX_LOG2N 7      // B200: +3 % at N=64, +1.5 % at N=128, nothing from N=256 on
 #endif
-template <class C, int BPS, int GROUPS, bool PIL>
+template <class C, int BPS, int GROUPS, bool PIL, bool CPP = false>      // CPP: CP pattern, see rx_frames_kernel
 __global__ void __launch_bounds__(C::T *GROUPS, MinBlocksTx<C>::value)
 tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restrict__ out, long long n_sym_total,
           int iters) {
@@ -1285,8 +1305,10 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     // this thread's samples n = j + m*T that also go into the cyclic prefix (n >= N - CP)
     // (tested as j >= ncp0 - m*T where it is needed: one compare against a uniform value per sample; a per-thread bit
     // mask made the compiler keep sixteen flag registers and rebuild the mask every symbol)
-    const int ncp0 = N - P.cp;
-    const float sqrtL = sqrtf((float)L), invL = 1.f / (float)L;
+    // symbol length entering the two normalisations: N + cp, or N + cp + cp_extra for the first symbol of a slot
+    const float sqrtL0 = sqrtf((float)L), invL0 = 1.f / (float)L;
+    const float sqrtL1 = sqrtf((float)(L + P.cp_extra)), invL1 = 1.f / (float)(L + P.cp_extra);
+    (void)sqrtL1; (void)invL1;
     const float emin = 1e-30f * (float)N * (float)N;
     // The payload buffer, viewed from its 4-byte-aligned base.  A symbol's packed row is copied word by word into one
     // of the group's two row buffers with cp.async while the previous symbol is built: no registers and no scoreboard
@@ -1317,7 +1339,11 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     long long q = gg < last ? gg : last, r;
     int s;
     locate(q, s, r);
-    long long oo = q * L + P.cp + j;                          // first useful sample of the symbol in `out`
+    long long oo = q * L + P.cp + j;                          // first useful sample of the symbol in `out` (uniform prefix)
+    // CP pattern: the frame index is needed as well (every slot before the symbol shifts it by cp_extra samples)
+    const long long step_f = CPP ? TG / fs : 0, f_last = CPP ? last / fs : 0;
+    long long f = CPP ? q / fs : 0;
+    const int nslots = CPP ? (fs + P.slot - 1) / P.slot : 0;
     auto request = [&](long long r, int buf) {               // synch symbols (r < 0) carry no payload: nothing to copy
         if (r >= 0) {
             const long long base = r & ~15ll, left = limit - base;            // left > 0: the row starts inside the buffer
@@ -1334,10 +1360,19 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
     request(s >= P.m0 ? r : -1, 0);
     for (int it = 0; it < iters; ++it) {
         // next work item; its payload row is requested as soon as the current one has landed
-        long long qn = q + TG, rn = r + dr, on = oo + dout;
+        long long qn = q + TG, rn = r + dr, on = oo + dout, fn = f + step_f;
         int sn = s + step_s;
-        if (sn >= fs) { sn -= fs; rn -= dr_wrap; }
-        if (qn > last) { qn = last; sn = s_last; rn = r_last; on = last * L + P.cp + j; }
+        if (sn >= fs) { sn -= fs; rn -= dr_wrap; if (CPP) ++fn; }
+        if (qn > last) { qn = last; sn = s_last; rn = r_last; on = last * L + P.cp + j; fn = f_last; }
+        // this symbol's prefix length and its extra displacement under a CP pattern
+        int ncp0 = N - P.cp;
+        long long xo = 0;
+        float sqrtL = sqrtL0, invL = invL0;
+        if (CPP) {
+            const int sl = s / P.slot;
+            xo = (long long)P.cp_extra * (f * nslots + sl + 1);
+            if (s == sl * P.slot) { ncp0 -= P.cp_extra; sqrtL = sqrtL1; invL = invL1; }
+        }
         float2 v[C::PPT];
         {
             // Every thread picks the bits of its own bins from the staged row.  Groups that share a warp can be on
@@ -1411,7 +1446,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             const float mx = s1 * acc.y * invL, my = s1 * acc.z * invL;
             const float var = s1 * s1 * acc.x * invL - (mx * mx + my * my);
             const float g = var > 0.f ? s1 * rsqrtf(var) : 0.f;
-            float2 *o = out + oo;
+            float2 *o = out + oo + xo;
             float2 *ocp = o - N;                              // sample n >= N-CP is also output n - (N-CP)
 #pragma unroll
             for (int m = 0; m < PPT; ++m) {
@@ -1420,11 +1455,12 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                 if (m >= MCP && j >= ncp0 - m * T) st_out(ocp + m * T, z);
             }
         };
-        if (4 * P.cp <= N) finish(std::true_type{}); else finish(std::false_type{});
+        if (4 * (P.cp + (CPP ? P.cp_extra : 0)) <= N) finish(std::true_type{}); else finish(std::false_type{});
         q = qn;
         s = sn;
         r = rn;
         oo = on;
+        f = fn;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }

@@ -72,9 +72,10 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     constexpr bool GSM = RxFOpts<LOG2N>::GSM, SB = RxFOpts<LOG2N>::SB;
     if (n_frames <= 0) return cudaSuccess;
     if (P.pil_k && P.n_cfo) return cudaErrorInvalidValue;       // the hypothesis bank is not combined with comb pilots
-#define OFDM_LAUNCH_RXF(PIL, CFO, EPI, Q)                                                                            \
+#define OFDM_LAUNCH_RXF(PIL, CFO, EPI, Q) OFDM_LAUNCH_RXF_(PIL, CFO, EPI, false, Q)
+#define OFDM_LAUNCH_RXF_(PIL, CFO, EPI, CPP, Q)                                                                         \
     {                                                                                                                \
-        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO, EPI>;                                      \
+        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO, EPI, CPP>;                                 \
         int SM = Smem<C, G, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : G * (Q.ls_stride * 4 + Q.es_stride * 8));       \
         cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);                                                 \
         if (e != cudaSuccess) return e;                                                                              \
@@ -89,6 +90,8 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     const bool bulk_ok = P.bulk_rows && !P.pil_k && !P.n_cfo && ((reinterpret_cast<unsigned long long>(eq) & 15ull) == 0) &&
                          ((reinterpret_cast<unsigned long long>(llr) & 15ull) == 0);
     const bool dense = (long long)P.ndb * 64 >= (long long)OFDM_DENSE_MIN_FILL64 * C::N;
+    const bool cpp = P.cp_extra != 0;                           // CP pattern: never together with pilots / hypothesis bank
+    if (cpp && (P.pil_k || P.n_cfo)) return cudaErrorInvalidValue;
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
         if (P.pil_k) OFDM_LAUNCH_RXF(true, false, EPI_SPARSE, Qp)
@@ -105,15 +108,19 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
                     if (eb != cudaSuccess) cudaGetLastError();              // rows do not fit next to the transform: not an error
                     bulk = eb == cudaSuccess && ep == cudaSuccess && db.ctas_per_sm >= dp.ctas_per_sm;
                 }
-                if (bulk) OFDM_LAUNCH_RXF(false, false, EPI_BULK, P)
+                if (bulk && cpp) OFDM_LAUNCH_RXF_(false, false, EPI_BULK, true, P)
+                else if (bulk) OFDM_LAUNCH_RXF(false, false, EPI_BULK, P)
             }
             // densely filled grids take the branch-free epilogue (same shared-memory footprint as the sparse one)
-            if (!bulk && dense) OFDM_LAUNCH_RXF(false, false, EPI_DENSE, Qp)
+            if (!bulk && dense && cpp) OFDM_LAUNCH_RXF_(false, false, EPI_DENSE, true, Qp)
+            else if (!bulk && dense) OFDM_LAUNCH_RXF(false, false, EPI_DENSE, Qp)
+            else if (!bulk && cpp) OFDM_LAUNCH_RXF_(false, false, EPI_SPARSE, true, Qp)
             else if (!bulk) OFDM_LAUNCH_RXF(false, false, EPI_SPARSE, Qp)
         }
         count_launch();
     })
 #undef OFDM_LAUNCH_RXF
+#undef OFDM_LAUNCH_RXF_
     return cudaGetLastError();
 }
 
@@ -154,10 +161,16 @@ cudaError_t launch_tx(const DevParams &P, const uint8_t *bits, float2 *out, long
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
     int SM = Smem<C, G, true, false>::BYTES;
     if (n_sym_total <= 0) return cudaSuccess;
+    if (P.cp_extra && P.pil_k) return cudaErrorInvalidValue;     // CP pattern: not combined with comb pilots
     OFDM_BPS_SWITCH(P.bps, {
         LaunchDims d;
         if (P.pil_k) {
             constexpr auto k = tx_kernel<C, BPS, G, true>;
+            cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
+            if (e != cudaSuccess) return e;
+            k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);
+        } else if (P.cp_extra) {
+            constexpr auto k = tx_kernel<C, BPS, G, false, true>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym_total, sms, d);
             if (e != cudaSuccess) return e;
             k<<<d.grid, TH, SM, st>>>(P, bits, out, n_sym_total, d.iters);

@@ -17,7 +17,8 @@ class OfdmParams(C.Structure):
         ("sync_advance", C.c_int32), ("gate", C.c_float), ("inv_reg_chanest", C.c_float),
         ("inv_reg_eq", C.c_float), ("inv_reg_eq_synch", C.c_float), ("llr_scale", C.c_float),
         ("pilot_spacing", C.c_int32), ("pilot_offset", C.c_int32), ("pilot_root", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("cp_first", C.c_int32), ("slot_syms", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -71,7 +72,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.ofdm_abi_version() != 2:
+        if l.ofdm_abi_version() != 3:
             raise OfdmError("libofdm_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -35,6 +35,8 @@ class ModemConfig:
     pilot_spacing: int = 0              # comb pilots in data symbols (extension); 0 = none
     pilot_offset: int = -1              # -1 -> pilot_spacing // 2
     pilot_root: int = 25
+    cp_first: int = 0                   # LTE normal-CP pattern (extension): prefix of symbols k % slot_syms == 0 ...
+    slot_syms: int = 0                  # ... of every frame; 0 = uniform cp_len.  Needs m0 == 1.
 
     def __post_init__(self):
         if isinstance(self.bps, str):
@@ -58,8 +60,15 @@ class ModemConfig:
         return self.m0 + self.d
 
     @property
+    def cp_pattern(self):
+        return self.cp_first > 0 and self.slot_syms > 0 and self.cp_first != self.cp_len
+
+    @property
     def frame_len(self):
-        return self.frame_syms * self.sym_len
+        n = self.frame_syms * self.sym_len
+        if self.cp_pattern:             # one longer prefix per started slot
+            n += (self.cp_first - self.cp_len) * ((self.frame_syms + self.slot_syms - 1) // self.slot_syms)
+        return n
 
     @property
     def mm(self):
@@ -106,6 +115,7 @@ class ModemConfig:
         p.inv_reg_chanest, p.inv_reg_eq, p.inv_reg_eq_synch = rc, re_, rs
         p.llr_scale = 1.0 / self.noise_var
         p.pilot_spacing, p.pilot_offset, p.pilot_root = self.pilot_spacing, max(self.pilot_offset, 0), self.pilot_root
+        p.cp_first, p.slot_syms = (self.cp_first, self.slot_syms) if self.cp_pattern else (0, 0)
         return p
 
 

@@ -51,6 +51,11 @@ class ModemParams:
     pilot_spacing: int = 0           # 0 = none; else every pilot_spacing-th used bin (list order) is a pilot
     pilot_offset: int = -1           # first pilot position in the used-bin list; -1 -> pilot_spacing // 2
     pilot_root: int = 25             # Zadoff-Chu root of the pilot sequence
+    # LTE "normal CP" pattern (EXTENSION, our definition; the reference assumes one CP length, rx_b_len =
+    # nfft + cp_len, SynchAndChanEst.py:79): symbol k of a frame has a prefix of cp_first samples when
+    # k % slot_syms == 0 and of cp_len samples otherwise (TS 36.211 5.6: 160/144 at 30.72 Msps, 7 symbols per slot).
+    cp_first: int = 0                # 0 = every symbol uses cp_len
+    slot_syms: int = 0
 
     def __post_init__(self):
         if self.zc_root is None:
@@ -70,8 +75,20 @@ class ModemParams:
         return self.m0 + self.d
 
     @property
+    def cp_pattern(self):
+        return self.cp_first > 0 and self.slot_syms > 0 and self.cp_first != self.cp_len
+
+    def sym_cp(self, k):
+        """prefix length of symbol k of a frame"""
+        return self.cp_first if self.cp_pattern and k % self.slot_syms == 0 else self.cp_len
+
+    def sym_start(self, k):
+        """offset of the first prefix sample of symbol k inside its frame (k = frame_syms gives the frame length)"""
+        return sum(self.nfft + self.sym_cp(i) for i in range(k))
+
+    @property
     def frame_len(self):
-        return self.frame_syms * self.sym_len
+        return self.sym_start(self.frame_syms)
 
     @property
     def mm(self):                    # MM, SynchAndChanEst.py:48-49
@@ -254,22 +271,26 @@ def tx_freq_grid(bits, prm: ModemParams, n_frames):
 # --------------------------------------------------------------------------------------------
 # a5  IFFT + CP add + power normalise
 # --------------------------------------------------------------------------------------------
-def tx_symb_gen(grid, cp_len):
+def tx_symb_gen(grid, cp_len, cps=None):
     """Per symbol: ifft -> [last CP samples, body] -> unit energy/sample -> divide by sqrt(var).
 
-    MultiAntennaSystem.py:189-219 (single antenna).  Returns the flat time waveform.
+    MultiAntennaSystem.py:189-219 (single antenna).  Returns the flat time waveform.  ``cps`` (EXTENSION)
+    gives every symbol its own prefix length; the two normalisations then use that symbol's length.
     """
     n_sym, N = grid.shape
-    L = N + cp_len
-    out = np.zeros(n_sym * L, dtype=complex)
+    cps = [cp_len] * n_sym if cps is None else list(cps)
+    out = np.zeros(n_sym * N + sum(cps), dtype=complex)
+    at = 0
     for s in range(n_sym):
+        L = N + cps[s]
         body = np.fft.ifft(grid[s], N)
-        t = np.concatenate((body[N - cp_len:], body))
+        t = np.concatenate((body[N - cps[s]:], body))
         energy = abs(np.dot(t, np.conj(t)))
         scale = np.sqrt(L / energy) if energy > 1e-30 else 1.0
         t = t * scale
         t = t * (1.0 / np.sqrt(np.var(t)))
-        out[s * L:(s + 1) * L] = t
+        out[at:at + L] = t
+        at += L
     return out
 
 
@@ -280,7 +301,8 @@ def pilot_values(prm: ModemParams):
 
 
 def tx_modulate(bits, prm: ModemParams, n_frames):
-    return tx_symb_gen(tx_freq_grid(bits, prm, n_frames), prm.cp_len)
+    cps = [prm.sym_cp(k) for k in range(prm.frame_syms)] * n_frames if prm.cp_pattern else None
+    return tx_symb_gen(tx_freq_grid(bits, prm, n_frames), prm.cp_len, cps)
 
 
 # --------------------------------------------------------------------------------------------
@@ -482,7 +504,7 @@ def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, litera
     """Loop-A body once per frame + loop-B body for all D data symbols of that frame.
 
     Frame f's synch FFT window opens at  first + f*frame_stride + CP - sync_advance ; data symbol n
-    opens at that position + M0*L + n*L.  This is the reference's per-lock arithmetic
+    opens at that position + M0*L + n*L (with a CP pattern: at the end of its own prefix, less sync_advance).  This is the reference's per-lock arithmetic
     (SynchAndChanEst.py:143-219 then :221-248) applied with one candidate per frame, which is how
     a receiver with known framing runs it.  Returns dict(delay, peak, locked, h[N], eq[D,ndb]) per
     frame stacked on axis 0.  With a CFO bank (``cfo``, rows from cfo_bank()) every frame picks its own
@@ -492,7 +514,9 @@ def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, litera
     """
     fs = prm.frame_len if frame_stride is None else frame_stride
     zc, bank = zc_for(prm), delay_bank(prm)
-    L = prm.sym_len
+    assert not prm.cp_pattern or prm.m0 == 1, "the CP pattern is defined for one synch symbol per frame"
+    # window of symbol k relative to the frame's synch window (uniform CP: k*L; with a CP pattern the prefixes differ)
+    woff = [prm.sym_start(k) + prm.sym_cp(k) - prm.sym_cp(0) for k in range(prm.frame_syms)]
     delay = np.zeros(n_frames, dtype=np.int32)
     peak = np.zeros(n_frames)
     locked = np.zeros(n_frames, dtype=np.uint8)
@@ -500,7 +524,7 @@ def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, litera
     eq = np.zeros((n_frames, prm.d, prm.n_payload_bins), dtype=complex)
     hyp = np.zeros(n_frames, dtype=np.int32)
     for f in range(n_frames):
-        pos = first + f * fs + prm.cp_len - prm.sync_advance
+        pos = first + f * fs + prm.sym_cp(0) - prm.sync_advance
         rot = nu = None
         if cfo is None:
             d_i, d_v, sd = sync_trial(rx, pos, prm, zc, bank, literal)
@@ -513,7 +537,7 @@ def rx_frames(rx, n_frames, prm: ModemParams, frame_stride=None, first=0, litera
         locked[f] = 1 if d_v > prm.gate * prm.mm else 0
         _, h[f], _ = chan_est(sd, d_i, prm, zc, bank, literal)
         for n in range(prm.d):
-            eq[f, n] = demod_symbol(rx, pos + prm.m0 * L + n * L, d_i, h[f], prm, literal, rot=rot, nu=nu)
+            eq[f, n] = demod_symbol(rx, pos + woff[prm.m0 + n], d_i, h[f], prm, literal, rot=rot, nu=nu)
     out = dict(delay=delay, peak=peak, locked=locked, h=h, eq=eq)
     if cfo is not None:
         out["hyp"] = hyp

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export: " + n
     assert set(_lib.SIGNATURES) == set(names)
     lib.ofdm_abi_version.restype = ctypes.c_int
-    assert lib.ofdm_abi_version() == 2
+    assert lib.ofdm_abi_version() == 3
 
 
 def test_params_struct_matches_header():
@@ -39,7 +39,7 @@ def test_params_struct_matches_header():
     body = txt[txt.index("typedef struct ofdm_params {"):txt.index("} ofdm_params;")]
     fields = re.findall(r"^\s*(int32_t|float)\s+(\w+)(\[\d+\])?;", body, flags=re.M)
     assert [f[1] for f in fields] == [f[0] for f in _lib.OfdmParams._fields_]
-    assert ctypes.sizeof(_lib.OfdmParams) == 4 * (len(fields) - 1) + 4 * 5 == 96
+    assert ctypes.sizeof(_lib.OfdmParams) == 4 * (len(fields) - 1) + 4 * 3 == 96      # two reserved words became the CP pattern
 
 
 def test_plan_create_needs_a_device_and_says_so():

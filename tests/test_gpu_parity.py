@@ -31,7 +31,8 @@ def oracle_prm(cfg):
                           num_data_bins=cfg.num_data_bins, m0=cfg.m0, d=cfg.d, bps=cfg.bps, snr=cfg.snr,
                           gate=cfg.gate, compat=cfg.compat, zc_root=cfg.zc_root, equalizer=cfg.equalizer,
                           sync_advance=cfg.sync_advance, pilot_spacing=cfg.pilot_spacing,
-                          pilot_offset=cfg.pilot_offset, pilot_root=cfg.pilot_root)
+                          pilot_offset=cfg.pilot_offset, pilot_root=cfg.pilot_root, cp_first=cfg.cp_first,
+                          slot_syms=cfg.slot_syms)
 
 
 def pack_symbols(bits, n_sym, per_sym, hard_stride):
@@ -144,3 +145,54 @@ def test_comb_pilot_mode_matches_oracle(kw):
     got_bits = unpack_symbols(got["hard"].cpu().numpy(), per_sym)
     assert np.array_equal(got_bits, oo.hard_bits(ref["eq"].reshape(-1), cfg.bps))
     assert np.mean(got_bits != bits) < (1e-9 if cfg.bps <= 2 else 2e-2)
+
+
+CP_PATTERN_CASES = [
+    dict(nfft=64, cp_len=16, cp_first=20, slot_syms=2, num_synch_bins=62, num_data_bins=60, m0=1, d=4, bps=2),
+    dict(nfft=128, cp_len=9, cp_first=10, slot_syms=7, num_synch_bins=126, num_data_bins=72, m0=1, d=13, bps=4),
+    dict(nfft=256, cp_len=64, cp_first=100, slot_syms=3, num_synch_bins=254, num_data_bins=240, m0=1, d=4, bps=6),   # CP > N/4
+    dict(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6),  # LTE 20 MHz
+]
+
+
+@pytest.mark.parametrize("kw", CP_PATTERN_CASES, ids=lambda k: "N%d_cp%d_%d_slot%d" % (k["nfft"], k["cp_first"], k["cp_len"], k["slot_syms"]))
+def test_cp_pattern_matches_oracle(kw):
+    """Extension (unpinned: the reference has one prefix length): LTE normal-CP pattern, first symbol of every slot
+    with the longer prefix.  TX waveform, frame length, and the framed receiver against the oracle."""
+    m = make(dict(kw, snr=100, gate=0.5, noise_var=0.01, sync_advance=2))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    assert cfg.frame_len == prm.frame_len
+    if cfg.nfft == 2048:
+        assert cfg.frame_len == 30720                       # one LTE subframe at 30.72 Msps
+    n_frames = 4
+    rng = np.random.default_rng(5)
+    per_sym = cfg.num_data_bins * cfg.bps
+    bits = rng.integers(0, 2, n_frames * cfg.d * per_sym)
+    ref_tx = oo.tx_modulate(bits, prm, n_frames)
+    packed = pack_symbols(bits, n_frames * cfg.d, per_sym, cfg.hard_stride)
+    tx = m.tx_modulate(torch.from_numpy(packed).cuda(), n_frames).cpu().numpy()
+    assert tx.shape == ref_tx.shape == (n_frames * cfg.frame_len,)
+    assert rel_err(tx, ref_tx) < RTOL
+    rx = oo.add_awgn(oo.apply_channel(ref_tx, oo.reference_channel(cfg.nfft))[:len(ref_tx)], 1e-4, rng).astype(np.complex64)
+    ref = oo.rx_frames(rx, n_frames, prm)
+    got = m.rx_frames(torch.from_numpy(rx).cuda(), n_frames, want_h=True)
+    assert np.array_equal(got["delay"].cpu().numpy(), ref["delay"])
+    assert np.array_equal(got["locked"].cpu().numpy(), ref["locked"]) and ref["locked"].all()
+    assert rel_err(got["h"].cpu().numpy(), ref["h"]) < RTOL
+    eq = got["eq"].cpu().numpy().reshape(ref["eq"].shape)
+    assert rel_err(eq, ref["eq"]) < RTOL
+    got_bits = unpack_symbols(got["hard"].cpu().numpy(), per_sym)
+    assert np.array_equal(got_bits, oo.hard_bits(ref["eq"].reshape(-1), cfg.bps))
+    assert np.mean(got_bits != bits) < (1e-9 if cfg.bps <= 2 else 2e-2)
+    ref_llr = oo.maxlog_llr(ref["eq"].reshape(n_frames * cfg.d, -1), cfg.bps, 1.0 / cfg.noise_var)
+    assert rel_err(got["llr"].cpu().numpy(), ref_llr) < RTOL
+    # the host-buffer entry point takes the same path
+    h = m.rx_frames_host(rx, n_frames)
+    assert np.array_equal(h["hard"], got["hard"].cpu().numpy())
+
+
+def test_cp_pattern_rejected_with_two_synch_symbols():
+    from ofdm_b200 import OfdmError
+    with pytest.raises(OfdmError):
+        make(dict(nfft=64, cp_len=16, cp_first=20, slot_syms=2, num_synch_bins=62, num_data_bins=60, m0=2, d=2, bps=2))

@@ -18,7 +18,7 @@ CASES = {
     "n64": n64(4),
     "n64_qpsk": n64(2),
     "n64_64qam": n64(6),
-    "lte": (ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100,
+    "lte": (ModemConfig(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100,
                         gate=0.5, noise_var=0.01), 4096),
     "n1024": (ModemConfig(nfft=1024, cp_len=256, num_synch_bins=1022, num_data_bins=960, m0=1, d=3, bps=4, snr=100,
                           gate=0.5, noise_var=0.01), 13107),

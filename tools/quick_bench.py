@@ -60,7 +60,7 @@ if __name__ == "__main__":
         for bps, nm in ((4, "16qam"), (2, "qpsk"), (6, "64qam")):
             run("N64_" + nm, ModemConfig(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=bps,
                                          snr=100, noise_var=0.01), 333334)
-        run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
+        run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
                                      bps=6, snr=100, noise_var=0.01), 4096)
         for n in (1024, 2048, 4096):
             ndb = int(0.9375 * n) // 4 * 4
@@ -72,7 +72,7 @@ if __name__ == "__main__":
             run("N%d_64qam" % n, ModemConfig(nfft=n, cp_len=n // 4, num_synch_bins=n - 2, num_data_bins=ndb, m0=1,
                                              d=3, bps=6, snr=100, noise_var=0.01), max(64, (1 << 26) // (4 * n * 5 // 4)))
     if which in ("large",):
-        run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
+        run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
                                      bps=6, snr=100, noise_var=0.01), 4096)
         for n in (1024, 2048, 4096):
             ndb = int(0.9375 * n) // 4 * 4
@@ -84,7 +84,7 @@ if __name__ == "__main__":
         run("N64_qpsk", ModemConfig(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2,
                                     snr=100, noise_var=0.01), 333334)
     if which in ("all", "lte"):
-        run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
+        run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
                                      bps=6, snr=100, noise_var=0.01), 4096)
     if which in ("ltex",):                                  # LTE grid (59 % of the bins used) on the per-lane epilogues
         for bps, nm in ((2, "qpsk"), (4, "16qam")):
