@@ -122,3 +122,17 @@ def test_sharding_helpers():
     blocks = [shard.frame_block(10, r, 4) for r in range(4)]
     assert blocks == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert shard.summarize([2, 100, 1.0, 4.0, 9, 10, 0, 0])["ber"] == 0.02
+
+
+def test_bench_frame_length_matches_the_host_numerology():
+    import bench
+    from ofdm_b200 import ModemConfig
+    for name, w in bench.WORKLOADS.items():
+        cfg = ModemConfig(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
+                          num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"],
+                          cp_first=w.get("cp_first", 0), slot_syms=w.get("slot_syms", 0))
+        assert bench.frame_len(w) == cfg.frame_len, name
+        rd, wr = bench.algorithmic_bytes(w, 10)
+        assert rd == 10 * cfg.frame_len * 8
+        assert wr == 10 * cfg.d * (cfg.num_data_bins * (8 + 4 * cfg.bps) + cfg.hard_stride) + 90
+    assert bench.frame_len(bench.WORKLOADS["rx_lte20_64qam"]) == 30720

@@ -15,4 +15,6 @@ python tools/prof_cases.py n64 lte > $O/prof_plain.log 2>&1 && \
       python tools/prof_cases.py n64 lte > $O/prof_ncu.log 2>&1
 python tools/sweep_nfft.py > $O/sweep_nfft.jsonl 2> $O/sweep_nfft.err
 python bench.py --workload rx_lte20_64qam --steps 20 --warmup 3 --no-cpu > $O/bench_lte.json 2> $O/bench_lte.err
+python bench.py --workload rx_lte20_streams --steps 10 --warmup 3 --no-cpu > $O/bench_lte_streams.json 2> $O/bench_lte_streams.err
+python tools/bench_sync.py > $O/bench_sync_search.jsonl 2> $O/bench_sync_search.err
 ls -la $O
