@@ -245,6 +245,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = ModemConfig(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
                       num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100.0, gate=0.5,
