@@ -428,7 +428,10 @@ template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = fal
     static constexpr int PK_BYTES = TXK ? 0 : 3 * C::N / 4 + 16;                    // packed row staged for aligned stores
     static constexpr int TX_ROW_BYTES = 3 * C::N / 4 + 16;                          // one packed payload row at any 16-byte phase (TX)
     static_assert((3 * C::N / 4 + 30) / 16 <= C::T, "one 16-byte chunk per thread must cover a payload row");
-    static constexpr int HB_STRIDE = TXK ? 2 * TX_ROW_BYTES : C::N + 16 + PK_BYTES; // +16: zero pad, keeps 16-byte alignment
+    // TX at N = 64: two 64-byte row buffers per group would put the four groups of a warp exactly 128 bytes (one bank
+    // sweep) apart, a 4-way conflict on every row copy and bit fetch (ncu: 3.1 wavefronts per LDS.U8) -> skew by 16 bytes
+    static constexpr int HB_STRIDE = TXK ? 2 * TX_ROW_BYTES + (C::LOG2N == 6 ? 16 : 0)
+                                         : C::N + 16 + PK_BYTES;                    // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
     static constexpr int LUT_BYTES = TXK ? 72 * 8 : 0;                              // constellation table (TX), entry 64 = 0
     static constexpr int HP_BYTES = (TXK || !PIL) ? 0 : GROUPS * (C::N / 2) * 8;    // per-symbol pilot estimates (RX, pilot mode)
@@ -1264,7 +1267,9 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
           int iters) {
     OFDM_KERNEL_PROLOGUE_(GROUPS, true, false)
     constexpr int N = C::N;
-    constexpr int ZERO = 64;                                 // LUT entry that maps unused bins to 0
+    // LUT entry that maps unused bins to 0: right behind the constellation, i.e. in a bank of its own below 64-QAM
+    // (entry 64 shared bank 0 with point 0: a 2-way conflict on every lookup that mixes guard and data bins)
+    constexpr int ZERO = 1 << BPS;
     const int L = N + P.cp, fs = P.m0 + P.d;
     // constellation table in shared memory: one LDS per bin instead of arithmetic on the bits
     // (bank-private copies of the table were tried: the 2-way conflicts of random lookups cost less than the
