@@ -430,8 +430,10 @@ template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = fal
     static_assert((3 * C::N / 4 + 30) / 16 <= C::T, "one 16-byte chunk per thread must cover a payload row");
     // TX at N = 64: two 64-byte row buffers per group would put the four groups of a warp exactly 128 bytes (one bank
     // sweep) apart, a 4-way conflict on every row copy and bit fetch (ncu: 3.1 wavefronts per LDS.U8) -> skew by 16 bytes
-    static constexpr int HB_STRIDE = TXK ? 2 * TX_ROW_BYTES + (C::LOG2N == 6 ? 16 : 0)
-                                         : C::N + 16 + PK_BYTES;                    // +16: zero pad, keeps 16-byte alignment
+    // (the receiver at N = 128 has two groups per warp 256 bytes apart, 2 wavefronts per hard-bit staging store, but is
+    // HBM-bound: skewing it changed nothing)
+    static constexpr int HB_RAW = TXK ? 2 * TX_ROW_BYTES : C::N + 16 + PK_BYTES;    // +16: zero pad, keeps 16-byte alignment
+    static constexpr int HB_STRIDE = HB_RAW + ((TXK && C::T < 32 && HB_RAW % 128 == 0) ? 16 : 0);
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
     static constexpr int LUT_BYTES = TXK ? 72 * 8 : 0;                              // constellation table (TX), entry 64 = 0
     static constexpr int HP_BYTES = (TXK || !PIL) ? 0 : GROUPS * (C::N / 2) * 8;    // per-symbol pilot estimates (RX, pilot mode)

@@ -20,6 +20,12 @@ CASES = {
     "n64_64qam": n64(6),
     "lte": (ModemConfig(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100,
                         gate=0.5, noise_var=0.01), 4096),
+    "n128": (ModemConfig(nfft=128, cp_len=32, num_synch_bins=126, num_data_bins=120, m0=1, d=3, bps=4, snr=100,
+                         gate=0.5, noise_var=0.01), 104857),
+    "n256": (ModemConfig(nfft=256, cp_len=64, num_synch_bins=254, num_data_bins=240, m0=1, d=3, bps=4, snr=100,
+                         gate=0.5, noise_var=0.01), 52428),
+    "n512": (ModemConfig(nfft=512, cp_len=128, num_synch_bins=510, num_data_bins=480, m0=1, d=3, bps=4, snr=100,
+                         gate=0.5, noise_var=0.01), 26214),
     "n1024": (ModemConfig(nfft=1024, cp_len=256, num_synch_bins=1022, num_data_bins=960, m0=1, d=3, bps=4, snr=100,
                           gate=0.5, noise_var=0.01), 13107),
     "n4096": (ModemConfig(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=3, bps=4, snr=100,
