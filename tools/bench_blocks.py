@@ -1,0 +1,76 @@
+"""Block-boundary benchmark: the drop-in GNU Radio blocks' work() on scheduler-sized host buffers (BASELINE configs[0],
+the path ofdm_chain.py drives), next to the stateful oracle blocks -- the reference's work() arithmetic on one host core,
+which is how GNU Radio runs a Python block (one thread per block, under the GIL); literal=True keeps the reference's
+dense diag matmuls.
+
+Every call moves the input buffer to the device, runs the sliding search, the host-side lock bookkeeping, the channel
+estimate and the symbol-list demodulation, and copies the written prefix back: launch and copy latency, not bandwidth,
+is what is measured here.  Prints one JSON line per case.  Not the contract bench (see bench.py)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "lte-gnu-radio-code_b200", "python"))
+from oracle import ofdm_oracle as oo  # noqa: E402  (CPU baseline leg only)
+from oracle.blocks_oracle import RxofdmBlockOracle, UtsaBlockOracle  # noqa: E402
+
+
+def waveform(n_samples, seed=7):
+    prm = oo.ModemParams(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2, snr=100)
+    nf = n_samples // prm.frame_len + 1
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, nf * prm.d * 60 * 2)
+    tx = oo.tx_modulate(bits, prm, nf)
+    rx = oo.add_awgn(oo.apply_channel(tx, oo.reference_channel(64))[:len(tx)], 1e-4, rng)
+    return np.concatenate((np.zeros(16, complex), rx))[:n_samples].astype(np.complex64)
+
+
+def second_call_seconds(make, rx, out, reps):
+    """mean time of the SECOND work() call of a fresh block: the first call primes the block's state and writes nothing
+    (SURVEY.md D7), and later calls on the same buffer search ever deeper because the lock rule remembers the last lock"""
+    ts = []
+    for _ in range(reps):
+        blk = make()
+        blk_work = (lambda: blk.work([rx], [out])) if hasattr(blk, "modem") else (lambda: blk.work(rx, out))
+        blk_work()
+        t0 = time.perf_counter()
+        blk_work()
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), blk
+
+
+def run(name, n_samples):
+    import RXOFDM
+    import utsa_ofdm
+    rx = waveform(n_samples)
+    nsym = n_samples // 80
+    if name == "utsa":
+        mk_b = lambda: utsa_ofdm.SynchAndChanEst(nsym, 64, 16, 62, [1, 3], 60, 100, 0.7, "/tmp/", "cest.pckl", 0, 0)
+        mk_o = lambda: UtsaBlockOracle(nsym, 64, 16, 62, [1, 3], 60, 100, 0.7, literal=True)
+    else:
+        mk_b = lambda: RXOFDM.synch_and_chan_est(nsym, 64, 16, 62, [1, 3], 60, 100, "/tmp/", "output_file", 0, 0, zc_root=23)
+        mk_o = lambda: RxofdmBlockOracle(nsym, 64, 16, 62, [1, 3], 60, 100, zc_root=23, literal=True)
+    out_b = np.zeros(n_samples, np.complex64)
+    out_o = np.zeros(n_samples, np.complex64)
+    second_call_seconds(mk_b, rx, out_b, 2)              # warm the library (plan tables, first launches)
+    t_b, blk = second_call_seconds(mk_b, rx, out_b, 20)
+    t_o, ora = second_call_seconds(mk_o, rx, out_o, 3)
+    n = ora.last_written
+    assert blk.last_written == n
+    err = float(np.max(np.abs(out_b[:n] - out_o[:n])) / (np.sqrt(np.mean(np.abs(out_o[:n]) ** 2)) + 1e-30)) if n else 0.0
+    print(json.dumps(dict(block=name, samples_per_call=n_samples, written_per_call=int(n),
+                          ms_per_call_b200=1e3 * t_b, ms_per_call_oracle_1core=1e3 * t_o, speedup=t_o / t_b,
+                          msamples_per_s_b200=n_samples / t_b / 1e6, msamples_per_s_oracle=n_samples / t_o / 1e6,
+                          rel_err_vs_oracle=err)), flush=True)
+
+
+if __name__ == "__main__":
+    # whole frames (the reference packing needs num_ofdm_symb % (M0+D) == 0); gr-RXOFDM keeps at most 100 locks
+    for name, sizes in (("utsa", (4160, 32000)), ("rxofdm", (4160, 16000))):
+        for n in sizes:
+            run(name, n)

@@ -17,4 +17,5 @@ python tools/sweep_nfft.py > $O/sweep_nfft.jsonl 2> $O/sweep_nfft.err
 python bench.py --workload rx_lte20_64qam --steps 20 --warmup 3 --no-cpu > $O/bench_lte.json 2> $O/bench_lte.err
 python bench.py --workload rx_lte20_streams --steps 10 --warmup 3 --no-cpu > $O/bench_lte_streams.json 2> $O/bench_lte_streams.err
 python tools/bench_sync.py > $O/bench_sync_search.jsonl 2> $O/bench_sync_search.err
+python tools/bench_blocks.py > $O/bench_blocks.jsonl 2> $O/bench_blocks.err
 ls -la $O

@@ -16,7 +16,7 @@ TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
 
 for src, dst in (("bench_n64.json", "bench_n64"), ("bench_reference.json", "bench_reference"), ("bench_lte.json", "bench_lte"),
                  ("sweep_nfft.jsonl", "sweep_nfft"), ("bench_lte_streams.json", "bench_lte_streams"),
-                 ("bench_sync_search.jsonl", "bench_sync_search")):
+                 ("bench_sync_search.jsonl", "bench_sync_search"), ("bench_blocks.jsonl", "bench_blocks")):
     ext = os.path.splitext(src)[1]
     shutil.copy(os.path.join(EV, src), os.path.join(PR, "%s_%s%s" % (TAG, dst, ext)))
 subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_export.py"), os.path.join(EV, "prof_final_raw.csv"),

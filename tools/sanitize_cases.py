@@ -16,11 +16,13 @@ for kw in (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d
     m = Modem(cfg)
     nf = 37
     # exactly-sized payload buffer (tail guard of the word loads) taken from the middle of a bigger one (odd alignment)
-    big = torch.randint(0, 256, (nf * cfg.d * cfg.hard_stride + 3,), dtype=torch.uint8, device="cuda")
-    bits = big[1:1 + nf * cfg.d * cfg.hard_stride]
-    tx = m.tx_modulate(bits.contiguous(), nf)
-    tx2 = m.tx_modulate(bits.clone(), nf)
-    assert torch.equal(tx, tx2)
+    # (every phase class of the transmitter's 16-byte row chunks)
+    big = torch.randint(0, 256, (nf * cfg.d * cfg.hard_stride + 16,), dtype=torch.uint8, device="cuda")
+    for off in (15, 8, 5, 1):
+        bits = big[off:off + nf * cfg.d * cfg.hard_stride]
+        tx = m.tx_modulate(bits.contiguous(), nf)
+        tx2 = m.tx_modulate(bits.clone(), nf)
+        assert torch.equal(tx, tx2), off
     rx = m.channel_awgn(tx, nf, torch.tensor([0.2, 1.0, 0.1j], dtype=torch.complex64, device="cuda"), 0.01, 5)
     cut = rx[: rx.numel() - 41].contiguous()                     # last frame runs off the buffer
     out = m.rx_frames(cut, nf, want_h=True)
