@@ -221,16 +221,21 @@ class Modem:
         return o
 
     # ---- RX, modular (what the stream blocks' work() drives) ---------------------------------
-    def sync_search(self, rx, first_start, stride, n_trials):
+    def sync_search(self, rx, first_start, stride, n_trials, packed=None):
+        """-> (peak f32, delay i32[, hyp i32]) per trial.  `packed`: an int32 device tensor of 2 (3 with a CFO bank) *
+        n_trials words that the results are written into back to back, so a caller can fetch them with one copy."""
         torch = _torch()
         rx = self._c64(rx)
-        peak = self.empty((n_trials,), torch.float32)
-        delay = self.empty((n_trials,), torch.int32)
+        if packed is None:
+            packed = self.empty(((3 if self.n_cfo else 2) * n_trials,), torch.int32)
+        assert packed.dtype == torch.int32 and packed.numel() >= (3 if self.n_cfo else 2) * n_trials
+        peak = packed[:n_trials].view(torch.float32)
+        delay = packed[n_trials:2 * n_trials]
         if not self.n_cfo:
             _lib.check(_lib.lib().ofdm_rx_sync_search(self._h, _ptr(rx), rx.numel(), first_start, stride, n_trials,
                                                       _ptr(peak), _ptr(delay), _stream()))
             return peak, delay
-        hyp = self.empty((n_trials,), torch.int32)
+        hyp = packed[2 * n_trials:3 * n_trials]
         _lib.check(_lib.lib().ofdm_rx_sync_search_cfo(self._h, _ptr(rx), rx.numel(), first_start, stride, n_trials,
                                                       _ptr(peak), _ptr(delay), _ptr(hyp), _stream()))
         return peak, delay, hyp
@@ -241,8 +246,12 @@ class Modem:
         n = pos.numel()
         assert pos.dtype == torch.int64 and delay.dtype == torch.int32
         h = self.empty((n, self.cfg.nfft), torch.complex64)
-        ht = self.empty((n, self.cfg.nfft), torch.complex64) if want_aux else None
-        se = self.empty((n, self.cfg.mm), torch.complex64) if want_aux else None
+        ht = se = None
+        if want_aux:                                     # one buffer, so both come back with one copy (.aux_flat)
+            aux = self.empty((n * (self.cfg.nfft + self.cfg.mm),), torch.complex64)
+            ht = aux[:n * self.cfg.nfft].view(n, self.cfg.nfft)
+            se = aux[n * self.cfg.nfft:].view(n, self.cfg.mm)
+            self.aux_flat = aux
         assert hyp is None or (hyp.dtype == torch.int32 and hyp.numel() == n)
         _lib.check(_lib.lib().ofdm_rx_chanest_cfo(self._h, _ptr(rx), rx.numel(), _ptr(pos), _ptr(delay), _ptr(hyp), n,
                                                   _ptr(h), _ptr(ht), _ptr(se), _stream()))

@@ -72,20 +72,44 @@ class RxBlockBase(gr.sync_block):
         nv = self._n_valid_trials(n)
         if nv == 0:
             return np.zeros(0, np.float32), np.zeros(0, np.int32)
-        res = self.modem.sync_search(rx, self.cfg.cp_len, self.cfg.stride, nv)
-        return tuple(r.cpu().numpy() for r in res)          # (peak, delay) or, with a CFO bank, (peak, delay, hyp)
+        k = 3 if self.modem.n_cfo else 2
+        packed = self.modem.empty((k * nv,), self._torch.int32)
+        self.modem.sync_search(rx, self.cfg.cp_len, self.cfg.stride, nv, packed=packed)
+        host = packed.cpu().numpy()                         # one copy: (peak, delay) or, with a CFO bank, (peak, delay, hyp)
+        return (host[:nv].view(np.float32),) + tuple(host[i * nv:(i + 1) * nv] for i in range(1, k))
+
+    def _to_device(self, i64=(), i32=()):
+        """Small per-call index lists -> device tensors with ONE host-to-device copy (every copy of a work() call is a
+        synchronisation, and the call is latency-bound): int64 lists first, then int32 lists, all of one length."""
+        torch = self._torch
+        n = len(i64[0]) if i64 else len(i32[0])
+        raw = np.empty(8 * n * len(i64) + 4 * n * len(i32), np.uint8)
+        at = 0
+        for v in i64:
+            raw[at:at + 8 * n].view(np.int64)[:] = v
+            at += 8 * n
+        for v in i32:
+            raw[at:at + 4 * n].view(np.int32)[:] = v
+            at += 4 * n
+        d = torch.from_numpy(raw).to(self.modem.device)
+        out, at = [], 0
+        for _ in i64:
+            out.append(d[at:at + 8 * n].view(torch.int64))
+            at += 8 * n
+        for _ in i32:
+            out.append(d[at:at + 4 * n].view(torch.int32))
+            at += 4 * n
+        return out
 
     def _estimate_into(self, rx, rows, pos, delay, hyp=None):
-        """Channel estimates for new locks -> state rows; aux outputs only when diagnostics ask."""
-        torch = self._torch
-        dev = self.modem.device
-        want_aux = True
-        h, ht, se = self.modem.chanest(rx, torch.tensor(pos, dtype=torch.int64, device=dev),
-                                       torch.tensor(delay, dtype=torch.int32, device=dev), want_aux=want_aux,
-                                       hyp=None if hyp is None else torch.tensor(hyp, dtype=torch.int32, device=dev))
-        idx = torch.tensor(rows, dtype=torch.int64, device=dev)
-        self._d_H.index_copy_(0, idx, h)
-        ht_h, se_h = ht.cpu().numpy(), se.cpu().numpy()
+        """Channel estimates for new locks -> state rows (+ time-domain channel and equalised preamble, which the
+        reference keeps as block state)."""
+        dv = self._to_device(i64=(pos, rows), i32=(delay,) if hyp is None else (delay, hyp))
+        h, ht, se = self.modem.chanest(rx, dv[0], dv[2], want_aux=True, hyp=None if hyp is None else dv[3])
+        self._d_H.index_copy_(0, dv[1], h)
+        n, c = len(rows), self.cfg
+        aux = self.modem.aux_flat.cpu().numpy()              # both auxiliary outputs in one copy
+        ht_h, se_h = aux[:n * c.nfft].reshape(n, c.nfft), aux[n * c.nfft:].reshape(n, c.mm)
         for i, r in enumerate(rows):
             self.est_chan_time[r] = ht_h[i]
             self.est_synch_freq[r] = se_h[i]
@@ -133,8 +157,6 @@ class RxBlockBase(gr.sync_block):
             return
         torch = self._torch
         dev = self.modem.device
-        eq, _, _ = self.modem.demod(rx, torch.tensor(start, dtype=torch.int64, device=dev),
-                                    torch.tensor(delay, dtype=torch.int32, device=dev),
-                                    torch.tensor(hrow, dtype=torch.int32, device=dev), self._d_H,
-                                    hyp=None if hyp is None else torch.tensor(hyp, dtype=torch.int32, device=dev))
+        dv = self._to_device(i64=(start,), i32=(delay, hrow) if hyp is None else (delay, hrow, hyp))
+        eq, _, _ = self.modem.demod(rx, dv[0], dv[1], dv[2], self._d_H, hyp=None if hyp is None else dv[3])
         self.est_data_freq[np.asarray(rows)] = eq.cpu().numpy()
