@@ -885,10 +885,15 @@ template <class C> struct MinBlocks {
     static constexpr int byregs = 65536 / (THREADS * REGS);
     static constexpr int value = C::LOG2N <= 9 ? OFDM_MINB_SMALL : (byregs < 1 ? 1 : byregs);
 };
+#ifndef OFDM_MINB_TX_SMALL_MAX_LOG2N
+#define OFDM_MINB_TX_SMALL_MAX_LOG2N 5        // transmitter sizes up to this one ask for 5 resident CTAs (<= 102 registers); B200:
+                                              // N=64 0.185 -> 0.193 ms with 5 x 89 registers, N=512 0.139 -> 0.145 ms: 4 CTAs stay
+#endif
 template <class C> struct MinBlocksTx {
     static constexpr int THREADS = C::T >= 128 ? C::T : 128;
     static constexpr int byregs = 65536 / (THREADS * 128);
-    static constexpr int value = C::LOG2N <= 9 ? OFDM_MINB_SMALL : (byregs < 1 ? 1 : byregs);
+    static constexpr int value = C::LOG2N <= OFDM_MINB_TX_SMALL_MAX_LOG2N ? 5
+                                 : (C::LOG2N <= 9 ? OFDM_MINB_SMALL : (byregs < 1 ? 1 : byregs));
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1435,15 +1440,15 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
             float3 acc = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
             for (int m = 0; m < PPT; ++m) {
+                // sum of t: the N body samples add up to N * X[0], and the DC bin is never used (data, pilots and the
+                // Zadoff-Chu bins all skip it), so only the prefix copies contribute to the symbol's mean
                 if (m < MCP) {
                     acc.x += cabs2(v[m]);
-                    acc.y += v[m].x;
-                    acc.z += v[m].y;
                 } else {
-                    const float w = (j >= ncp0 - m * T) ? 2.f : 1.f;
-                    acc.x = fmaf(w, cabs2(v[m]), acc.x);
-                    acc.y = fmaf(w, v[m].x, acc.y);
-                    acc.z = fmaf(w, v[m].y, acc.z);
+                    const float c = (j >= ncp0 - m * T) ? 1.f : 0.f;
+                    acc.x = fmaf(c + 1.f, cabs2(v[m]), acc.x);
+                    acc.y = fmaf(c, v[m].x, acc.y);
+                    acc.z = fmaf(c, v[m].y, acc.z);
                 }
             }
             acc = group_sum3<T, GROUPS>(acc, redf, j, gid);
