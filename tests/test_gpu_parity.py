@@ -196,3 +196,27 @@ def test_cp_pattern_rejected_with_two_synch_symbols():
     from ofdm_b200 import OfdmError
     with pytest.raises(OfdmError):
         make(dict(nfft=64, cp_len=16, cp_first=20, slot_syms=2, num_synch_bins=62, num_data_bins=60, m0=2, d=2, bps=2))
+
+
+def test_cp_pattern_many_frames_multi_iteration():
+    """More symbols than resident symbol groups, so the persistent groups take several strides through the CP-pattern
+    addressing (frame index, slot shifts, clamping at the end of the list)."""
+    kw = dict(nfft=64, cp_len=16, cp_first=24, slot_syms=3, num_synch_bins=62, num_data_bins=60, m0=1, d=6, bps=2)
+    m = make(dict(kw, snr=100, gate=0.5, noise_var=0.01))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    n_frames = 4001                                          # 28 007 symbols on at most 148 * 5 * 16 groups
+    rng = np.random.default_rng(8)
+    per_sym = cfg.num_data_bins * cfg.bps
+    bits = rng.integers(0, 2, n_frames * cfg.d * per_sym)
+    ref_tx = oo.tx_modulate(bits, prm, n_frames)
+    packed = pack_symbols(bits, n_frames * cfg.d, per_sym, cfg.hard_stride)
+    d_tx = m.tx_modulate(torch.from_numpy(packed).cuda(), n_frames)
+    assert rel_err(d_tx.cpu().numpy(), ref_tx) < RTOL
+    got = m.rx_frames(d_tx, n_frames)
+    assert bool(got["locked"].all().item()) and bool((got["delay"] == 0).all().item())
+    assert np.array_equal(unpack_symbols(got["hard"].cpu().numpy(), per_sym), bits)
+    sub = slice(n_frames - 40, n_frames)                     # the last strides against the oracle
+    ref = oo.rx_frames(ref_tx.astype(np.complex64), n_frames, prm)["eq"][sub]
+    eq = got["eq"].cpu().numpy().reshape(n_frames, cfg.d, -1)[sub]
+    assert rel_err(eq, ref) < RTOL
