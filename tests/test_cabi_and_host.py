@@ -136,3 +136,10 @@ def test_bench_frame_length_matches_the_host_numerology():
         assert rd == 10 * cfg.frame_len * 8
         assert wr == 10 * cfg.d * (cfg.num_data_bins * (8 + 4 * cfg.bps) + cfg.hard_stride) + 90
     assert bench.frame_len(bench.WORKLOADS["rx_lte20_64qam"]) == 30720
+
+
+def test_graft_entry_build_passes():
+    """The driver's build check: compiles (a no-op when the library is current), loads the library, resolves every
+    symbol and checks the ABI version against the header."""
+    import __graft_entry__ as g
+    g.build()
