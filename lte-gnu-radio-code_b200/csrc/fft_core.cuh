@@ -77,7 +77,7 @@ template <int LOG2N_, int PPT_, bool CH_ = false, bool PAD_ = false> struct FftC
 };
 
 // Points per thread for each transform size and kernel family (overridable for A/B runs, e.g.
-// -DOFDM_PPT_RX_4096=8).  Measured on B200 (tools/sweep_minb.sh): 16 points per thread speed the
+// -DOFDM_PPT_RX_4096=8).  Measured on B200 (tools/build_variant.sh + tools/run_variants.sh): 16 points per thread speed the
 // transmitter up by 11-28 % at N >= 256 and the receiver by 14 % at N = 4096; at N = 1024/2048 the
 // receiver also carries 16 equaliser gains per thread and is faster with 8.
 #ifndef OFDM_PPT_TX_LARGE
