@@ -1262,6 +1262,9 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
 // Both normalisations are scale factors derived from two sums over the L = N+CP output samples
 // (CP samples count twice), so the symbol is written to HBM once, already normalised.
 // ------------------------------------------------------------------------------------------------
+#ifndef OFDM_TX_MIDZERO
+#define OFDM_TX_MIDZERO 1                 // see tx_kernel: guard band compiled out for grids below 5/8 fill (LTE)
+#endif
 #ifndef OFDM_TX_LUT32
 #define OFDM_TX_LUT32 1                   // B200: +2 % at N=64, +2.5 % at N=2048 (0 = float2 entries)
 #endif
@@ -1408,29 +1411,54 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
                     const unsigned val = (w >> (16 - (bo & 7) - BPS)) & ((1u << BPS) - 1u);
                     v[m] = !used ? make_float2(0.f, 0.f) : (pq.is_pilot ? __ldg(P.pilot_tx + j + m * T) : look(val));
                 }
-            } else {
+                if (s < P.m0) {
+                    const float2 *z = P.zc_tx + s * N + j;
 #pragma unroll
-                for (int m = 0; m < PPT; ++m) {
-                    // (skipping the fetch + lookup for guard bins was tried, per thread and per row with a branch on kernel
-                    // parameters only: 4-19 % slower either way -- the straight-line form lets all loads issue together)
-                    const uint8_t *q = rp + (m < PPT / 2 ? byp : byn) + m * (T * BPS / 8);
-                    unsigned val;
-                    if (BPS == 6) {                              // a 6-bit field can straddle two bytes
-                        const unsigned w = ((unsigned)q[0] << 8) | (unsigned)q[1];
-                        val = (w >> (m < PPT / 2 ? shp : shn)) & 63u;
-                    } else {
-                        val = ((unsigned)q[0] >> ((m < PPT / 2 ? shp : shn) - 8)) & ((1u << BPS) - 1u);
+                    for (int m = 0; m < PPT; ++m) v[m] = __ldg(z + m * T);
+                }
+                fft_group<C, true, GROUPS, false, TWR>(v, tws, b0, b1, j, gid, pp, twreg);
+            } else {
+                // Bits -> points -> inverse transform.  MZ ("middle zero"): a data symbol whose grid fills less than
+                // 5/8 of the transform (every LTE bandwidth) has bins 5T..11T-1 empty for every thread, i.e. inputs
+                // m = 5..10 of the first radix-16 pass are zero: their fetch + lookup and 12 of that pass' 32 first-layer
+                // additions are compiled out.  The choice is uniform per symbol group, and groups are whole warps here.
+                auto front = [&](auto mz) {
+                    constexpr bool MZ = decltype(mz)::value;
+#pragma unroll
+                    for (int m = 0; m < PPT; ++m) {
+                        if (MZ && m >= 5 && m < 11) {
+                            v[m] = make_float2(0.f, 0.f);
+                            continue;
+                        }
+                        // (skipping the fetch + lookup for single guard bins was tried, per thread and per row with a
+                        // branch on kernel parameters only: 4-19 % slower either way -- the straight-line form lets all
+                        // loads issue together)
+                        const uint8_t *q = rp + (m < PPT / 2 ? byp : byn) + m * (T * BPS / 8);
+                        unsigned val;
+                        if (BPS == 6) {                          // a 6-bit field can straddle two bytes
+                            const unsigned w = ((unsigned)q[0] << 8) | (unsigned)q[1];
+                            val = (w >> (m < PPT / 2 ? shp : shn)) & 63u;
+                        } else {
+                            val = ((unsigned)q[0] >> ((m < PPT / 2 ? shp : shn) - 8)) & ((1u << BPS) - 1u);
+                        }
+                        v[m] = look((map.mask & (1u << m)) ? val : ZERO);
                     }
-                    v[m] = look((map.mask & (1u << m)) ? val : ZERO);
+                    if (!MZ && s < P.m0) {
+                        const float2 *z = P.zc_tx + s * N + j;
+#pragma unroll
+                        for (int m = 0; m < PPT; ++m) v[m] = __ldg(z + m * T);
+                    }
+                    fft_group<C, true, GROUPS, false, TWR, MZ>(v, tws, b0, b1, j, gid, pp, twreg);
+                };
+                constexpr bool MZ_OK = OFDM_TX_MIDZERO != 0 && PPT == 16 && T >= 32;
+                if constexpr (MZ_OK) {
+                    if (s >= P.m0 && P.ndb < 10 * T) front(std::true_type{});
+                    else front(std::false_type{});
+                } else {
+                    front(std::false_type{});
                 }
             }
-            if (s < P.m0) {
-                const float2 *z = P.zc_tx + s * N + j;
-#pragma unroll
-                for (int m = 0; m < PPT; ++m) v[m] = __ldg(z + m * T);
-            }
         }
-        fft_group<C, true, GROUPS, false, TWR>(v, tws, b0, b1, j, gid, pp, twreg);
         // Power / mean sums with the CP samples counted twice, one scale, stores with the CP copy.  With CP <= N/4 (every
         // numerology in use) only the last quarter of a thread's samples can repeat in the prefix, so the common case
         // is compiled without the per-sample compare, weight select and predicated second store for the other three

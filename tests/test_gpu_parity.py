@@ -56,10 +56,15 @@ CASES = [
     dict(nfft=1024, cp_len=72, num_synch_bins=1022, num_data_bins=600, m0=1, d=2, bps=4),
     dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=3, bps=6),
     dict(nfft=4096, cp_len=288, num_synch_bins=4094, num_data_bins=3840, m0=1, d=2, bps=2),
+    # either side of the transmitter's "middle zero" threshold (num_data_bins < 10/16 nfft) and an LTE 5 MHz grid
+    dict(nfft=512, cp_len=36, num_synch_bins=510, num_data_bins=318, m0=1, d=2, bps=4),
+    dict(nfft=512, cp_len=36, num_synch_bins=510, num_data_bins=320, m0=1, d=2, bps=4),
+    dict(nfft=512, cp_len=36, num_synch_bins=510, num_data_bins=300, m0=2, d=2, bps=6),
+    dict(nfft=4096, cp_len=288, num_synch_bins=4094, num_data_bins=2400, m0=1, d=2, bps=2),
 ]
 
 
-@pytest.mark.parametrize("kw", CASES, ids=lambda k: "N%d_b%d_m%d" % (k["nfft"], k["bps"], k["m0"]))
+@pytest.mark.parametrize("kw", CASES, ids=lambda k: "N%d_n%d_b%d_m%d" % (k["nfft"], k["num_data_bins"], k["bps"], k["m0"]))
 def test_tx_matches_oracle(kw):
     m = make(dict(kw, snr=100))
     cfg = m.cfg
@@ -75,7 +80,7 @@ def test_tx_matches_oracle(kw):
     assert rel_err(out, ref) < RTOL
 
 
-@pytest.mark.parametrize("kw", CASES, ids=lambda k: "N%d_b%d_m%d" % (k["nfft"], k["bps"], k["m0"]))
+@pytest.mark.parametrize("kw", CASES, ids=lambda k: "N%d_n%d_b%d_m%d" % (k["nfft"], k["num_data_bins"], k["bps"], k["m0"]))
 def test_rx_frames_matches_oracle(kw):
     m = make(dict(kw, snr=100, gate=0.5, noise_var=0.01, sync_advance=min(3, kw["cp_len"])))
     cfg = m.cfg
