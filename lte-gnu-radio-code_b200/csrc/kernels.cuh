@@ -435,7 +435,7 @@ template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = fal
     static constexpr int HB_RAW = TXK ? 2 * TX_ROW_BYTES : C::N + 16 + PK_BYTES;    // +16: zero pad, keeps 16-byte alignment
     static constexpr int HB_STRIDE = HB_RAW + ((TXK && C::T < 32 && HB_RAW % 128 == 0) ? 16 : 0);
     static constexpr int HB_BYTES = GROUPS * HB_STRIDE;
-    static constexpr int LUT_BYTES = TXK ? 72 * 8 : 0;                              // constellation table (TX), entry 64 = 0
+    static constexpr int LUT_BYTES = TXK ? 72 * 8 : 0;                              // constellation table (TX) + its zero entry
     static constexpr int HP_BYTES = (TXK || !PIL) ? 0 : GROUPS * (C::N / 2) * 8;    // per-symbol pilot estimates (RX, pilot mode)
     static constexpr int GS_BYTES = GSM ? GROUPS * C::N * 8 : 0;                    // equaliser gains, slot m*T + j of the group
     static constexpr int OFF_TW = FFT_BYTES;
