@@ -210,6 +210,101 @@ __global__ void channel_kernel(const float2 *__restrict__ x, float2 *__restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Acquisition without a transform per trial (stride-1 sliding search, one synch symbol, synch bins = all but DC and
+// the band edge -- the gr-utsa_ofdm block's configuration).  Same values as rx_sync_search_kernel up to rounding:
+//   c[d; p] / p_est = r(p+d) + sum_{i=1..d} (x[p+d-i] - x[p+d-i+N]) h[N-i],   r(q) = sum_m x[q+m] h[m],
+//   h[m] = sum_{k in S} conj(zc_k) e^{-j2pi km/N}      (oracle/ofdm_oracle.py: sync_search_time_domain has the derivation)
+// so every position q needs one N-tap correlation and a (CP+1)-long PREFIX sum, and the unit-power factor follows from
+// sum_{k in S} |X_k|^2 = N sum_n |x[p+n]|^2 - |X_0|^2 - |X_{N/2}|^2, all three accumulated in the same pass over the
+// window.  A CTA takes TP = 128*R - CP consecutive trials: thread t owns positions q0 + t + 128 j, j < R (lane-contiguous
+// shared-memory reads, the tap h[m] is a broadcast), and the delay maximum of trial p = q - i is kept in shared memory
+// with a packed (|c|^2, -d) 64-bit atomicMax, which resolves ties to the lowest delay like np.argmax.
+// ------------------------------------------------------------------------------------------------
+constexpr int TD_R = 8, TD_THREADS = 128, TD_TQ = TD_R * TD_THREADS;
+
+__global__ void __launch_bounds__(TD_THREADS)
+rx_sync_search_td_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
+                         long long n_trials, float *__restrict__ peak_out, int *__restrict__ delay_out) {
+    extern __shared__ __align__(16) unsigned char td_smem[];
+    const int N = P.nfft, CP = P.cp, t = threadIdx.x;
+    const int TP = TD_TQ - CP;                                          // trials per CTA
+    const int XW = TD_TQ + N + CP;                                      // samples staged: q0 - CP .. q0 + TQ + N - 1
+    float2 *X = reinterpret_cast<float2 *>(td_smem);
+    float2 *H = X + XW;
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(H + N);
+    float *pw = reinterpret_cast<float *>(best + TD_TQ);
+    const long long tile0 = (long long)blockIdx.x * TP;                 // first trial of the tile
+    const long long q0 = first_start + tile0;                           // its window start = first position of the tile
+    const long long last_trial = n_trials - 1;
+    for (int i = t; i < XW; i += TD_THREADS) {
+        const long long g = q0 - CP + i;
+        X[i] = (g >= 0 && g < n_samples) ? __ldg(x + g) : make_float2(0.f, 0.f);
+    }
+    for (int i = t; i < N; i += TD_THREADS) H[i] = __ldg(P.h_td + i);
+    for (int i = t; i < TD_TQ; i += TD_THREADS) best[i] = 0ull;
+    __syncthreads();
+    float2 acc[TD_R], s0[TD_R], s1[TD_R];
+    float en[TD_R];
+#pragma unroll
+    for (int j = 0; j < TD_R; ++j) {
+        acc[j] = s0[j] = s1[j] = make_float2(0.f, 0.f);
+        en[j] = 0.f;
+    }
+    const float2 *xb = X + CP + t;                                      // position q0 + t + 128 j reads xb[128 j + m]
+    for (int m = 0; m < N; m += 2) {
+        const float2 h0 = H[m], h1 = H[m + 1];
+#pragma unroll
+        for (int j = 0; j < TD_R; ++j) {
+            const float2 a = xb[TD_THREADS * j + m], b = xb[TD_THREADS * j + m + 1];
+            acc[j].x = fmaf(a.x, h0.x, fmaf(-a.y, h0.y, acc[j].x));
+            acc[j].y = fmaf(a.x, h0.y, fmaf(a.y, h0.x, acc[j].y));
+            acc[j].x = fmaf(b.x, h1.x, fmaf(-b.y, h1.y, acc[j].x));
+            acc[j].y = fmaf(b.x, h1.y, fmaf(b.y, h1.x, acc[j].y));
+            en[j] = fmaf(a.x, a.x, fmaf(a.y, a.y, en[j]));
+            en[j] = fmaf(b.x, b.x, fmaf(b.y, b.y, en[j]));
+            s0[j].x += a.x + b.x;                                       // X_0
+            s0[j].y += a.y + b.y;
+            s1[j].x += a.x - b.x;                                       // X_{N/2}: alternating signs
+            s1[j].y += a.y - b.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < TD_R; ++j)                                      // power in the synch bins of the window at q
+        pw[t + TD_THREADS * j] = (float)N * en[j] - cabs2(s0[j]) - cabs2(s1[j]);
+    auto offer = [&](int j, int i) {                                    // c[i; q - i] for position j of this thread
+        const int pl = t + TD_THREADS * j - i;                          // trial index inside the tile
+        if (pl >= 0 && pl < TP && tile0 + pl <= last_trial) {
+            const unsigned long long key =
+                ((unsigned long long)__float_as_uint(cabs2(acc[j])) << 32) | (unsigned)(0x7fffffff - i);
+            atomicMax(best + pl, key);
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < TD_R; ++j) offer(j, 0);
+    for (int i = 1; i <= CP; ++i) {
+        const float2 hh = H[N - i];
+#pragma unroll
+        for (int j = 0; j < TD_R; ++j) {
+            const float2 a = xb[TD_THREADS * j - i], b = xb[TD_THREADS * j - i + N];
+            const float2 dl = make_float2(a.x - b.x, a.y - b.y);
+            acc[j].x = fmaf(dl.x, hh.x, fmaf(-dl.y, hh.y, acc[j].x));
+            acc[j].y = fmaf(dl.x, hh.y, fmaf(dl.y, hh.x, acc[j].y));
+            offer(j, i);
+        }
+    }
+    __syncthreads();
+    for (int pl = t; pl < TP; pl += TD_THREADS) {
+        const long long tr = tile0 + pl;
+        if (tr > last_trial) break;
+        const unsigned long long key = best[pl];
+        const float p = pw[pl];
+        const float p_est = p > 0.f ? sqrtf((float)P.mm / p) : 0.f;
+        peak_out[tr] = p_est * sqrtf(__uint_as_float((unsigned)(key >> 32)));
+        delay_out[tr] = 0x7fffffff - (int)(key & 0xffffffffu);
+    }
+}
+
 }  // namespace ofdm
 
 // ------------------------------------------------------------------------------------------------
@@ -355,10 +450,33 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
         const double a = -(two_pi / (double)n_pil) * (double)p->pilot_root * q;
         pilot_tx[k] = make_float2((float)cos(a), (float)sin(a));
     }
+    // taps of the time-domain acquisition kernel (rx_sync_search_td_kernel): h[m] = sum_idx conj(zc[idx]) e^{-j2pi k m/N},
+    // only for the configuration it serves (one synch symbol on every bin but DC and the band edge)
+    const bool td_ok = (m0 == 1 && nsb == N - 2);
+    std::vector<float2> h_td(N, make_float2(0.f, 0.f));
+    if (td_ok) {
+        std::vector<double> cs(N), sn(N);
+        for (int k = 0; k < N; ++k) {
+            cs[k] = cos(two_pi * (double)k / (double)N);
+            sn[k] = sin(two_pi * (double)k / (double)N);
+        }
+        for (int m = 0; m < N; ++m) {
+            double ar = 0.0, ai = 0.0;
+            for (int idx = 0; idx < nsb; ++idx) {
+                const int sbin = idx < h ? idx - h : idx - h + 1;
+                const int k = ((sbin % N) + N) % N;
+                const int e2 = (int)(((long long)k * m) % N);            // e^{-j2pi km/N} = cs - j sn
+                ar += zr[idx] * cs[e2] - zi[idx] * sn[e2];               // conj(zc) = zr - j zi
+                ai += -zr[idx] * sn[e2] - zi[idx] * cs[e2];
+            }
+            h_td[m] = make_float2((float)ar, (float)ai);
+        }
+    }
     const size_t b_tw = sizeof(float2) * N, b_zb = sizeof(float2) * m0 * N, b_w = sizeof(float) * N,
-                 b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * m0 * N, b_pt = sizeof(float2) * N;
+                 b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * m0 * N, b_pt = sizeof(float2) * N,
+                 b_ht = sizeof(float2) * N;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt) + al(b_pt);
+    const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt) + al(b_pt) + al(b_ht);
     e = cudaMalloc(&pl->d_tables, total);
     if (e != cudaSuccess) {
         delete pl;
@@ -379,6 +497,8 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     D.zc_dup = (const float2 *)put(zc_dup.data(), b_zd);
     D.zc_tx = (const float2 *)put(zc_tx.data(), b_zt);
     D.pilot_tx = (const float2 *)put(pilot_tx.data(), b_pt);
+    D.h_td = (const float2 *)put(h_td.data(), b_ht);
+    if (!td_ok) D.h_td = nullptr;
     if (e != cudaSuccess) {
         cudaFree(pl->d_tables);
         delete pl;
@@ -509,6 +629,24 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
                             int64_t n_trials, float *d_peak, int32_t *d_delay, int32_t *d_hyp, void *stream) {
     if (pl && n_trials == 0) return OFDM_OK;
     if (!pl || !d_time || !d_peak || !d_delay || n_trials < 0 || stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_sync_search: bad argument%s");
+    // stride-1 search of the utsa configuration: time-domain kernel, no transform per trial (OFDM_SYNC_TD=0 disables it)
+    const char *td_env = getenv("OFDM_SYNC_TD");
+    const bool td_on = !(td_env && atoi(td_env) == 0);
+    if (td_on && stride == 1 && pl->dev.h_td && !pl->dev.n_cfo && first_start >= 0) {
+        const int N = pl->prm.nfft, CP = pl->prm.cp_len, TP = TD_TQ - CP;
+        const int smem = (TD_TQ + N + CP) * 8 + N * 8 + TD_TQ * 8 + TD_TQ * 4;
+        static int max_set = 0;
+        if (smem > max_set) {
+            CU(cudaFuncSetAttribute(rx_sync_search_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "ofdm_rx_sync_search(attr)");
+            max_set = smem;
+        }
+        const long long tiles = (n_trials + TP - 1) / TP;
+        rx_sync_search_td_kernel<<<(unsigned)tiles, TD_THREADS, smem, (cudaStream_t)stream>>>(
+            pl->dev, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay);
+        count_launch();
+        CU(cudaGetLastError(), "ofdm_rx_sync_search(td)");
+        return OFDM_OK;
+    }
     CU(pl->ks->sync_search(pl->dev, (const float2 *)d_time, n_samples, first_start, stride, n_trials, d_peak, d_delay,
                            d_hyp, (cudaStream_t)stream, pl->sms),
        "ofdm_rx_sync_search");

@@ -48,6 +48,7 @@ struct DevParams {
     int cfo_continuous;
     const double *cfo_nu;             // [n_cfo] cycles per sample
     const float2 *pilot_tx;   // [N]      pilot value in FFT bin k (0 elsewhere)
+    const float2 *h_td;       // [N]      taps of the time-domain acquisition kernel (api.cu), or null when it does not apply
 };
 
 // position of a used-bin-list index among pilots / payload bins

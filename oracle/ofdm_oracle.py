@@ -412,6 +412,71 @@ def sync_trial(in0, start, prm: ModemParams, zc=None, bank=None, literal=False, 
     return int(np.argmax(mag)), float(np.max(mag)), sd
 
 
+def sync_search_time_domain(in0, first_start, stride, n_trials, prm: ModemParams):
+    """Every trial of the sliding search (sync_trial at first_start + t*stride) WITHOUT a transform per trial.
+
+    Derivation (M0 windows s = 0..M0-1 at p + s*L, synch bins S, y_k = X_k conj(zc_k)):
+        c[d; p] / p_est = sum_k X_k conj(zc_k) e^{+j2pi dk/N} = sum_n x[p+n] g[(d - n) mod N],
+        g[m] = sum_{k in S} conj(zc_k) e^{+j2pi km/N}          (N times the inverse DFT of the scattered conj(ZC)).
+    With h[m] = g[(-m) mod N] and the linear sliding correlation r(q) = sum_m x[q+m] h[m]:
+        c[d; p] / p_est = r(p+d) + sum_{i=1..d} (x[p+d-i] - x[p+d-i+N]) h[N-i]
+    i.e. for every position q = p+d the CP+1 delays are r(q) plus a PREFIX SUM over i.  The unit-power factor needs
+    sum_{k in S} |X_k|^2 = N sum_n |x[p+n]|^2 - sum_{k not in S} |X_k|^2, the second term from a direct DFT of the
+    few unused bins (DC and the band edge).  Same numbers as sync_trial up to rounding; this is the specification of
+    the fast acquisition path, not what the reference executes.
+    Returns (peak[n_trials], delay[n_trials]).  Windows past the end are zero-padded like np.fft.fft.
+    """
+    N, CP, L, M0, nsb = prm.nfft, prm.cp_len, prm.sym_len, prm.m0, prm.num_synch_bins
+    assert nsb < N, "the +-N/2 alias case (num_synch_bins == nfft) keeps the transform path"
+    sb = bins_used(nsb, N)
+    zc = zc_for(prm)
+    last = first_start + (n_trials - 1) * stride
+    need = last + CP + (M0 - 1) * L + 2 * N + 1
+    x = np.zeros(max(need, len(in0)), dtype=complex)
+    x[:len(in0)] = np.asarray(in0, dtype=complex)
+    n_q = last - first_start + CP + 1                                  # positions q = first_start .. last + CP
+    num = np.zeros((n_q, CP + 1), dtype=complex)                        # num[q - first_start, d] = c[d; q-d] / p_est
+    unused = np.setdiff1d(np.arange(N), sb)
+    pw = np.zeros(last - first_start + 1)                                # sum over windows of sum_{k in S} |X_k|^2 at p
+    nn = np.arange(N)
+    for s in range(M0):
+        Z = np.zeros(N, dtype=complex)
+        Z[sb] = np.conj(zc[s * nsb:(s + 1) * nsb])
+        g = N * np.fft.ifft(Z)
+        h = g[(-nn) % N]
+        xs = x[s * L:]
+        # r(q) for q = first_start .. last + CP
+        seg = xs[first_start:first_start + n_q + N - 1]
+        r = np.correlate(seg, np.conj(h), mode="valid")                  # sum_m seg[q+m] * h[m]
+        for qi in range(n_q):
+            q = first_start + qi
+            acc = r[qi]
+            num[qi, 0] += acc
+            for i in range(1, CP + 1):
+                a = q - i
+                dl = (xs[a] - xs[a + N]) if a >= 0 else (0.0 - xs[a + N] if a + N >= 0 else 0.0)
+                acc = acc + dl * h[N - i]
+                num[qi, i] += acc
+        # window energy and the unused bins at every p
+        e = np.abs(xs[first_start:first_start + (last - first_start) + N]) ** 2
+        ce = np.concatenate(([0.0], np.cumsum(e)))
+        energy = ce[N:N + last - first_start + 1] - ce[:last - first_start + 1]
+        pw += N * energy
+        for k in unused:
+            ph = np.exp(-2j * np.pi * k * nn / N)
+            for pi in range(last - first_start + 1):
+                pw[pi] -= abs(np.dot(xs[first_start + pi:first_start + pi + N], ph)) ** 2
+    peak = np.zeros(n_trials)
+    delay = np.zeros(n_trials, dtype=np.int32)
+    for t in range(n_trials):
+        pi = t * stride
+        mags = np.array([abs(num[pi + d, d]) for d in range(CP + 1)])
+        p_est = np.sqrt(prm.mm / pw[pi]) if pw[pi] > 0 else 0.0
+        delay[t] = int(np.argmax(mags))
+        peak[t] = p_est * mags[delay[t]]
+    return peak, delay
+
+
 def sync_trial_cfo(in0, start, prm: ModemParams, cfo, zc=None, bank=None, literal=False, nus=None):
     """The trial repeated for every row of the CFO bank; the hypothesis with the largest peak wins
     (first one on ties, np.argmax).  SynchEstAndFO.py:247-277.

@@ -238,3 +238,34 @@ def test_on_device_loopback_counts_match_oracle_counters():
     assert lb.run(n_frames, seed=6)["summary"]["bit_errors"] == 0
     taps = lb.taps_random(n_frames, [0.2, 0.7, 0.1], 3)
     assert lb.run(n_frames, seed=7, taps=taps, noise_sigma=0.01)["summary"]["frames"] == n_frames
+
+
+@pytest.mark.parametrize("kw,n_frames", [
+    (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2), 40),
+    (dict(nfft=256, cp_len=20, num_synch_bins=254, num_data_bins=200, m0=1, d=2, bps=4), 9),
+    (dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=1, bps=2), 2),
+], ids=["N64", "N256", "N2048"])
+def test_time_domain_acquisition_equals_transform_search(kw, n_frames, monkeypatch):
+    """Stride-1 search of the utsa configuration: the time-domain kernel (no transform per trial) against the
+    per-trial transform kernel on the same capture, incl. windows that run off the end of the buffer, and against
+    the oracle's derivation on a stretch of trials."""
+    m = make(dict(kw, snr=100, compat="utsa", zc_root=23))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    _, rx = synth(cfg, prm, n_frames, 5, noise=1e-3)
+    d_rx = torch.from_numpy(rx).cuda()
+    n_trials = len(rx) - cfg.cp_len - 7                      # the last trials read past the end (zero padding)
+    monkeypatch.setenv("OFDM_SYNC_TD", "0")
+    pk0, dl0 = (a.cpu().numpy() for a in m.sync_search(d_rx, cfg.cp_len, 1, n_trials))
+    monkeypatch.setenv("OFDM_SYNC_TD", "1")
+    pk1, dl1 = (a.cpu().numpy() for a in m.sync_search(d_rx, cfg.cp_len, 1, n_trials))
+    assert rel_err(pk1, pk0) < RTOL
+    strong = pk0 > 0.3 * prm.mm
+    assert strong.sum() >= n_frames
+    assert np.array_equal(dl1[strong], dl0[strong])
+    assert np.mean(dl1 == dl0) > 0.99                        # elsewhere only near-ties between noise lags may differ
+    n_chk = min(300, n_trials)
+    rp, rd = oo.sync_search_time_domain(rx, cfg.cp_len, 1, n_chk, prm)
+    assert rel_err(pk1[:n_chk], rp) < RTOL
+    s2 = rp > 0.3 * prm.mm
+    assert np.array_equal(dl1[:n_chk][s2], rd[s2])
