@@ -328,6 +328,7 @@ struct ofdm_plan {
     size_t stage_bytes[NSLOT];
     void *small;                   // per-frame results of the host-buffer receiver (delay, peak, locked)
     size_t small_bytes;
+    int td_smem_set;               // dynamic shared memory the time-domain search kernel has been allowed on this device
 };
 
 static const KernelSet *kset_for(int log2n) {
@@ -635,10 +636,9 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
     if (td_on && stride == 1 && pl->dev.h_td && !pl->dev.n_cfo && first_start >= 0) {
         const int N = pl->prm.nfft, CP = pl->prm.cp_len, TP = TD_TQ - CP;
         const int smem = (TD_TQ + N + CP) * 8 + N * 8 + TD_TQ * 8 + TD_TQ * 4;
-        static int max_set = 0;
-        if (smem > max_set) {
+        if (smem > pl->td_smem_set) {                          // per plan, i.e. per device: the attribute belongs to the context
             CU(cudaFuncSetAttribute(rx_sync_search_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "ofdm_rx_sync_search(attr)");
-            max_set = smem;
+            pl->td_smem_set = smem;
         }
         const long long tiles = (n_trials + TP - 1) / TP;
         rx_sync_search_td_kernel<<<(unsigned)tiles, TD_THREADS, smem, (cudaStream_t)stream>>>(
