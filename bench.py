@@ -188,7 +188,7 @@ def cpu_reference_rate(wname, target_seconds, literal=True, cores=None):
     import multiprocessing as mp
     w = WORKLOADS[wname]
     cores = cores or len(os.sched_getaffinity(0))
-    probe = 8 if w["nfft"] >= 1024 else 64
+    probe = 2 if w["nfft"] >= 1024 else 64          # the literal arithmetic takes seconds per LTE frame
     dt, _ = _cpu_chunk((wname, probe, 1, literal))
     per_frame = dt / probe
     frames_per_core = max(probe, int(target_seconds / per_frame))
