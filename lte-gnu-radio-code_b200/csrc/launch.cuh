@@ -72,15 +72,19 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     constexpr bool GSM = RxFOpts<LOG2N>::GSM, SB = RxFOpts<LOG2N>::SB;
     if (n_frames <= 0) return cudaSuccess;
     if (P.pil_k && P.n_cfo) return cudaErrorInvalidValue;       // the hypothesis bank is not combined with comb pilots
+    // the branch-free (dense) epilogue may want a different split of the transform over threads (CfgRxFD, fft_core.cuh)
+    using CD = CfgRxFD<LOG2N>;
+    constexpr int GD = GroupsFor<CD>::value;
 #define OFDM_LAUNCH_RXF(PIL, CFO, EPI, Q) OFDM_LAUNCH_RXF_(PIL, CFO, EPI, false, Q)
-#define OFDM_LAUNCH_RXF_(PIL, CFO, EPI, CPP, Q)                                                                         \
+#define OFDM_LAUNCH_RXF_(PIL, CFO, EPI, CPP, Q) OFDM_LAUNCH_RXF_C(C, G, PIL, CFO, EPI, CPP, Q)
+#define OFDM_LAUNCH_RXF_C(CC, GG, PIL, CFO, EPI, CPP, Q)                                                               \
     {                                                                                                                \
-        constexpr auto k = rx_frames_kernel<C, BPS, G, PIL, GSM, SB, CFO, EPI, CPP>;                                 \
-        int SM = Smem<C, G, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : G * (Q.ls_stride * 4 + Q.es_stride * 8));       \
-        cudaError_t e = plan_launch<k>(TH, SM, G, n_frames, sms, d);                                                 \
+        constexpr auto k = rx_frames_kernel<CC, BPS, GG, PIL, GSM, SB, CFO, EPI, CPP>;                               \
+        int SM = Smem<CC, GG, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : GG * (Q.ls_stride * 4 + Q.es_stride * 8));    \
+        cudaError_t e = plan_launch<k>(CC::T * GG, SM, GG, n_frames, sms, d);                                        \
         if (e != cudaSuccess) return e;                                                                              \
-        k<<<d.grid, TH, SM, st>>>(Q, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak, locked, hyp, \
-                                  H, eq, llr, hard);                                                                 \
+        k<<<d.grid, CC::T * GG, SM, st>>>(Q, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak,      \
+                                          locked, hyp, H, eq, llr, hard);                                            \
     }
     // The per-lane variant only knows the 64-QAM LLR staging of small transforms (api.cu); the bulk-store variant
     // (64-QAM only, see data_epilogue_bulk) needs 16-byte aligned rows and must not cost a resident CTA.
@@ -112,8 +116,8 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
                 else if (bulk) OFDM_LAUNCH_RXF(false, false, EPI_BULK, P)
             }
             // densely filled grids take the branch-free epilogue (same shared-memory footprint as the sparse one)
-            if (!bulk && dense && cpp) OFDM_LAUNCH_RXF_(false, false, EPI_DENSE, true, Qp)
-            else if (!bulk && dense) OFDM_LAUNCH_RXF(false, false, EPI_DENSE, Qp)
+            if (!bulk && dense && cpp) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE, true, Qp)
+            else if (!bulk && dense) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE, false, Qp)
             else if (!bulk && cpp) OFDM_LAUNCH_RXF_(false, false, EPI_SPARSE, true, Qp)
             else if (!bulk) OFDM_LAUNCH_RXF(false, false, EPI_SPARSE, Qp)
         }
@@ -121,6 +125,7 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     })
 #undef OFDM_LAUNCH_RXF
 #undef OFDM_LAUNCH_RXF_
+#undef OFDM_LAUNCH_RXF_C
     return cudaGetLastError();
 }
 
