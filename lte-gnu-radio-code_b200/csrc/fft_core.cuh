@@ -148,8 +148,10 @@ template <int LOG2N> struct PptRxF {
 };
 template <int LOG2N>
 using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N), OFDM_RX_LAY_PAD != 0>;
-// The dense-epilogue variant of the framed receiver (grids above 3/4 fill) at N = 2048: 16 points per thread (two
-// exchanges instead of three, half the barriers) is 5 % faster there, while the bulk-row LTE kernel loses 10 % with it.
+// The per-lane-epilogue variants of the framed receiver (sparse and dense) at N = 2048: 16 points per thread (two
+// exchanges instead of three, half the barriers) are 4-8 % faster there (B200: 1920-bin grid 16-QAM 0.345 -> 0.326 ms,
+// QPSK 0.311 -> 0.287 ms; LTE grid QPSK 0.539 -> 0.500 ms, 16-QAM 0.585 -> 0.561 ms), while the bulk-row 64-QAM kernel
+// loses 10 % with it (0.711 -> 0.788 ms) and keeps 8.
 #ifndef OFDM_PPT_RXFD_2048
 #define OFDM_PPT_RXFD_2048 16
 #endif

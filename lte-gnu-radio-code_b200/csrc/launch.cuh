@@ -72,7 +72,8 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     constexpr bool GSM = RxFOpts<LOG2N>::GSM, SB = RxFOpts<LOG2N>::SB;
     if (n_frames <= 0) return cudaSuccess;
     if (P.pil_k && P.n_cfo) return cudaErrorInvalidValue;       // the hypothesis bank is not combined with comb pilots
-    // the branch-free (dense) epilogue may want a different split of the transform over threads (CfgRxFD, fft_core.cuh)
+    // the per-lane epilogues (sparse and dense) may want a different split of the transform over threads than the
+    // bulk-row, pilot and hypothesis-bank variants (CfgRxFD, fft_core.cuh)
     using CD = CfgRxFD<LOG2N>;
     constexpr int GD = GroupsFor<CD>::value;
 #define OFDM_LAUNCH_RXF(PIL, CFO, EPI, Q) OFDM_LAUNCH_RXF_(PIL, CFO, EPI, false, Q)
@@ -118,8 +119,8 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
             // densely filled grids take the branch-free epilogue (same shared-memory footprint as the sparse one)
             if (!bulk && dense && cpp) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE, true, Qp)
             else if (!bulk && dense) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE, false, Qp)
-            else if (!bulk && cpp) OFDM_LAUNCH_RXF_(false, false, EPI_SPARSE, true, Qp)
-            else if (!bulk) OFDM_LAUNCH_RXF(false, false, EPI_SPARSE, Qp)
+            else if (!bulk && cpp) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_SPARSE, true, Qp)
+            else if (!bulk) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_SPARSE, false, Qp)
         }
         count_launch();
     })
