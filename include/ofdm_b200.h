@@ -106,7 +106,10 @@ int ofdm_tx_modulate(ofdm_plan *plan, const uint8_t *d_bits, float *d_time, int6
 /* RX sliding search: trial t opens its FFT window at sample first_start + t*stride.  For each
  * trial: M0 FFTs, synch-bin pick, unit-power normalise, (CP+1)-delay correlation with the ZC,
  * max / argmax.  Replaces the body of loop A up to the gate test (SynchAndChanEst.py:145-164,
- * synch_and_chan_est.py:148-168).  d_peak[t] = max|c|, d_delay[t] = argmax. */
+ * synch_and_chan_est.py:148-168).  d_peak[t] = max|c|, d_delay[t] = argmax.
+ * With stride == 1, one synch symbol on every bin but DC and the band edge (the gr-utsa_ofdm block's configuration)
+ * and no hypothesis bank, the same values come from a time-domain kernel that needs no transform per trial
+ * (environment OFDM_SYNC_TD=0 forces the per-trial transforms, 1 the plain time-domain kernel). */
 int ofdm_rx_sync_search(ofdm_plan *plan, const float *d_time, int64_t n_samples, int64_t first_start,
                         int64_t stride, int64_t n_trials, float *d_peak, int32_t *d_delay, void *stream);
 
