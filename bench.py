@@ -235,27 +235,14 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
+def make_batch(m, w, nf, rank=0):
+    """The synthetic batch of one rank, generated on the device (not timed): random payload -> CUDA transmitter ->
+    test-bench channel (the reference's 5 taps, or an independent random 5-tap multipath per frame) + Philox AWGN.
+    Returns (packed payload bits, tx waveform, taps, rx waveform) as device tensors.  tests/test_gpu_bench_parity.py
+    rebuilds exactly this batch and checks slices of it against the oracle."""
     import torch
-    import torch.distributed as dist
-    from ofdm_b200 import Modem, ModemConfig, launch_count
-
-    wname = args.workload
-    w = WORKLOADS[wname]
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # keep stdout for the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = ModemConfig(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
-                      num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100.0, gate=0.5,
-                      noise_var=2 * w["noise_sigma"] ** 2, cp_first=w.get("cp_first", 0), slot_syms=w.get("slot_syms", 0))
-    m = Modem(cfg)
-    nf, nf_total, scaling = frames_for_rank(w, rank, world)
+    cfg, dev = m.cfg, m.device
     nsym = nf * cfg.d
-
-    # synthetic batch, generated on the device (not timed): payload -> CUDA TX -> 5-tap channel + AWGN
     g = torch.Generator(device=dev)
     g.manual_seed(2024 + rank)
     bits = torch.randint(0, 256, (nsym * cfg.hard_stride,), dtype=torch.uint8, device=dev, generator=g)
@@ -268,6 +255,35 @@ def run_ours(args, rank, world, local_rank):
     else:
         taps = torch.tensor(REF_TAPS / np.linalg.norm(REF_TAPS), dtype=torch.complex64, device=dev)
     rx = m.channel_awgn(tx, nf, taps, w["noise_sigma"], 2024 + rank)
+    return bits, tx, taps, rx
+
+
+def modem_config(w):
+    from ofdm_b200 import ModemConfig
+    return ModemConfig(nfft=w["nfft"], cp_len=w["cp_len"], num_synch_bins=w["num_synch_bins"],
+                       num_data_bins=w["num_data_bins"], m0=w["m0"], d=w["d"], bps=w["bps"], snr=100.0, gate=0.5,
+                       noise_var=2 * w["noise_sigma"] ** 2, cp_first=w.get("cp_first", 0), slot_syms=w.get("slot_syms", 0))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ofdm_b200 import Modem, launch_count
+
+    wname = args.workload
+    w = WORKLOADS[wname]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # keep stdout for the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = modem_config(w)
+    m = Modem(cfg)
+    nf, nf_total, scaling = frames_for_rank(w, rank, world)
+    nsym = nf * cfg.d
+
+    bits, tx, taps, rx = make_batch(m, w, nf, rank)
     out = m.rx_frames(rx, nf)
     torch.cuda.synchronize()
 

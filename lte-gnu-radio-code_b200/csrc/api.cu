@@ -184,6 +184,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 
 // test-bench channel: y[f,n] = sum_t h[f,t] x[f,n-t] + sigma*(g1 + j g2), frames independent
+// (MultiAntennaSystem.py:221-231 rx_signal_gen + :257-260 additive_noise; oracle: channel_awgn_frames.  Sample i of
+// the batch draws its noise from Philox counter (i, 0, 0) under key `seed`: u1, u2 from the first two words, Box-Muller.)
 __global__ void channel_kernel(const float2 *__restrict__ x, float2 *__restrict__ y, long long n_frames, int frame_len,
                                const float2 *__restrict__ taps, int n_taps, int taps_per_frame, float sigma,
                                unsigned long long seed) {
@@ -200,9 +202,11 @@ __global__ void channel_kernel(const float2 *__restrict__ x, float2 *__restrict_
                                           make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
             const float u1 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f;
             const float u2 = ((float)r.y + 0.5f) * 2.3283064365386963e-10f;
-            const float rad = sigma * sqrtf(-2.f * __logf(u1));
+            // full-precision logf / sincospif (not the fast intrinsics): the oracle restates this stream in double
+            // precision (oracle/ofdm_oracle.py: philox_awgn) and the parity test holds the two to 1e-5 of sigma
+            const float rad = sigma * sqrtf(-2.f * logf(u1));
             float sn, cs;
-            __sincosf(6.283185307179586f * u2, &sn, &cs);
+            sincospif(2.f * u2, &sn, &cs);
             acc.x += rad * cs;
             acc.y += rad * sn;
         }
@@ -468,6 +472,20 @@ struct ofdm_plan {
     int td_smem_set;               // dynamic shared memory the time-domain search kernel has been allowed on this device
 };
 
+// Makes the plan's device current for the duration of one entry point (and restores the caller's), so a plan created
+// on cuda:1 launches there -- with that device's SM count and shared-memory attributes -- whatever device the calling
+// thread happens to have current.
+struct DevGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DevGuard(const ofdm_plan *pl) {
+        if (pl && cudaGetDevice(&prev) == cudaSuccess && prev != pl->device) switched = cudaSetDevice(pl->device) == cudaSuccess;
+    }
+    ~DevGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 static const KernelSet *kset_for(int log2n) {
     switch (log2n) {
         case 6: return &kset_6;
@@ -697,6 +715,7 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
 }
 
 int ofdm_plan_destroy(ofdm_plan *pl) {
+    DevGuard dev_guard(pl);
     if (!pl) return OFDM_OK;
     cudaFree(pl->d_tables);
     if (pl->d_cfo) cudaFree(pl->d_cfo);
@@ -723,6 +742,7 @@ int ofdm_plan_frame_len(const ofdm_plan *pl) {
 }
 
 int ofdm_tx_modulate(ofdm_plan *pl, const uint8_t *d_bits, float *d_time, int64_t n_frames, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_time || (!d_bits && pl->prm.d > 0) || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_tx_modulate: bad argument%s");
     CU(pl->ks->tx(pl->dev, d_bits, (float2 *)d_time, n_frames * (pl->prm.m0 + pl->prm.d), (cudaStream_t)stream, pl->sms),
@@ -731,12 +751,12 @@ int ofdm_tx_modulate(ofdm_plan *pl, const uint8_t *d_bits, float *d_time, int64_
 }
 
 int ofdm_plan_set_cfo_bank(ofdm_plan *pl, const double *cycles_per_sample, int32_t n_hyp, int32_t phase_continuous) {
+    DevGuard dev_guard(pl);
     if (!pl || n_hyp < 0 || n_hyp > 64 || (n_hyp > 0 && !cycles_per_sample))
         return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: bad argument (0..64 hypotheses)%s");
     if (n_hyp > 0 && pl->prm.pilot_spacing) return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: not available with comb pilots%s");
     if (n_hyp > 0 && pl->dev.cp_extra) return fail(OFDM_EINVAL, "ofdm_plan_set_cfo_bank: not available with a CP pattern%s");
     if (pl->d_cfo) cudaFree(pl->d_cfo);
-    if (pl->small) cudaFree(pl->small);
     pl->d_cfo = nullptr;
     pl->dev.n_cfo = 0;
     pl->dev.cfo = nullptr;
@@ -765,13 +785,16 @@ int ofdm_plan_set_cfo_bank(ofdm_plan *pl, const double *cycles_per_sample, int32
 
 int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first_start, int64_t stride,
                             int64_t n_trials, float *d_peak, int32_t *d_delay, int32_t *d_hyp, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_trials == 0) return OFDM_OK;
     if (!pl || !d_time || !d_peak || !d_delay || n_trials < 0 || stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_sync_search: bad argument%s");
     // stride-1 search of the utsa configuration: time-domain kernel, no transform per trial (OFDM_SYNC_TD=0 disables it)
     // (OFDM_SYNC_TD: 0 = per-trial transforms, 1 = plain time-domain kernel, 2 = register-blocked time-domain kernel)
     const char *td_env = getenv("OFDM_SYNC_TD");
     const int td_mode = td_env ? atoi(td_env) : OFDM_SYNC_TD_DEFAULT;
-    if (td_mode != 0 && stride == 1 && pl->dev.h_td && !pl->dev.n_cfo && first_start >= 0) {
+    // (a tile yields TD_TQ - CP trials for TD_TQ N-tap correlations: only worth it -- and only well-defined -- while
+    // the prefix is at most half a tile; longer prefixes fall through to the per-trial transforms)
+    if (td_mode != 0 && stride == 1 && pl->dev.h_td && !pl->dev.n_cfo && first_start >= 0 && 2 * pl->prm.cp_len <= TD_TQ) {
         const int N = pl->prm.nfft, CP = pl->prm.cp_len, TP = TD_TQ - CP, A = (CP + 7) & ~7;
         const int smem = td_mode == 2 ? 8 * ((TD_TQ + N + A) / 8 + 1) * 8 + N * 8 + 8 * (TD_TQ / 8 + 1) * 12
                                       : (TD_TQ + N + CP) * 8 + N * 8 + TD_TQ * 8 + TD_TQ * 4;
@@ -789,6 +812,8 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
                 pl->dev, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay);
         count_launch();
         CU(cudaGetLastError(), "ofdm_rx_sync_search(td)");
+        // no hypothesis bank on this path: the winning hypothesis is 0, as the per-trial kernel reports it
+        if (d_hyp) CU(cudaMemsetAsync(d_hyp, 0, (size_t)n_trials * sizeof(int32_t), (cudaStream_t)stream), "ofdm_rx_sync_search(hyp)");
         return OFDM_OK;
     }
     CU(pl->ks->sync_search(pl->dev, (const float2 *)d_time, n_samples, first_start, stride, n_trials, d_peak, d_delay,
@@ -804,6 +829,7 @@ int ofdm_rx_sync_search(ofdm_plan *pl, const float *d_time, int64_t n_samples, i
 int ofdm_rx_chanest_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_pos,
                         const int32_t *d_delay, const int32_t *d_hyp, int64_t n_locks, float *d_H, float *d_htime,
                         float *d_synch_eq, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_locks == 0) return OFDM_OK;
     if (!pl || !d_time || !d_pos || !d_delay || !d_H || n_locks < 0) return fail(OFDM_EINVAL, "ofdm_rx_chanest: bad argument%s");
     CU(pl->ks->chanest(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_pos, d_delay, d_hyp, n_locks,
@@ -819,6 +845,7 @@ int ofdm_rx_chanest(ofdm_plan *pl, const float *d_time, int64_t n_samples, const
 int ofdm_rx_demod_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, const int64_t *d_start,
                       const int32_t *d_delay, const int32_t *d_hrow, const int32_t *d_hyp, const float *d_H, int64_t n_sym,
                       float *d_eq, float *d_llr, uint8_t *d_hard, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_sym == 0) return OFDM_OK;
     if (!pl || !d_time || !d_start || !d_delay || !d_hrow || !d_H || !d_eq || n_sym < 0)
         return fail(OFDM_EINVAL, "ofdm_rx_demod: bad argument%s");
@@ -836,6 +863,7 @@ int ofdm_rx_demod(ofdm_plan *pl, const float *d_time, int64_t n_samples, const i
 int ofdm_rx_frames_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_t first, int64_t frame_stride,
                        int64_t n_frames, int32_t *d_delay, float *d_peak, uint8_t *d_locked, int32_t *d_hyp, float *d_H,
                        float *d_eq, float *d_llr, uint8_t *d_hard, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_time || !d_delay || !d_peak || !d_locked || !d_eq || n_frames < 0)
         return fail(OFDM_EINVAL, "ofdm_rx_frames: bad argument%s");
@@ -853,6 +881,7 @@ int ofdm_rx_frames(ofdm_plan *pl, const float *d_time, int64_t n_samples, int64_
 
 int ofdm_bit_recovery(ofdm_plan *pl, const float *d_in, int64_t n, float *d_llr0, float *d_llr1, uint8_t *d_hard,
                       double *d_ws, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n == 0) return OFDM_OK;
     if (!pl || !d_in || !d_llr0 || !d_llr1 || !d_hard || !d_ws || n < 0) return fail(OFDM_EINVAL, "ofdm_bit_recovery: bad argument%s");
     if (n == 0) return OFDM_OK;
@@ -871,6 +900,7 @@ int ofdm_bit_recovery(ofdm_plan *pl, const float *d_in, int64_t n, float *d_llr0
 
 int ofdm_dsss_despread(ofdm_plan *pl, const float *d_eq, int64_t n_rows, int32_t row_len, const float *d_code, int32_t sf,
                        float *d_out, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_rows == 0) return OFDM_OK;
     if (!pl || !d_eq || !d_code || !d_out || n_rows < 0 || sf < 1 || row_len < sf)
         return fail(OFDM_EINVAL, "ofdm_dsss_despread: bad argument%s");
@@ -887,6 +917,7 @@ int ofdm_dsss_despread(ofdm_plan *pl, const float *d_eq, int64_t n_rows, int32_t
 
 int ofdm_counters(ofdm_plan *pl, const uint8_t *d_bits_rx, const uint8_t *d_bits_tx, const float *d_eq,
                   const uint8_t *d_locked, int64_t n_frames, double *d_cnt, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_bits_tx || !d_cnt || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_counters: bad argument%s");
     if (n_frames == 0) return OFDM_OK;
@@ -903,6 +934,7 @@ int ofdm_counters(ofdm_plan *pl, const uint8_t *d_bits_rx, const uint8_t *d_bits
 
 int ofdm_channel_awgn(ofdm_plan *pl, const float *d_tx, float *d_rx, int64_t n_frames, const float *d_taps,
                       int32_t n_taps, int32_t taps_per_frame, float noise_sigma, uint64_t seed, void *stream) {
+    DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !d_tx || !d_rx || !d_taps || n_taps < 1 || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_channel_awgn: bad argument%s");
     if (n_frames == 0) return OFDM_OK;
@@ -944,6 +976,7 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, int64_t first, int64_t frame_stride,
                         int64_t n_frames, int32_t *h_delay, float *h_peak, uint8_t *h_locked, float *h_eq, float *h_llr,
                         uint8_t *h_hard) {
+    DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !h_time || !h_eq || n_frames < 0 || frame_stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_frames_host: bad argument%s");
     if (n_frames == 0) return OFDM_OK;
@@ -1021,6 +1054,7 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
 }
 
 int ofdm_tx_modulate_host(ofdm_plan *pl, const uint8_t *h_bits, float *h_time, int64_t n_frames) {
+    DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
     if (!pl || !h_time || (!h_bits && pl->prm.d > 0) || n_frames < 0) return fail(OFDM_EINVAL, "ofdm_tx_modulate_host: bad argument%s");
     if (n_frames == 0) return OFDM_OK;

@@ -20,10 +20,13 @@ struct LaunchDims {
 void count_launch();
 
 // grid = min(#CTAs needed, resident CTAs on the whole device): persistent groups stride over the work.
-// The occupancy query is cached per (device, dynamic shared-memory size).
+// The occupancy query is cached per device and dynamic shared-memory size (one slot per device: a process that drives
+// several GPUs from several threads keeps every device's answer, and the attribute is only ever raised).
 template <auto kernel>
 static inline cudaError_t plan_launch(int threads, int &smem, int groups, long long work, int sms, LaunchDims &dims) {
-    static int cached_dev = -1, cached_bps = 0, cached_smem = -1, max_smem = -1;
+    constexpr int MAXDEV = 64;
+    struct Slot { int smem = -1, bps = 0, max_smem = -1; };
+    static Slot slots[MAXDEV];
     static std::mutex mu;                      // blocks of one flowgraph call work() from their own threads
     std::lock_guard<std::mutex> lock(mu);
     // tuning aid: OFDM_SMEM_PAD=<bytes> inflates the dynamic shared-memory request to lower occupancy
@@ -32,25 +35,26 @@ static inline cudaError_t plan_launch(int threads, int &smem, int groups, long l
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev != cached_dev || smem != cached_smem) {
-        if (dev != cached_dev || smem > max_smem) {
+    if (dev < 0 || dev >= MAXDEV) return cudaErrorInvalidDevice;
+    Slot &c = slots[dev];
+    if (smem != c.smem) {
+        if (smem > c.max_smem) {
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            max_smem = smem;
+            c.max_smem = smem;
         }
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_bps, kernel, threads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.bps, kernel, threads, smem);
         if (e != cudaSuccess) return e;
-        if (cached_bps < 1) cached_bps = 1;
-        cached_dev = dev;
-        cached_smem = smem;
+        if (c.bps < 1) c.bps = 1;
+        c.smem = smem;
     }
     const long long need = (work + groups - 1) / groups;
-    const long long cap = (long long)sms * cached_bps;
+    const long long cap = (long long)sms * c.bps;
     long long grid = need < cap ? need : cap;
     if (grid < 1) grid = 1;
     dims.grid = (int)grid;
     dims.iters = (int)((work + grid * groups - 1) / (grid * groups));
-    dims.ctas_per_sm = cached_bps;
+    dims.ctas_per_sm = c.bps;
     return cudaSuccess;
 }
 

@@ -128,8 +128,8 @@ def _ptr(t):
     return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(_torch().cuda.current_stream(device).cuda_stream)
 
 
 class Modem:
@@ -170,15 +170,21 @@ class Modem:
         phase_continuous=True (extension) continues the phasor from the buffer origin instead of restarting it at
         every window, which is what a real carrier offset needs."""
         nu = np.asarray([float(f) / float(fs) for f in fo_range], dtype=np.float64)
-        self.n_cfo = int(nu.size)
         with _torch().cuda.device(self.device):
             _lib.check(_lib.lib().ofdm_plan_set_cfo_bank(self._h, C.c_void_p(nu.ctypes.data if nu.size else 0), nu.size,
                                                          1 if phase_continuous else 0))
+        self.n_cfo = int(nu.size)                        # only once the plan has accepted the bank
 
     # ---- helpers ---------------------------------------------------------------------------
+    def _stream(self):
+        """The plan's device's current stream (the library itself makes that device current for the launch, so a
+        Modem on cuda:1 works while cuda:0 is torch's current device)."""
+        return _stream(self.device)
+
     def _c64(self, x):
         torch = _torch()
         assert x.dtype == torch.complex64 and x.is_cuda and x.is_contiguous()
+        assert x.device == self.device, "tensor on %s handed to a plan on %s" % (x.device, self.device)
         return x
 
     def empty(self, shape, dtype):
@@ -193,7 +199,7 @@ class Modem:
         assert bits.numel() >= n_frames * cfg.d * cfg.hard_stride
         if out is None:
             out = self.empty((n_frames * cfg.frame_len,), torch.complex64)
-        _lib.check(_lib.lib().ofdm_tx_modulate(self._h, _ptr(bits), _ptr(out), n_frames, _stream()))
+        _lib.check(_lib.lib().ofdm_tx_modulate(self._h, _ptr(bits), _ptr(out), n_frames, self._stream()))
         return out
 
     # ---- RX, framed (throughput path) --------------------------------------------------------
@@ -217,7 +223,7 @@ class Modem:
         _lib.check(_lib.lib().ofdm_rx_frames_cfo(
             self._h, _ptr(rx), rx.numel(), first, fs, n_frames, _ptr(o["delay"]), _ptr(o["peak"]),
             _ptr(o["locked"]), _ptr(o.get("hyp")), _ptr(o.get("h")), _ptr(o["eq"]), _ptr(o.get("llr")),
-            _ptr(o.get("hard")), _stream()))
+            _ptr(o.get("hard")), self._stream()))
         return o
 
     # ---- RX, modular (what the stream blocks' work() drives) ---------------------------------
@@ -233,11 +239,11 @@ class Modem:
         delay = packed[n_trials:2 * n_trials]
         if not self.n_cfo:
             _lib.check(_lib.lib().ofdm_rx_sync_search(self._h, _ptr(rx), rx.numel(), first_start, stride, n_trials,
-                                                      _ptr(peak), _ptr(delay), _stream()))
+                                                      _ptr(peak), _ptr(delay), self._stream()))
             return peak, delay
         hyp = packed[2 * n_trials:3 * n_trials]
         _lib.check(_lib.lib().ofdm_rx_sync_search_cfo(self._h, _ptr(rx), rx.numel(), first_start, stride, n_trials,
-                                                      _ptr(peak), _ptr(delay), _ptr(hyp), _stream()))
+                                                      _ptr(peak), _ptr(delay), _ptr(hyp), self._stream()))
         return peak, delay, hyp
 
     def chanest(self, rx, pos, delay, want_aux=False, hyp=None):
@@ -254,7 +260,7 @@ class Modem:
             self.aux_flat = aux
         assert hyp is None or (hyp.dtype == torch.int32 and hyp.numel() == n)
         _lib.check(_lib.lib().ofdm_rx_chanest_cfo(self._h, _ptr(rx), rx.numel(), _ptr(pos), _ptr(delay), _ptr(hyp), n,
-                                                  _ptr(h), _ptr(ht), _ptr(se), _stream()))
+                                                  _ptr(h), _ptr(ht), _ptr(se), self._stream()))
         return h, ht, se
 
     def demod(self, rx, start, delay, hrow, h, want_llr=False, want_hard=False, hyp=None):
@@ -269,7 +275,7 @@ class Modem:
         assert hyp is None or (hyp.dtype == torch.int32 and hyp.numel() == n)
         _lib.check(_lib.lib().ofdm_rx_demod_cfo(self._h, _ptr(rx), rx.numel(), _ptr(start), _ptr(delay), _ptr(hrow),
                                                 _ptr(hyp), _ptr(self._c64(h)), n, _ptr(eq), _ptr(llr), _ptr(hard),
-                                                _stream()))
+                                                self._stream()))
         return eq, llr, hard
 
     # ---- DSSS despreading (legacy receiver) ------------------------------------------------------
@@ -282,7 +288,7 @@ class Modem:
         n_rows, row_len = eq.shape
         sf = code.numel()
         out = self.empty((n_rows, row_len // sf), torch.complex64)
-        _lib.check(_lib.lib().ofdm_dsss_despread(self._h, _ptr(eq), n_rows, row_len, _ptr(code), sf, _ptr(out), _stream()))
+        _lib.check(_lib.lib().ofdm_dsss_despread(self._h, _ptr(eq), n_rows, row_len, _ptr(code), sf, _ptr(out), self._stream()))
         return out
 
     # ---- legacy demapper, counters, test-bench channel ----------------------------------------
@@ -295,7 +301,7 @@ class Modem:
         hard = self.empty((2 * n,), torch.uint8)
         ws = self.empty((2,), torch.float64)
         _lib.check(_lib.lib().ofdm_bit_recovery(self._h, _ptr(x), n, _ptr(llr0), _ptr(llr1), _ptr(hard), _ptr(ws),
-                                                _stream()))
+                                                self._stream()))
         return llr0, llr1, hard
 
     def counters(self, bits_tx, n_frames, bits_rx=None, eq=None, locked=None, cnt=None):
@@ -303,7 +309,7 @@ class Modem:
         if cnt is None:
             cnt = torch.zeros(8, dtype=torch.float64, device=self.device)
         _lib.check(_lib.lib().ofdm_counters(self._h, _ptr(bits_rx), _ptr(bits_tx), _ptr(eq), _ptr(locked), n_frames,
-                                            _ptr(cnt), _stream()))
+                                            _ptr(cnt), self._stream()))
         return cnt
 
     def channel_awgn(self, tx, n_frames, taps, noise_sigma, seed, out=None):
@@ -316,7 +322,7 @@ class Modem:
         if out is None:
             out = torch.empty_like(tx)
         _lib.check(_lib.lib().ofdm_channel_awgn(self._h, _ptr(tx), _ptr(out), n_frames, _ptr(taps), n_taps,
-                                                per_frame, float(noise_sigma), int(seed), _stream()))
+                                                per_frame, float(noise_sigma), int(seed), self._stream()))
         return out
 
     # ---- host-buffer entry points (numpy in, numpy out; copies inside the call) -----------------

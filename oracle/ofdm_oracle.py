@@ -343,6 +343,70 @@ def add_awgn(x, noise_var, rng):
 
 
 # --------------------------------------------------------------------------------------------
+# a7 (test bench), batched form used by the benchmarks: per-frame FIR + counter-based AWGN.
+# The reference draws its noise from NumPy's global generator (MultiAntennaSystem.py:257-260, unseeded), which no
+# other implementation can reproduce; the batched generator therefore uses Philox4x32-10 (Salmon, Moraes, Dror, Shaw,
+# "Parallel random numbers: as easy as 1, 2, 3", SC'11 -- the Random123 reference algorithm) keyed by (seed) and
+# counted by the absolute sample index, so the CUDA generator and this restatement produce the same stream.
+# --------------------------------------------------------------------------------------------
+PHILOX_M0, PHILOX_M1 = 0xD2511F53, 0xCD9E8D57
+PHILOX_W0, PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(counter, key):
+    """counter: uint32 [..., 4], key: (k0, k1) -> uint32 [..., 4].  Ten rounds of
+    (c0, c1, c2, c3) <- (hi(M1*c2) ^ c1 ^ k0, lo(M1*c2), hi(M0*c0) ^ c3 ^ k1, lo(M0*c0)), key bumped by the Weyl
+    constants between rounds."""
+    c = np.asarray(counter, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (c[..., i].copy() for i in range(4))
+    k0, k1 = np.uint64(int(key[0]) & 0xFFFFFFFF), np.uint64(int(key[1]) & 0xFFFFFFFF)
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(PHILOX_M0) * c0
+        p1 = np.uint64(PHILOX_M1) * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & m32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(PHILOX_W0)) & m32
+        k1 = (k1 + np.uint64(PHILOX_W1)) & m32
+    return np.stack((c0, c1, c2, c3), axis=-1).astype(np.uint32)
+
+
+def philox_awgn(n, sigma, seed, first=0):
+    """Complex noise samples first..first+n-1 of the stream `seed`: per-component standard deviation sigma.
+    Sample i uses counter (i mod 2^32, i >> 32, 0, 0) and key (seed mod 2^32, seed >> 32); its first two output
+    words become u1, u2 = (float32(word) + 0.5) * 2^-32 (formed in float32 like the CUDA generator), and the sample is
+    the Box-Muller pair sigma * sqrt(-2 ln u1) * (cos 2 pi u2 + j sin 2 pi u2), evaluated here in double precision."""
+    i = np.arange(first, first + n, dtype=np.uint64)
+    ctr = np.zeros((n, 4), dtype=np.uint64)
+    ctr[:, 0] = i & np.uint64(0xFFFFFFFF)
+    ctr[:, 1] = i >> np.uint64(32)
+    r = philox4x32_10(ctr, (int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF))
+    scale = np.float32(2.0 ** -32)
+    u1 = ((r[:, 0].astype(np.float32) + np.float32(0.5)) * scale).astype(np.float64)
+    u2 = ((r[:, 1].astype(np.float32) + np.float32(0.5)) * scale).astype(np.float64)
+    rad = float(sigma) * np.sqrt(-2.0 * np.log(u1))
+    return rad * (np.cos(TWO_PI * u2) + 1j * np.sin(TWO_PI * u2))
+
+
+def channel_awgn_frames(tx, n_frames, frame_len, taps, sigma=0.0, seed=0):
+    """Batched test-bench channel: every frame is filtered on its own -- y[f, n] = sum_t h[f, t] x[f, n - t], the
+    np.convolve of MultiAntennaSystem.py:221-231 truncated to the frame, with nothing leaking in from the previous
+    frame -- then sigma * philox noise is added (the `additive_noise` step, :257-260, with a reproducible stream).
+    taps: [n_taps] shared by every frame or [n_frames, n_taps] one row per frame."""
+    x = np.asarray(tx, dtype=complex).reshape(n_frames, frame_len)
+    h = np.asarray(taps, dtype=complex)
+    y = np.empty_like(x)
+    for f in range(n_frames):
+        hf = h[f] if h.ndim == 2 else h
+        y[f] = np.convolve(x[f], hf)[:frame_len]
+    y = y.reshape(-1)
+    if sigma > 0:
+        y = y + philox_awgn(y.size, sigma, seed)
+    return y
+
+
+# --------------------------------------------------------------------------------------------
 # a8-a10  one synchronisation trial
 # --------------------------------------------------------------------------------------------
 def delay_bank(prm: ModemParams):
