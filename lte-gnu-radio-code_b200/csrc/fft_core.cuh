@@ -23,6 +23,50 @@
 
 namespace ofdm {
 
+// Complex arithmetic on Blackwell's packed FP32 pipe.  A complex number is one 64-bit register pair (re, im) and
+// add.rn.f32x2 / mul.rn.f32x2 / fma.rn.f32x2 (FADD2 / FMUL2 / FFMA2) work on both halves at once; their operands
+// take a half-swap (.LO_HI), per-half signs and a 32-bit broadcast (.F32) for free, so
+//   a +- b         = 1 FADD2                          (2 FADD before)
+//   a * w          = FMUL2(a, w.x) ; FFMA2(swap(a), (-w.y, +w.y), .)     (2 FMUL + 2 FFMA before)
+//   a * (+-i)      = nothing: the swap and the signs fold into the instruction that consumes the product
+// which halves the floating-point instruction count of every butterfly (the N >= 1024 kernels are bound by
+// instruction issue).  -DOFDM_F32X2=0 builds the scalar forms for A/B runs.
+#ifndef OFDM_F32X2
+#define OFDM_F32X2 1
+#endif
+__device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+// ptxas 12.9 copies the result of a packed instruction into a fresh register pair (two MOVs) when that result is the
+// data operand of a 64-bit store; naming the two halves as scalars first (an empty asm, no instruction) makes it store
+// from the pair the instruction wrote.  Used on every value that goes from packed arithmetic to shared or global memory.
+__device__ __forceinline__ float2 pin(float2 r) {
+#if OFDM_F32X2
+    asm("" : "+f"(r.x), "+f"(r.y));
+#endif
+    return r;
+}
+#if OFDM_F32X2
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return __ffma2_rn(cswap(a), make_float2(-b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
+    return __ffma2_rn(cswap(a), make_float2(b.y, -b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// a + s * b with a real s
+__device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return __ffma2_rn(b, make_float2(s, s), a); }
+// acc + (a.x^2, a.y^2): a power sum kept as two partial sums, added up once at the end
+__device__ __forceinline__ float2 cpow_acc(float2 acc, float2 a) { return __ffma2_rn(a, a, acc); }
+// acc + a * b
+__device__ __forceinline__ float2 cmul_acc(float2 acc, float2 a, float2 b) {
+    return __ffma2_rn(cswap(a), make_float2(-b.y, b.y), __ffma2_rn(a, make_float2(b.x, b.x), acc));
+}
+// acc + w * (a.x^2, a.y^2)
+__device__ __forceinline__ float2 cpow_acc_w(float2 acc, float2 a, float w) {
+    return __ffma2_rn(__fmul2_rn(a, make_float2(w, w)), a, acc);
+}
+#else
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -32,6 +76,15 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return make_float2(fmaf(s, b.x, a.x), fmaf(s, b.y, a.y)); }
+__device__ __forceinline__ float2 cpow_acc(float2 acc, float2 a) { return make_float2(fmaf(a.x, a.x, acc.x), fmaf(a.y, a.y, acc.y)); }
+__device__ __forceinline__ float2 cmul_acc(float2 acc, float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, fmaf(-a.y, b.y, acc.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, acc.y)));
+}
+__device__ __forceinline__ float2 cpow_acc_w(float2 acc, float2 a, float w) {
+    return make_float2(fmaf(w * a.x, a.x, acc.x), fmaf(w * a.y, a.y, acc.y));
+}
+#endif
 __device__ __forceinline__ float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
 // multiply by -i (forward) or +i (inverse)
 template <bool INV> __device__ __forceinline__ float2 mul_mi(float2 a) {
@@ -213,16 +266,10 @@ template <bool INV> __device__ __forceinline__ void bfly8(float2 (&a)[8]) {
     float2 b1 = cadd(a[1], a[5]), c1 = csub(a[1], a[5]);
     float2 b2 = cadd(a[2], a[6]), c2 = csub(a[2], a[6]);
     float2 b3 = cadd(a[3], a[7]), c3 = csub(a[3], a[7]);
-    // c_n *= W8^n  (forward W8 = exp(-i*pi/4); inverse = conjugate)
-    if (INV) {
-        c1 = make_float2((c1.x - c1.y) * h, (c1.x + c1.y) * h);
-        c2 = make_float2(-c2.y, c2.x);
-        c3 = make_float2((-c3.x - c3.y) * h, (c3.x - c3.y) * h);
-    } else {
-        c1 = make_float2((c1.x + c1.y) * h, (c1.y - c1.x) * h);
-        c2 = make_float2(c2.y, -c2.x);
-        c3 = make_float2((c3.y - c3.x) * h, (-c3.x - c3.y) * h);
-    }
+    // c_n *= W8^n  (forward W8 = exp(-i*pi/4); inverse = conjugate):  W8 c = h (c -+ i c),  W8^3 c = h (-c -+ i c)
+    c1 = cscale(cadd(c1, mul_mi<INV>(c1)), h);
+    c2 = mul_mi<INV>(c2);
+    c3 = cscale(csub(mul_mi<INV>(c3), c3), h);
     bfly4<INV>(b0, b1, b2, b3);   // X0 X2 X4 X6
     bfly4<INV>(c0, c1, c2, c3);   // X1 X3 X5 X7
     a[0] = b0; a[2] = b1; a[4] = b2; a[6] = b3;
@@ -243,12 +290,10 @@ template <bool INV> __device__ __forceinline__ float2 mul_w16(float2 a, int m) {
         default: wr = -c; wi = s; break;   // 9
     }
     if (INV) wi = -wi;
-    if (m == 4) return make_float2(-a.y * wi, a.x * wi);
-    if (m == 2 || m == 6) {                 // |wr| == |wi|: two adds, two multiplies
-        const float sr = a.x * wr, si = a.y * wr;                       // wr = +-h
-        return (wi == wr) ? make_float2(sr - si, sr + si) : make_float2(sr + si, si - sr);
-    }
-    return make_float2(fmaf(a.x, wr, -a.y * wi), fmaf(a.x, wi, a.y * wr));
+    if (m == 4) return mul_mi<INV>(a);
+    if (m == 2) return cscale(cadd(a, mul_mi<INV>(a)), h);                  // W8   = h (1 -+ i)
+    if (m == 6) return cscale(csub(mul_mi<INV>(a), a), h);                  // W8^3 = h (-1 -+ i)
+    return cmul(a, make_float2(wr, wi));
 }
 
 // 4-point DFT whose second and / or third input is known to be zero (Z1: a1 == 0, Z2: a2 == 0): x + 0 is not folded
@@ -407,7 +452,7 @@ template <class C, bool INV, int GROUPS, int P, bool SB = false, bool TWR = fals
             if (!SB) pp ^= 1;
             const int e = (j / Ns) * (Ns * C::PPT) + (j & (Ns - 1));
 #pragma unroll
-            for (int q = 0; q < C::PPT; ++q) buf[lay<C, P>(e + q * Ns)] = v[q];
+            for (int q = 0; q < C::PPT; ++q) buf[lay<C, P>(e + q * Ns)] = pin(v[q]);
             group_sync<C::T, GROUPS>(gid);
 #pragma unroll
             for (int m = 0; m < C::PPT; ++m) v[m] = buf[lay<C, P>(j + m * C::T)];

@@ -137,6 +137,7 @@ template <int T, int PPT> __device__ __forceinline__ int bin_out(const BinMap &b
 #define OFDM_RX_CS_MIN_LOG2N 7
 #endif
 template <bool CS = true, class V> __device__ __forceinline__ void st_out(V *p, V v) {
+    if constexpr (std::is_same<V, float2>::value) v = pin(v);
     if (CS) __stcs(p, v); else *p = v;
 }
 
@@ -524,12 +525,12 @@ __device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2
     const float2 *zb = P.zc_bin + s * N + j;
     const float *wb = P.w_bin + j;
 #pragma unroll
+    float2 pw2 = make_float2(pw, 0.f);                        // weighted power as two partial sums (re^2, im^2)
     for (int m = 0; m < PPT; ++m) {
-        pw = fmaf(__ldg(wb + m * T), cabs2(v[m]), pw);
-        const float2 z = __ldg(zb + m * T);
-        ys[m].x = fmaf(v[m].x, z.x, fmaf(-v[m].y, z.y, ys[m].x));
-        ys[m].y = fmaf(v[m].x, z.y, fmaf(v[m].y, z.x, ys[m].y));
+        pw2 = cpow_acc_w(pw2, v[m], __ldg(wb + m * T));
+        ys[m] = cmul_acc(ys[m], v[m], __ldg(zb + m * T));
     }
+    pw = pw2.x + pw2.y;
     if (P.dup_bin >= 0) {
 #pragma unroll
         for (int m = 0; m < PPT; ++m)
@@ -610,13 +611,13 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     // per-bin dependency chains are one basic block the scheduler can interleave.  For grids where most bins are used
     // (chosen at launch from the fill ratio, launch_rx_frames).
     const unsigned mask = D.map.mask;
-    float pw = 0.f;
+    float2 pw2 = make_float2(0.f, 0.f);                       // sum |Y|^2 as two partial sums (re^2, im^2)
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
-        if (DENSE) pw += (mask & (1u << m)) ? cabs2(v[m]) : 0.f;
-        else if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
+        if (DENSE) pw2 = cpow_acc_w(pw2, v[m], (mask & (1u << m)) ? 1.f : 0.f);
+        else if (mask & (1u << m)) pw2 = cpow_acc(pw2, v[m]);
     }
-    pw = group_sum<T, GROUPS>(pw, redf, j, gid);
+    const float pw = group_sum<T, GROUPS>(pw2.x + pw2.y, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
     // 64-QAM: a bin's six LLRs are 24 bytes, so per-lane stores would leave every 32-byte sector
@@ -715,11 +716,11 @@ __device__ __forceinline__ void data_epilogue_bulk(const DevParams &P, const Dat
     constexpr int T = C::T, PPT = C::PPT;
     const unsigned mask = D.map.mask;
     if (j == 0) bulk_wait_read();
-    float pw = 0.f;
+    float2 pw2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < PPT; ++m)
-        if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
-    pw = group_sum<T, GROUPS>(pw, redf, j, gid);
+        if (mask & (1u << m)) pw2 = cpow_acc(pw2, v[m]);
+    const float pw = group_sum<T, GROUPS>(pw2.x + pw2.y, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
     float2 *eqp = es + D.map.base_p, *eqn = es + (D.map.base_n - (PPT / 2) * T);
@@ -734,7 +735,7 @@ __device__ __forceinline__ void data_epilogue_bulk(const DevParams &P, const Dat
                 for (int m = c; m < c + CH; ++m) {
                     const bool used = (mask & (1u << m)) != 0;
                     const float2 z = cscale(cmul(G.get(m), v[m]), p0);
-                    if (used) (m < PPT / 2 ? eqp : eqn)[m * T] = z;
+                    if (used) (m < PPT / 2 ? eqp : eqn)[m * T] = pin(z);
                     float Lb[BPS];
                     unsigned bits;
                     D.dem.run(z, Lb, bits);
@@ -758,7 +759,7 @@ __device__ __forceinline__ void data_epilogue_bulk(const DevParams &P, const Dat
     for (int m = 0; m < PPT; ++m) {
         if (CH == 0 && (mask & (1u << m))) {
             const float2 z = cscale(cmul(G.get(m), v[m]), p0);
-            (m < PPT / 2 ? eqp : eqn)[m * T] = z;
+            (m < PPT / 2 ? eqp : eqn)[m * T] = pin(z);
             if (soft || hard) {
                 float Lb[BPS];
                 unsigned bits;
@@ -801,11 +802,11 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
                                                     uint8_t *__restrict__ hard_out) {
     constexpr int T = C::T, PPT = C::PPT;
     const unsigned mask = D.map.mask;
-    float pw = 0.f;
+    float2 pw2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < PPT; ++m)
-        if (mask & (1u << m)) pw = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, pw));
-    pw = group_sum<T, GROUPS>(pw, redf, j, gid);
+        if (mask & (1u << m)) pw2 = cpow_acc(pw2, v[m]);
+    const float pw = group_sum<T, GROUPS>(pw2.x + pw2.y, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;
     float2 z[C::PPT];
 #pragma unroll
@@ -1466,20 +1467,20 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
         // quarters; the branch is on a kernel parameter, hence uniform.
         auto finish = [&](auto quarter) {
             constexpr int MCP = decltype(quarter)::value ? 3 * PPT / 4 : 0;      // first m whose sample can be in the CP
-            float3 acc = make_float3(0.f, 0.f, 0.f);
+            float2 pw2 = make_float2(0.f, 0.f), mean2 = make_float2(0.f, 0.f);      // (re^2, im^2) partial sums; sum of the prefix copies
 #pragma unroll
             for (int m = 0; m < PPT; ++m) {
                 // sum of t: the N body samples add up to N * X[0], and the DC bin is never used (data, pilots and the
                 // Zadoff-Chu bins all skip it), so only the prefix copies contribute to the symbol's mean
                 if (m < MCP) {
-                    acc.x += cabs2(v[m]);
+                    pw2 = cpow_acc(pw2, v[m]);
                 } else {
                     const float c = (j >= ncp0 - m * T) ? 1.f : 0.f;
-                    acc.x = fmaf(c + 1.f, cabs2(v[m]), acc.x);
-                    acc.y = fmaf(c, v[m].x, acc.y);
-                    acc.z = fmaf(c, v[m].y, acc.z);
+                    pw2 = cpow_acc_w(pw2, v[m], c + 1.f);
+                    mean2 = caxpy(mean2, c, v[m]);
                 }
             }
+            float3 acc = make_float3(pw2.x + pw2.y, mean2.x, mean2.y);
             acc = group_sum3<T, GROUPS>(acc, redf, j, gid);
             // v holds N*ifft(X) = N*t.  Reference: t -> t*sqrt(L/sum|t|^2) -> /sqrt(var); with the first
             // factor applied the mean power is 1, so var = 1 - |mean|^2 and both steps are one scale g.
