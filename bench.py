@@ -203,6 +203,22 @@ def cpu_reference_rate(wname, target_seconds, literal=True, cores=None):
                               wall_seconds=wall)
 
 
+def config_for(wname, world):
+    """The `config` object of the JSON line: the workload definition only, identical in both arms (the size of the
+    sample a run actually timed is reported beside it, as `sample`)."""
+    w = WORKLOADS[wname]
+    nf, nf_total, _ = frames_for_rank(w, 0, world)
+    rd, wr = algorithmic_bytes(w, nf)
+    cp_pattern = [w["cp_first"], w["slot_syms"]] if w.get("cp_first") else None
+    return {"workload": wname, "nfft": w["nfft"], "cp_len": w["cp_len"], "cp_pattern": cp_pattern,
+            "num_synch_bins": w["num_synch_bins"], "num_data_bins": w["num_data_bins"], "synch_dat": [w["m0"], w["d"]],
+            "bps": w["bps"], "frames_per_gpu": nf, "data_symbols_per_gpu": nf * w["d"], "frames_total": nf_total,
+            "channel": "independent random 5-tap multipath per frame + AWGN" if w.get("multipath")
+            else "reference 5-tap channel + AWGN", "outputs": "eq c64 + llr f32 + packed hard bits",
+            "cache": "inputs+outputs per step = %.2f GB per GPU, far larger than the 126 MB L2" % ((rd + wr) / 1e9),
+            "parallelism": "frames sharded by rank, no data-path collective"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -216,18 +232,18 @@ def run_reference(args, rank, world):
         if i >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates))
-    L = w["nfft"] + w["cp_len"]
+    sample = ("%d frames (%d data symbols) per step: literal NumPy restatement of the reference block arithmetic "
+              "(dense diag matmuls kept), one process per core; GNU Radio scheduler overhead excluded (not installed)"
+              % (info["frames"], info["data_symbols"]))
     out = {"impl": "reference", "metric": "rx_ofdm_data_symbols_per_s", "value": v, "unit": "symbols/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * info["seconds"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": wname, **{k: w[k] for k in ("nfft", "cp_len", "num_data_bins", "bps", "m0", "d")}},
+           "config": config_for(wname, world),
+           "sample": {"frames_per_step": info["frames"], "data_symbols_per_step": info["data_symbols"],
+                      "note": "a bounded sample of the workload in `config`; rates are per data symbol"},
            "msamples_per_s": v * frame_len(w) / w["d"] / 1e6,
-           "cpu_baseline": {"value": v, "unit": "symbols/s", "cores": info["cores"], "kind": "port",
-                            "sample": "%d frames (%d data symbols) per step: literal NumPy restatement of the "
-                                      "reference block arithmetic (dense diag matmuls kept), one process per core; "
-                                      "GNU Radio scheduler overhead excluded (not installed)"
-                                      % (info["frames"], info["data_symbols"])},
+           "cpu_baseline": {"value": v, "unit": "symbols/s", "cores": info["cores"], "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "symbols/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -265,6 +281,101 @@ def modem_config(w):
                        noise_var=2 * w["noise_sigma"] ** 2, cp_first=w.get("cp_first", 0), slot_syms=w.get("slot_syms", 0))
 
 
+def bind_near_gpu(local_rank):
+    """Run this rank -- and therefore allocate its pinned host buffers, first touch -- on the CPUs of the NUMA node its
+    GPU hangs off, when the box exposes more than one node.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if len(nodes) < 2:
+            return "1 NUMA node visible: nothing to bind"
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]
+        node = int(open(path).read()) if os.path.exists(path) else -1
+        if node < 0:
+            return "%d NUMA nodes, GPU node unknown" % len(nodes)
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return "GPU on node %d, none of its CPUs are available to this process" % node
+        os.sched_setaffinity(0, allowed)
+        return "bound to NUMA node %d (%d CPUs) before allocating pinned buffers" % (node, len(allowed))
+    except Exception as e:                                   # binding is an optimisation, never a failure
+        return "not bound (%s)" % type(e).__name__
+
+
+def time_device(fn, steps, warmup, barrier, local_rank, launch_count):
+    """Device time of `steps` back-to-back calls of fn on the current stream (CUDA events), with clocks sampled."""
+    import torch
+    for _ in range(max(3, warmup)):
+        fn()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    barrier()
+    launches = launch_count() - l0
+    clocks = sampler.stop()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[steps]), per, launches, clocks
+
+
+def roofline_entry(wname, w, nf, k_ms, kernel, direction="rx"):
+    peak, peak_src = measured_peak_gbs()
+    cfg_bytes = algorithmic_bytes(w, nf)
+    if direction == "rx":
+        alg = sum(cfg_bytes)
+    else:                                                     # transmitter: packed payload in, waveform out
+        hs = (w["num_data_bins"] * w["bps"] + 7) // 8
+        alg = nf * w["d"] * hs + nf * frame_len(w) * 8
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel": kernel,
+         "kernel_ms": k_ms, "frac_of_nominal_8TBs": achieved / 8000.0}
+    if direction == "rx":
+        r["traffic"] = profiled_traffic(wname)
+        if r["traffic"]:
+            # the same launch measured on the bytes DRAM actually moved (ncu capture under profiles/): below the
+            # algorithmic figure where cyclic-prefix lines are skipped by address and never fetched
+            r["achieved_dram"] = r["traffic"] / (k_ms * 1e-3) / 1e9
+            r["frac_dram"] = r["achieved_dram"] / peak
+    return r
+
+
+def pinned_outputs(torch, cfg, nf, want_eq=True, want_llr=True, want_hard=True):
+    nsym = nf * cfg.d
+    h = {"delay": torch.empty(nf, dtype=torch.int32, pin_memory=True),
+         "peak": torch.empty(nf, dtype=torch.float32, pin_memory=True),
+         "locked": torch.empty(nf, dtype=torch.uint8, pin_memory=True),
+         "eq": torch.empty((nsym, cfg.num_data_bins), dtype=torch.complex64, pin_memory=True) if want_eq else None,
+         "llr": torch.empty((nsym, cfg.num_data_bins * cfg.bps), dtype=torch.float32, pin_memory=True) if want_llr else None,
+         "hard": torch.empty((nsym, cfg.hard_stride), dtype=torch.uint8, pin_memory=True) if want_hard else None}
+    return h, {k: (None if v is None else v.numpy()) for k, v in h.items()}
+
+
+def time_e2e(m, rx_np, nf, h_np, steps, barrier, reduce_max):
+    import torch
+    for _ in range(2):
+        m.rx_frames_host(rx_np, nf, out=h_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.rx_frames_host(rx_np, nf, out=h_np)
+    torch.cuda.synchronize()
+    return reduce_max((time.perf_counter() - t0) / steps)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -274,61 +385,42 @@ def run_ours(args, rank, world, local_rank):
     w = WORKLOADS[wname]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_near_gpu(local_rank)
     if world > 1:
         # keep stdout for the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    cfg = modem_config(w)
-    m = Modem(cfg)
-    nf, nf_total, scaling = frames_for_rank(w, rank, world)
-    nsym = nf * cfg.d
-
-    bits, tx, taps, rx = make_batch(m, w, nf, rank)
-    out = m.rx_frames(rx, nf)
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg = modem_config(w)
+    m = Modem(cfg)
+    nf, nf_total, scaling = frames_for_rank(w, rank, world)
+    nsym = nf * cfg.d
+    bits, tx, taps, rx = make_batch(m, w, nf, rank)
+    out = m.rx_frames(rx, nf)
+    torch.cuda.synchronize()
+
     # ---- device-resident throughput (`value`) -----------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        m.rx_frames(rx, nf, out=out)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for i in range(args.steps):
-        m.rx_frames(rx, nf, out=out)
-        ev[i + 1].record()
-    barrier()
-    launches = launch_count() - l0
-    clocks = sampler.stop()
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[args.steps])
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    total_ms, per_launch_ms, launches, clocks = time_device(lambda: m.rx_frames(rx, nf, out=out), args.steps, args.warmup,
+                                                            barrier, local_rank, launch_count)
+    ms_per_step = reduce_max(total_ms) / args.steps
     value = nf_total * cfg.d / (ms_per_step * 1e-3)
 
-    # ---- TX throughput, same batch (reported beside it) -------------------------------------------
-    for _ in range(3):
-        m.tx_modulate(bits, nf, out=tx)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    # ---- TX throughput, same batch (reported beside it; rewrites tx with identical content) ---------
     tx_steps = max(3, min(args.steps, 20))
-    for _ in range(tx_steps):
-        m.tx_modulate(bits, nf, out=tx)
-    e1.record()
-    torch.cuda.synchronize()
-    tx_ms = e0.elapsed_time(e1) / tx_steps
-    # regenerate rx (tx buffer was rewritten with identical content)
+    tx_total, tx_per, tx_launches, tx_clocks = time_device(lambda: m.tx_modulate(bits, nf, out=tx), tx_steps, 3, barrier,
+                                                           local_rank, launch_count)
+    tx_ms = tx_total / tx_steps
 
     # ---- BER / EVM: counters on each GPU, one NCCL all-reduce ------------------------------------
     cnt = m.counters(bits, nf, bits_rx=out["hard"], eq=out["eq"], locked=out["locked"])
@@ -336,74 +428,93 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     cnt = cnt.cpu().numpy()
 
-    # ---- end to end through the host-buffer C-ABI entry point (`e2e`) -----------------------------
+    # ---- end to end through the host-buffer C-ABI entry point (`e2e`), per output set ---------------
     h_rx = torch.empty(rx.shape, dtype=torch.complex64, pin_memory=True)
     h_rx.copy_(rx)
-    h_out = {"delay": torch.empty(nf, dtype=torch.int32, pin_memory=True),
-             "peak": torch.empty(nf, dtype=torch.float32, pin_memory=True),
-             "locked": torch.empty(nf, dtype=torch.uint8, pin_memory=True),
-             "eq": torch.empty((nsym, cfg.num_data_bins), dtype=torch.complex64, pin_memory=True),
-             "llr": torch.empty((nsym, cfg.num_data_bins * cfg.bps), dtype=torch.float32, pin_memory=True),
-             "hard": torch.empty((nsym, cfg.hard_stride), dtype=torch.uint8, pin_memory=True)}
-    h_np = {k: v.numpy() for k, v in h_out.items()}
     rx_np = h_rx.numpy()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        m.rx_frames_host(rx_np, nf, out=h_np)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        m.rx_frames_host(rx_np, nf, out=h_np)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    same = bool(np.array_equal(h_np["hard"], out["hard"].cpu().numpy()))
-    h2d = rx_np.nbytes
-    d2h = sum(v.nbytes for v in h_np.values())
+    e2e_sets = {}
+    same = None
+    for label, (weq, wllr, whard) in (("eq+llr+hard", (True, True, True)), ("llr+hard", (False, True, True)),
+                                       ("hard", (False, False, True))):
+        h_t, h_np = pinned_outputs(torch, cfg, nf, weq, wllr, whard)
+        e2e_s = time_e2e(m, rx_np, nf, h_np, e2e_steps, barrier, reduce_max)
+        ok = bool(np.array_equal(h_np["hard"], out["hard"].cpu().numpy()))
+        if wllr:
+            ok = ok and bool(np.array_equal(h_np["llr"], out["llr"].cpu().numpy()))
+        if label == "eq+llr+hard":
+            same = ok
+        e2e_sets[label] = {"value": nf_total * cfg.d / e2e_s, "unit": "symbols/s", "ms_per_step": 1e3 * e2e_s,
+                           "h2d_bytes_per_step": rx_np.nbytes,
+                           "d2h_bytes_per_step": sum(v.nbytes for v in h_np.values() if v is not None),
+                           "matches_device_path": ok}
+        del h_t, h_np
+    del h_rx, rx_np
+
+    # ---- the LTE workload (BASELINE configs[2]) beside the default line, RX and TX, with its own clocks ----
+    lte = None
+    if wname == "rx_n64_16qam_1m" and not args.no_lte:
+        del rx, tx, out, bits
+        torch.cuda.empty_cache()
+        lname = "rx_lte20_64qam"
+        lw = WORKLOADS[lname]
+        lm = Modem(modem_config(lw))
+        lnf = lw["n_frames"]
+        lbits, ltx, ltaps, lrx = make_batch(lm, lw, lnf, rank)
+        lout = lm.rx_frames(lrx, lnf)
+        lsteps = max(5, min(args.steps, 20))
+        lt, lper, ll, lclk = time_device(lambda: lm.rx_frames(lrx, lnf, out=lout), lsteps, 3, barrier, local_rank, launch_count)
+        lt_tx, lper_tx, ll_tx, lclk_tx = time_device(lambda: lm.tx_modulate(lbits, lnf, out=ltx), lsteps, 3, barrier,
+                                                     local_rank, launch_count)
+        lcnt = lm.counters(lbits, lnf, bits_rx=lout["hard"], eq=lout["eq"], locked=lout["locked"])
+        if world > 1:
+            dist.all_reduce(lcnt, op=dist.ReduceOp.SUM)
+        lcnt = lcnt.cpu().numpy()
+        l_ms, l_tx_ms = reduce_max(lt) / lsteps, reduce_max(lt_tx) / lsteps
+        lte = {"config": config_for(lname, world), "steps": lsteps,
+               "rx": {"value": lnf * world * lm.cfg.d / (l_ms * 1e-3), "unit": "symbols/s", "ms_per_step": l_ms,
+                      "msamples_per_s": lnf * world * lm.cfg.frame_len / (l_ms * 1e-3) / 1e6,
+                      "roofline": roofline_entry(lname, lw, lnf, float(np.mean(lper)), "rx_frames_kernel"),
+                      "gpu_launches": int(ll), "clocks": lclk},
+               "tx": {"value": lnf * world * lm.cfg.d / (l_tx_ms * 1e-3), "unit": "symbols/s", "ms_per_step": l_tx_ms,
+                      "roofline": roofline_entry(lname, lw, lnf, float(np.mean(lper_tx)), "tx_kernel", "tx"),
+                      "gpu_launches": int(ll_tx), "clocks": lclk_tx},
+               "quality": {"ber": lcnt[0] / max(lcnt[1], 1.0), "evm_rms": float(np.sqrt(lcnt[2] / max(lcnt[3], 1e-30))),
+                           "frames_locked": lcnt[4], "frames": lcnt[5]}}
+        del lbits, ltx, ltaps, lrx, lout, lm
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    rd, wr = algorithmic_bytes(w, nf)
-    peak, peak_src = measured_peak_gbs()
     k_ms = float(np.mean(per_launch_ms))
-    achieved = (rd + wr) / (k_ms * 1e-3) / 1e9
-    L = cfg.sym_len
-    tx_bytes = nsym * cfg.hard_stride + nf * cfg.frame_len * 8
+    main_set = e2e_sets["eq+llr+hard"]
     res = {
         "metric": "rx_ofdm_data_symbols_per_s", "value": value, "unit": "symbols/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wname, "nfft": cfg.nfft, "cp_len": cfg.cp_len,
-                   "cp_pattern": [cfg.cp_first, cfg.slot_syms] if cfg.cp_pattern else None, "num_synch_bins": cfg.num_synch_bins,
-                   "num_data_bins": cfg.num_data_bins, "synch_dat": [cfg.m0, cfg.d], "bps": cfg.bps,
-                   "frames_per_gpu": nf, "data_symbols_per_gpu": nsym, "frames_total": nf_total,
-                   "channel": "independent random 5-tap multipath per frame + AWGN" if w.get("multipath")
-                   else "reference 5-tap channel + AWGN", "outputs": "eq c64 + llr f32 + packed hard bits",
-                   "cache": "inputs+outputs per step = %.2f GB per GPU, far larger than the 126 MB L2" % ((rd + wr) / 1e9),
-                   "parallelism": "frames sharded by rank, no data-path collective"},
+        "config": config_for(wname, world),
         "msamples_per_s": value * cfg.frame_len / cfg.d / 1e6,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": profiled_traffic(wname), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": rd + wr, "kernel": "rx_frames_kernel",
-                     "kernel_ms": k_ms, "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": nf_total * cfg.d / e2e_s, "unit": "symbols/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+        "roofline": roofline_entry(wname, w, nf, k_ms, "rx_frames_kernel"),
+        "e2e": {"value": main_set["value"], "unit": "symbols/s", "h2d_bytes_per_step": main_set["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": main_set["d2h_bytes_per_step"], "ms_per_step": main_set["ms_per_step"],
+                "steps": e2e_steps,
                 "api": "Modem.rx_frames_host -> ofdm_rx_frames_host (pinned host buffers, chunked double-buffered "
-                       "copies inside the call)", "timer": "host perf_counter around synchronous calls",
-                "matches_device_path": same},
+                       "copies inside the call)", "timer": "host perf_counter around synchronous calls, max over ranks",
+                "matches_device_path": same, "host_numa": numa},
+        # the same call asked for fewer outputs: what a decoder on the host needs (LLRs + hard bits, or hard bits only)
+        "e2e_llr_hard": e2e_sets["llr+hard"], "e2e_hard_only": e2e_sets["hard"],
         "gpu_launches": int(launches),
         "clocks": clocks,
         "tx": {"value": nf_total * cfg.d / (tx_ms * 1e-3), "unit": "symbols/s", "ms_per_step": tx_ms,
-               "achieved_GBs": tx_bytes / (tx_ms * 1e-3) / 1e9, "frac": tx_bytes / (tx_ms * 1e-3) / 1e9 / peak},
+               "roofline": roofline_entry(wname, w, nf, float(np.mean(tx_per)), "tx_kernel", "tx"),
+               "gpu_launches": int(tx_launches), "clocks": tx_clocks},
         "quality": {"ber": cnt[0] / max(cnt[1], 1.0), "bits": cnt[1], "evm_rms": float(np.sqrt(cnt[2] / max(cnt[3], 1e-30))),
                     "frames_locked": cnt[4], "frames": cnt[5], "reduced_over": "NCCL all_reduce(sum)" if world > 1 else "1 GPU"},
     }
+    if lte is not None:
+        res["lte"] = lte
     if world == 1 and not args.no_cpu:
         v, info = cpu_reference_rate(wname, args.cpu_seconds / 2.0, literal=True)
         v2, info2 = cpu_reference_rate(wname, args.cpu_seconds / 4.0, literal=False)
@@ -432,6 +543,7 @@ def main():
     ap.add_argument("--workload", default="rx_n64_16qam_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-lte", action="store_true", help="skip the LTE workload reported beside the default line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OFDM_B200_ABI_VERSION 3
+#define OFDM_B200_ABI_VERSION 4
 
 enum {
     OFDM_OK = 0,
@@ -136,7 +136,9 @@ int ofdm_rx_demod(ofdm_plan *plan, const float *d_time, int64_t n_samples, const
  * leaves the SM.  Frame f's synch window opens at first + f*frame_stride + cp_len - sync_advance
  * (cp_first instead of cp_len with a CP pattern).
  * Outputs per frame: d_delay, d_peak, d_locked (peak > gate*M0*nsb); d_H nullable (nfft per frame).
- * Per data symbol (n_frames*D rows): d_eq, d_llr (nullable), d_hard (nullable). */
+ * Per data symbol (n_frames*D rows): d_eq, d_llr, d_hard -- each nullable, at least one given: a caller that feeds a
+ * decoder asks for LLRs (or hard bits) only and the equalised symbols (SynchAndChanEst.py:246, est_data_freq) are
+ * then never written. */
 int ofdm_rx_frames(ofdm_plan *plan, const float *d_time, int64_t n_samples, int64_t first,
                    int64_t frame_stride, int64_t n_frames, int32_t *d_delay, float *d_peak,
                    uint8_t *d_locked, float *d_H, float *d_eq, float *d_llr, uint8_t *d_hard,
@@ -202,11 +204,45 @@ int ofdm_channel_awgn(ofdm_plan *plan, const float *d_tx, float *d_rx, int64_t n
 
 /* Host-buffer convenience entry points (what a GNU Radio work() sees): stage through plan-owned
  * device buffers, copies inside the call, chunked and double-buffered on internal streams.
- * They synchronise before returning.  Pinned host memory makes the copies asynchronous. */
+ * They synchronise before returning.  Pinned host memory makes the copies asynchronous.
+ * ofdm_rx_frames_host: h_eq, h_llr, h_hard are each nullable (at least one given); an output that is not asked for is
+ * neither computed into device memory nor copied back. */
 int ofdm_rx_frames_host(ofdm_plan *plan, const float *h_time, int64_t n_samples, int64_t first,
                         int64_t frame_stride, int64_t n_frames, int32_t *h_delay, float *h_peak,
                         uint8_t *h_locked, float *h_eq, float *h_llr, uint8_t *h_hard);
 int ofdm_tx_modulate_host(ofdm_plan *plan, const uint8_t *h_bits, float *h_time, int64_t n_frames);
+
+/* One call per work() of the two live receiver blocks (the scheduler boundary,
+ * GRR/gr-RXOFDM/python/synch_and_chan_est.py:121-124,:140-142).  A block object owns the state the reference keeps in
+ * NumPy arrays between calls -- the lock counter, time_synch_ref, est_chan_freq_P -- plus pinned staging memory and a
+ * stream.  ofdm_rx_block_work copies the scheduler's samples in, runs loop A (sliding search, the lock rule and its
+ * bookkeeping, channel estimate of the new locks: SynchAndChanEst.py:143-219 / synch_and_chan_est.py:146-221) and
+ * loop B (data symbols: :221-248 / :224-250) on the device and synchronises ONCE; the result pointers refer to pinned
+ * memory owned by the block and stay valid until its next call.
+ *   mode 0 = gr-utsa_ofdm SynchAndChanEst: search stride 1, the first acceptable lock only, every data symbol of the
+ *            buffer equalised with channel row 0; `rows` = num_ofdm_symb state rows.
+ *   mode 1 = gr-RXOFDM synch_and_chan_est: stride cp_len-1, every acceptable lock (up to 100), the first data symbol
+ *            after each lock with that lock's row.
+ * The counter reset at the end of work() (:261 / :265) is applied; what the block writes to its output stream (and
+ * the "nothing on the first call" rule, :257) stays with the caller, which owns the output buffer. */
+typedef struct ofdm_rx_block ofdm_rx_block;
+typedef struct {
+    int32_t n_new_locks;            /* locks accepted by this call */
+    int32_t n_demod;                /* data symbols demodulated by this call */
+    int32_t obs_after_search;       /* corr_obs / cor_obs after loop A (before the reset) */
+    int32_t n_state_rows;           /* rows of time_synch_ref (1 in mode 0, 100 in mode 1) */
+    const int64_t *time_synch_ref;  /* [n_state_rows][3]: window start, delay, int(peak) */
+    const int32_t *new_rows;        /* [n_new_locks]: state row each new lock was stored in */
+    const float *chan_time;         /* [n_new_locks][nfft] complex64: ifft of the new estimates (:202) */
+    const float *synch_freq;        /* [n_new_locks][M0*nsb] complex64: equalised synch symbols (:213-218) */
+    const int32_t *demod_rows;      /* [n_demod]: row of est_data_freq each demodulated symbol belongs to */
+    const float *data_freq;         /* [n_demod][num_data_bins] complex64 */
+} ofdm_rx_block_result;
+int ofdm_rx_block_create(ofdm_plan *plan, int32_t mode, int32_t rows, ofdm_rx_block **block_out);
+int ofdm_rx_block_destroy(ofdm_rx_block *block);
+int ofdm_rx_block_work(ofdm_rx_block *block, const float *h_in, int64_t n_samples, ofdm_rx_block_result *result);
+/* est_chan_freq_P: copies the first `rows` channel rows (nfft complex64 each) to h_H. */
+int ofdm_rx_block_chan_freq(ofdm_rx_block *block, float *h_H, int32_t rows);
 
 /* Introspection for benchmarks: kernels launched by this library since load. */
 uint64_t ofdm_launch_count(void);

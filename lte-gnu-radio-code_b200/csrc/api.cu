@@ -8,8 +8,7 @@
 #include <new>
 #include <vector>
 
-#include "../../include/ofdm_b200.h"
-#include "launch.cuh"
+#include "plan.cuh"
 
 namespace ofdm {
 
@@ -17,19 +16,14 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
-static int fail(int code, const char *fmt, const char *a = "", long long b = 0) {
+int fail(int code, const char *fmt, const char *a, long long b) {
     snprintf(g_err, sizeof(g_err), fmt, a, b);
     return code;
 }
-static int cuda_fail(cudaError_t e, const char *where) {
+int cuda_fail(cudaError_t e, const char *where) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return OFDM_ECUDA;
 }
-#define CU(call, where)                                   \
-    do {                                                  \
-        cudaError_t e__ = (call);                         \
-        if (e__ != cudaSuccess) return cuda_fail(e__, where); \
-    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // misc kernels
@@ -453,38 +447,12 @@ rx_sync_search_td8_kernel(const DevParams P, const float2 *__restrict__ x, long 
 // ------------------------------------------------------------------------------------------------
 using namespace ofdm;
 
-struct ofdm_plan {
-    ofdm_params prm;
-    DevParams dev;
-    const KernelSet *ks;
-    int device, sms, log2n;
-    void *d_tables;                // one allocation holding every table
-    void *d_cfo;                   // frequency-offset hypothesis bank (optional)
-    // staging for the host-buffer entry points (grown on demand, freed with the plan)
-    static const int NSLOT = 3;
-    cudaStream_t st[NSLOT];
-    cudaEvent_t ev[NSLOT];
-    bool streams_made;
-    void *stage[NSLOT];
-    size_t stage_bytes[NSLOT];
-    void *small;                   // per-frame results of the host-buffer receiver (delay, peak, locked)
-    size_t small_bytes;
-    int td_smem_set;               // dynamic shared memory the time-domain search kernel has been allowed on this device
-};
-
-// Makes the plan's device current for the duration of one entry point (and restores the caller's), so a plan created
-// on cuda:1 launches there -- with that device's SM count and shared-memory attributes -- whatever device the calling
-// thread happens to have current.
-struct DevGuard {
-    int prev = -1;
-    bool switched = false;
-    explicit DevGuard(const ofdm_plan *pl) {
-        if (pl && cudaGetDevice(&prev) == cudaSuccess && prev != pl->device) switched = cudaSetDevice(pl->device) == cudaSuccess;
-    }
-    ~DevGuard() {
-        if (switched) cudaSetDevice(prev);
-    }
-};
+#ifndef OFDM_BULK16_MIN_N_DEFAULT
+#define OFDM_BULK16_MIN_N_DEFAULT 8192          // off until measured
+#endif
+#ifndef OFDM_BULK4_MIN_N_DEFAULT
+#define OFDM_BULK4_MIN_N_DEFAULT 8192
+#endif
 
 static const KernelSet *kset_for(int log2n) {
     switch (log2n) {
@@ -695,9 +663,15 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
         // small to pay for the extra barrier (N=64: 0.45 -> 0.49 ms), and 16-QAM / QPSK rows are already stored with
         // full sectors (N=2048, 1920 bins, 16-QAM: 0.353 -> 0.367 ms), so only the 64-QAM kernels have this variant.
         // Environment override for A/B runs: OFDM_BULK_MIN_N (a value above 4096 disables it).
-        const char *eb = getenv("OFDM_BULK_MIN_N");
-        const int bulk_min = eb ? atoi(eb) : 1024;
-        if (pk == 0 && N >= bulk_min && p->bps == 6 && ((ndb * p->bps) & 3) == 0 && (ndb & 1) == 0) {
+        // Below 64-QAM the per-lane stores already write full sectors, but the registers a store reads stay reserved
+        // until the memory system has taken the data, and the largest transforms (one CTA of 222-register threads per
+        // SM) stall on exactly that (ncu, N=4096 16-QAM: 26 % long-scoreboard on the demapper's register reuse).
+        // OFDM_BULK16_MIN_N / OFDM_BULK4_MIN_N: smallest N whose 16-QAM / QPSK-BPSK rows leave through the async proxy.
+        const char *eb = getenv("OFDM_BULK_MIN_N"), *eb16 = getenv("OFDM_BULK16_MIN_N"), *eb4 = getenv("OFDM_BULK4_MIN_N");
+        const int bulk_min = p->bps == 6 ? (eb ? atoi(eb) : 1024)
+                                         : (p->bps == 4 ? (eb16 ? atoi(eb16) : OFDM_BULK16_MIN_N_DEFAULT)
+                                                        : (eb4 ? atoi(eb4) : OFDM_BULK4_MIN_N_DEFAULT));
+        if (pk == 0 && N >= bulk_min && ((ndb * p->bps) & 3) == 0 && (ndb & 1) == 0) {
             D.bulk_rows = 1;
             D.ls_stride = ((ndb * p->bps + 31) & ~31) + 16;
             D.es_stride = ((ndb + 15) & ~15) + 8;
@@ -833,7 +807,7 @@ int ofdm_rx_chanest_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, c
     if (pl && n_locks == 0) return OFDM_OK;
     if (!pl || !d_time || !d_pos || !d_delay || !d_H || n_locks < 0) return fail(OFDM_EINVAL, "ofdm_rx_chanest: bad argument%s");
     CU(pl->ks->chanest(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_pos, d_delay, d_hyp, n_locks,
-                       (float2 *)d_H, (float2 *)d_htime, (float2 *)d_synch_eq, (cudaStream_t)stream, pl->sms),
+                       (float2 *)d_H, (float2 *)d_htime, (float2 *)d_synch_eq, (cudaStream_t)stream, pl->sms, nullptr, nullptr),
        "ofdm_rx_chanest");
     return OFDM_OK;
 }
@@ -850,7 +824,7 @@ int ofdm_rx_demod_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, con
     if (!pl || !d_time || !d_start || !d_delay || !d_hrow || !d_H || !d_eq || n_sym < 0)
         return fail(OFDM_EINVAL, "ofdm_rx_demod: bad argument%s");
     CU(pl->ks->rx_demod(pl->dev, (const float2 *)d_time, n_samples, (const long long *)d_start, d_delay, d_hrow, d_hyp,
-                        (const float2 *)d_H, n_sym, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms),
+                        (const float2 *)d_H, n_sym, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms, nullptr),
        "ofdm_rx_demod");
     return OFDM_OK;
 }
@@ -865,8 +839,8 @@ int ofdm_rx_frames_cfo(ofdm_plan *pl, const float *d_time, int64_t n_samples, in
                        float *d_eq, float *d_llr, uint8_t *d_hard, void *stream) {
     DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
-    if (!pl || !d_time || !d_delay || !d_peak || !d_locked || !d_eq || n_frames < 0)
-        return fail(OFDM_EINVAL, "ofdm_rx_frames: bad argument%s");
+    if (!pl || !d_time || !d_delay || !d_peak || !d_locked || n_frames < 0 || (!d_eq && !d_llr && !d_hard))
+        return fail(OFDM_EINVAL, "ofdm_rx_frames: bad argument (at least one of eq / llr / hard is needed)%s");
     CU(pl->ks->rx_frames(pl->dev, (const float2 *)d_time, n_samples, first, frame_stride, n_frames, d_delay, d_peak,
                          d_locked, d_hyp, (float2 *)d_H, (float2 *)d_eq, d_llr, d_hard, (cudaStream_t)stream, pl->sms),
        "ofdm_rx_frames");
@@ -978,7 +952,8 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
                         uint8_t *h_hard) {
     DevGuard dev_guard(pl);
     if (pl && n_frames == 0) return OFDM_OK;
-    if (!pl || !h_time || !h_eq || n_frames < 0 || frame_stride < 1) return fail(OFDM_EINVAL, "ofdm_rx_frames_host: bad argument%s");
+    if (!pl || !h_time || (!h_eq && !h_llr && !h_hard) || n_frames < 0 || frame_stride < 1)
+        return fail(OFDM_EINVAL, "ofdm_rx_frames_host: bad argument (at least one of eq / llr / hard is needed)%s");
     if (n_frames == 0) return OFDM_OK;
     int rc = ensure_streams(pl);
     if (rc) return rc;
@@ -1037,11 +1012,12 @@ int ofdm_rx_frames_host(ofdm_plan *pl, const float *h_time, int64_t n_samples, i
         if (hi < lo) hi = lo;
         CU(cudaMemcpyAsync(din, h_time + 2 * lo, (size_t)(hi - lo) * 8, cudaMemcpyHostToDevice, st), "H2D");
         CU(pl->ks->rx_frames(pl->dev, (const float2 *)din, hi - lo, first + f0 * frame_stride - lo, frame_stride, nf, ddl + f0,
-                             dpk + f0, dlk + f0, nullptr, nullptr, (float2 *)deq, h_llr ? dll : nullptr, h_hard ? dhd : nullptr, st, pl->sms),
+                             dpk + f0, dlk + f0, nullptr, nullptr, h_eq ? (float2 *)deq : nullptr, h_llr ? dll : nullptr,
+                             h_hard ? dhd : nullptr, st, pl->sms),
            "ofdm_rx_frames_host(kernel)");
         if (h_llr)
             CU(cudaMemcpyAsync(h_llr + f0 * p.d * ndb * p.bps, dll, (size_t)nf * p.d * ndb * p.bps * 4, cudaMemcpyDeviceToHost, st), "D2H");
-        CU(cudaMemcpyAsync(h_eq + 2 * f0 * p.d * ndb, deq, (size_t)nf * p.d * ndb * 8, cudaMemcpyDeviceToHost, st), "D2H");
+        if (h_eq) CU(cudaMemcpyAsync(h_eq + 2 * f0 * p.d * ndb, deq, (size_t)nf * p.d * ndb * 8, cudaMemcpyDeviceToHost, st), "D2H");
         if (h_hard) CU(cudaMemcpyAsync(h_hard + f0 * p.d * hs, dhd, (size_t)nf * p.d * hs, cudaMemcpyDeviceToHost, st), "D2H");
         f0 += nf;
     }

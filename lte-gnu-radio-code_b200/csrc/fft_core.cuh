@@ -100,19 +100,23 @@ __host__ __device__ constexpr int fft_ns(int log2n, int ppt, int p) {
     return 1 << (fft_lp(ppt) * (p < log2n / fft_lp(ppt) ? p : log2n / fft_lp(ppt)));
 }
 // shared twiddle table: pass p >= 1 holds rows of Ns entries, row for multiplier q entry r = W_N^(q*r*N/(Ns*R)).
-// Full table: rows q = 1..R-1.  Chained table (CH): rows q = 1, 2, 4, .. only; the other multipliers are
-// products of those (3 = 1*2, 5 = 1*4, ...), which trades shared-memory reads for FMA-pipe work.
+// Full table (CH 0): rows q = 1..R-1.  Chained table (CH 1): rows q = 1, 2, 4, .. only; the other multipliers are
+// products of those (3 = 1*2, 5 = 1*4, ...), which trades shared-memory reads for FMA-pipe work.  Power table (CH 2):
+// row q = 1 only, W^q = W^(q/2) * W^(q - q/2) -- one shared-memory read per butterfly and R-2 complex multiplies, two
+// packed instructions each.  With the butterflies on the packed pipe the shared-memory data path is the busiest unit
+// of the N >= 1024 kernels (ncu: l1tex data-pipe wavefronts 72 % in the LTE transmitter, FMA pipe 24 %), so reads are
+// what to save.  A product of k unit-modulus fp32 factors is off by <= k * 6e-8: W^15 to 4e-7, far inside the 1e-4 bar.
 __host__ __device__ constexpr int fft_log2(int r) { return r <= 1 ? 0 : 1 + fft_log2(r / 2); }
-__host__ __device__ constexpr int fft_tw_rows(int r, bool ch) { return ch ? fft_log2(r) : r - 1; }
-__host__ __device__ constexpr int fft_tw_off(int log2n, int ppt, int p, bool ch = false) {
+__host__ __device__ constexpr int fft_tw_rows(int r, int ch) { return ch == 2 ? 1 : (ch == 1 ? fft_log2(r) : r - 1); }
+__host__ __device__ constexpr int fft_tw_off(int log2n, int ppt, int p, int ch = 0) {
     int o = 0;
     for (int i = 1; i < p; ++i) o += fft_tw_rows(fft_radix(log2n, ppt, i), ch) * fft_ns(log2n, ppt, i);
     return o;
 }
 
-template <int LOG2N_, int PPT_, bool CH_ = false, bool PAD_ = false> struct FftCfg {
-    static constexpr int LOG2N = LOG2N_, PPT = PPT_;
-    static constexpr bool CH = CH_, PAD = PAD_;
+template <int LOG2N_, int PPT_, int CH_ = 0, bool PAD_ = false> struct FftCfg {
+    static constexpr int LOG2N = LOG2N_, PPT = PPT_, CH = CH_;
+    static constexpr bool PAD = PAD_;
     static constexpr int N = 1 << LOG2N;
     static constexpr int T = N / PPT;                     // threads per symbol group
     static constexpr int LP = fft_lp(PPT);
@@ -154,13 +158,25 @@ template <int LOG2N> struct PptRx {
 template <int LOG2N> struct PptTx {
     static constexpr int value = LOG2N >= OFDM_PPT_TX_MIN_LOG2N ? OFDM_PPT_TX_LARGE : 8;
 };
-// chained twiddles (FftCfg CH) from this size on; 13 = never.  Measured on B200: +2 % for the framed
-// receiver at N >= 1024, +3 % for the transmitter at N = 4096, neutral or slightly negative below.
+// reduced twiddle tables (FftCfg CH) from this size on; 13 = never.  Round 1 (scalar butterflies): chained rows +2 % for
+// the framed receiver at N >= 1024, +3 % for the transmitter at N = 4096.  With packed butterflies the FMA pipe has
+// room and the shared-memory data path is the busiest unit, so the transmitter takes the reduced table from N = 256.
 #ifndef OFDM_TW_CHAIN_TX_MIN_LOG2N
-#define OFDM_TW_CHAIN_TX_MIN_LOG2N 12
+#define OFDM_TW_CHAIN_TX_MIN_LOG2N 8
 #endif
 #ifndef OFDM_TW_CHAIN_RXF_MIN_LOG2N
 #define OFDM_TW_CHAIN_RXF_MIN_LOG2N 10
+#endif
+// which reduced table the sizes at or above those thresholds use: 1 = chained rows, 2 = first row + powers
+// B200, packed butterflies (same box, ms per launch):  transmitter LTE 64-QAM 0.338 (full table) -> 0.316 (chained rows)
+// / 0.317 (powers), N=2048 0.176 -> 0.163 / 0.162, N=4096 0.199 -> 0.199 / 0.197, N=256 0.113 -> 0.111, N=512 0.136 ->
+// 0.133 (powers);  framed receiver, chained -> powers: LTE 64-QAM 0.702 -> 0.675, N=2048 16-QAM 0.338 -> 0.333, N=4096
+// 0.410 -> 0.403, N=1024 0.298 -> 0.295; below N=1024 the receiver is HBM-bound and does not care.
+#ifndef OFDM_TW_CHAIN_TX_MODE
+#define OFDM_TW_CHAIN_TX_MODE 2
+#endif
+#ifndef OFDM_TW_CHAIN_RXF_MODE
+#define OFDM_TW_CHAIN_RXF_MODE 2
 #endif
 #ifndef OFDM_TX_LAY_PAD
 #define OFDM_TX_LAY_PAD 1
@@ -168,7 +184,7 @@ template <int LOG2N> struct PptTx {
 #ifndef OFDM_RX_LAY_PAD
 #define OFDM_RX_LAY_PAD 0
 #endif
-template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value, false, OFDM_RX_LAY_PAD != 0>;
+template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value, 0, OFDM_RX_LAY_PAD != 0>;
 
 // The fused framed receiver (rx_frames_kernel) has its own knobs, because it is the one kernel that
 // keeps per-frame state (the equaliser gains) alive across symbols:
@@ -200,7 +216,7 @@ template <int LOG2N> struct PptRxF {
     static constexpr int value = LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RXF_1024 : (LOG2N == 11 ? OFDM_PPT_RXF_2048 : OFDM_PPT_RXF_4096));
 };
 template <int LOG2N>
-using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N), OFDM_RX_LAY_PAD != 0>;
+using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N ? OFDM_TW_CHAIN_RXF_MODE : 0), OFDM_RX_LAY_PAD != 0>;
 // The per-lane-epilogue variants of the framed receiver (sparse and dense) at N = 2048: 16 points per thread (two
 // exchanges instead of three, half the barriers) are 4-8 % faster there (B200: 1920-bin grid 16-QAM 0.345 -> 0.326 ms,
 // QPSK 0.311 -> 0.287 ms; LTE grid QPSK 0.539 -> 0.500 ms, 16-QAM 0.585 -> 0.561 ms), while the bulk-row 64-QAM kernel
@@ -210,13 +226,13 @@ using CfgRxF = FftCfg<LOG2N, PptRxF<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_RXF_M
 #endif
 template <int LOG2N>
 using CfgRxFD = FftCfg<LOG2N, (LOG2N == 11 ? OFDM_PPT_RXFD_2048 : PptRxF<LOG2N>::value),
-                       (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N), OFDM_RX_LAY_PAD != 0>;
+                       (LOG2N >= OFDM_TW_CHAIN_RXF_MIN_LOG2N ? OFDM_TW_CHAIN_RXF_MODE : 0), OFDM_RX_LAY_PAD != 0>;
 template <int LOG2N> struct RxFOpts {
     static constexpr bool GSM = LOG2N >= OFDM_GSM_MIN_LOG2N;
     static constexpr bool SB = LOG2N >= OFDM_SB_MIN_LOG2N || LOG2N <= OFDM_SB_SMALL_MAX_LOG2N;
 };
 template <int LOG2N>
-using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_TX_MIN_LOG2N), OFDM_TX_LAY_PAD != 0>;
+using CfgTx = FftCfg<LOG2N, PptTx<LOG2N>::value, (LOG2N >= OFDM_TW_CHAIN_TX_MIN_LOG2N ? OFDM_TW_CHAIN_TX_MODE : 0), OFDM_TX_LAY_PAD != 0>;
 
 // Exchange layout for the buffer written by pass P (Ns = PPT^P), chosen so that the scattered write
 // out[(j/Ns)*Ns*R + j%Ns + q*Ns] and the contiguous read in[j + m*T] both hit 16 distinct 8-byte
@@ -371,7 +387,7 @@ template <class C> struct LastPassTw {
     static constexpr int P = C::NPASS - 1, R = C::radix(P), Ns = C::ns(P), B = C::PPT / R;
     static constexpr int COUNT = P > 0 ? B * (R - 1) : 1;
     static __device__ __forceinline__ void load(float2 (&w)[COUNT], const float2 *tws, int j) {
-        static_assert(!C::CH, "register twiddles are taken from the full table");
+        static_assert(C::CH == 0, "register twiddles are taken from the full table");
         if (P > 0) {
 #pragma unroll
             for (int b = 0; b < B; ++b) {
@@ -424,9 +440,17 @@ template <class C, bool INV, int GROUPS, int P, bool SB = false, bool TWR = fals
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 const float2 *t = tws + off + ((j + b * C::T) & (Ns - 1));
-                if constexpr (!C::CH) {
+                if constexpr (C::CH == 0) {
 #pragma unroll
                     for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], t[(q - 1) * Ns]);
+                } else if constexpr (C::CH == 2) {
+                    // one row: W^r; every other multiplier is a product of two smaller ones (depth log2 R)
+                    float2 w[R];
+                    w[1] = t[0];
+#pragma unroll
+                    for (int q = 2; q < R; ++q) w[q] = cmul(w[q / 2], w[q - q / 2]);
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], w[q]);
                 } else {
                     // rows hold W^(1*r), W^(2*r), W^(4*r), ..; multiplier q = 2^a + rest is built as w[2^a] * w[rest],
                     // visiting q in an order that lets every product be used and dropped at once

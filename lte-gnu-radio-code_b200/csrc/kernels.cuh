@@ -415,17 +415,23 @@ __device__ __forceinline__ void pack_bits(const uint8_t *hb, unsigned *pk, uint8
 #ifndef OFDM_PF_DEPTH
 #define OFDM_PF_DEPTH 1
 #endif
+// ... and for the bulk-row variant (64-QAM, N >= 1024), whose 2 CTAs x 8 warps per SM leave DRAM latency exposed: two
+// symbols ahead.  B200, LTE 20 MHz 64-QAM: 0.697 -> 0.662 ms; the per-lane kernels lose 2-3 % with it and stay at 1.
+#ifndef OFDM_PF_DEPTH_BULK
+#define OFDM_PF_DEPTH_BULK 2
+#endif
 
 // shared-memory carve-up per CTA.  TXK: transmitter (no staging, no packed-row area); PIL: room for the
 // per-symbol pilot estimates; GSM: per-frame equaliser gains in thread-private slots; SB: one FFT
 // exchange buffer instead of two.
-template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = false, bool SB = false> struct Smem {
+template <class C, int GROUPS, bool TXK = false, bool PIL = true, bool GSM = false, bool SB = false, int PFD = OFDM_PF_DEPTH>
+struct Smem {
     static constexpr int THREADS = C::T * GROUPS;
     static constexpr int NBUF = SB ? 1 : 2;
     static constexpr int GSTRIDE = (C::LOG2N == 6) ? (NBUF * C::BUF + 8) : NBUF * C::BUF;   // complex slots per group
     static constexpr int FFT_BYTES = GROUPS * GSTRIDE * 8;
     static constexpr int TW_BYTES = C::TW_ENTRIES * 8;                              // pass twiddles, shared by the CTA
-    static constexpr int STAGE_BYTES = TXK ? 0 : OFDM_PF_DEPTH * THREADS * C::PPT * 8;   // symbols in flight: PPT samples per thread each (RX)
+    static constexpr int STAGE_BYTES = TXK ? 0 : PFD * THREADS * C::PPT * 8;   // symbols in flight: PPT samples per thread each (RX)
     static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
     static constexpr int PK_BYTES = TXK ? 0 : 3 * C::N / 4 + 16;                    // packed row staged for aligned stores
     static constexpr int TX_ROW_BYTES = 3 * C::N / 4 + 16;                          // one packed payload row at any 16-byte phase (TX)
@@ -619,7 +625,8 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     }
     const float pw = group_sum<T, GROUPS>(pw2.x + pw2.y, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
-    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr);
+    // every output is optional: a caller that only decodes wants LLRs or hard bits, not the equalised symbols
+    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr), weq = (eq_out != nullptr);
     // 64-QAM: a bin's six LLRs are 24 bytes, so per-lane stores would leave every 32-byte sector
     // half-written by each instruction (2.9x the sector writes at L2, ncu).  The row is assembled in
     // shared memory instead and written with full 16-byte lanes.
@@ -641,7 +648,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
                 for (int m = c; m < c + CH; ++m) {
                     const bool used = (mask & (1u << m)) != 0;
                     const float2 z = cscale(cmul(G.get(m), v[m]), p0);
-                    if (used) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
+                    if (used && weq) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
                     float Lb[BPS];
                     unsigned bits;
                     D.dem.run(z, Lb, bits);
@@ -669,7 +676,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     for (int m = 0; m < PPT; ++m) {
         if (CH == 0 && (mask & (1u << m))) {
             const float2 z = cscale(cmul(G.get(m), v[m]), p0);
-            st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
+            if (weq) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
             if (soft || hard) {
                 float Lb[BPS];
                 unsigned bits;
@@ -782,7 +789,7 @@ __device__ __forceinline__ void data_epilogue_bulk(const DevParams &P, const Dat
     fence_async_smem();
     group_sync<T, GROUPS>(gid);
     if (j == 0) {
-        bulk_store_row(eq_out + row * P.ndb, es, (unsigned)P.ndb * 8u);
+        if (eq_out != nullptr) bulk_store_row(eq_out + row * P.ndb, es, (unsigned)P.ndb * 8u);
         if (soft) bulk_store_row(llr_out + row * P.ndb * BPS, ls, (unsigned)(P.ndb * BPS) * 4u);
         bulk_commit();
     }
@@ -830,7 +837,7 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
                 const float inv = den > 0.f ? __fdividef(1.f, den) : 0.f;
                 const float2 e = cscale(cmul(make_float2(h.x, -h.y), z[m]), inv);
                 const long long o = row * P.ndd + pp.dj;
-                st_out(eq_out + o, e);
+                if (eq_out != nullptr) st_out(eq_out + o, e);
                 if (soft || hard) {
                     float Lb[BPS];
                     unsigned bits;
@@ -938,7 +945,8 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                  float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, int *__restrict__ hyp_out,
                  float2 *__restrict__ H_out, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                  uint8_t *__restrict__ hard_out) {
-    OFDM_KERNEL_PROLOGUE_(GROUPS, false, PIL, GSM, SB)
+    constexpr int DEPTH = EPI == EPI_BULK ? OFDM_PF_DEPTH_BULK : OFDM_PF_DEPTH;
+    OFDM_KERNEL_PROLOGUE_(GROUPS, false, PIL, GSM, SB, DEPTH)
     constexpr int N = C::N;
     const int L = N + P.cp, fs = P.m0 + P.d;
     const DataCtx<C, BPS> D(P, j);
@@ -950,7 +958,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
     long long pos = off0 + f * frame_stride;
     // request cursor: runs OFDM_PF_DEPTH symbols ahead of the symbol being processed, through the same
     // (frame, symbol) sequence; frames past the end of the list repeat the last one (valid windows)
-    constexpr int DEPTH = OFDM_PF_DEPTH, SLOT = S::THREADS * PPT;
+    constexpr int SLOT = S::THREADS * PPT;
     // Window of symbol s relative to the frame's first window: s*L, plus cp_extra for every slot boundary crossed (CP
     // pattern).  Kept as running offsets (wo: symbol in hand, pf_wo: request cursor) with a position-in-slot counter.
     long long pf_pos = pos;
@@ -1149,13 +1157,22 @@ __global__ void __launch_bounds__(C::T *GROUPS, MinBlocks<C>::value)
 rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples,
                   const long long *__restrict__ pos_in, const int *__restrict__ delay_in,
                   const int *__restrict__ hyp_in, long long n_locks, int iters, float2 *__restrict__ H_out,
-                  float2 *__restrict__ htime_out, float2 *__restrict__ synch_eq_out) {
+                  float2 *__restrict__ htime_out, float2 *__restrict__ synch_eq_out,
+                  const int *__restrict__ row_in, const int *__restrict__ count_dev) {
+    // count_dev (block path, ofdm_rx_block_work): the number of listed locks is decided by a kernel earlier in the
+    // stream, so the launch is sized for the most there can be and the actual count is read here; row_in: the row of
+    // H_out each lock's estimate belongs to (the block's est_chan_freq_P state) instead of its list position
+    if (count_dev != nullptr) {
+        n_locks = *count_dev < n_locks ? *count_dev : n_locks;
+        if (n_locks <= 0) return;
+    }
     OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
     const int L = N + P.cp;
     for (int it = 0; it < iters; ++it) {
         long long i = gg + (long long)it * total_groups;
         i = i < n_locks - 1 ? i : n_locks - 1;
+        const long long hrow = row_in != nullptr ? (long long)row_in[i] : i;
         const long long pos = pos_in[i];
         const int delay = delay_in[i];
         const int hyp = (hyp_in != nullptr && P.n_cfo > 0) ? hyp_in[i] : -1;
@@ -1180,7 +1197,7 @@ rx_chanest_kernel(const DevParams P, const float2 *__restrict__ x, long long n_s
         }
         chan_core<C>(P, ys, ydup, p_est, delay, P.inv_reg_eq_synch, j, H, G);
 #pragma unroll
-        for (int m = 0; m < PPT; ++m) H_out[i * N + j + m * T] = H[m];
+        for (int m = 0; m < PPT; ++m) H_out[hrow * N + j + m * T] = H[m];
         if (htime_out != nullptr) {                              // ifft(chan_est1): SynchAndChanEst.py:202
             float2 c[C::PPT];
 #pragma unroll
@@ -1227,7 +1244,12 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
                 const long long *__restrict__ start_in, const int *__restrict__ delay_in,
                 const int *__restrict__ hrow_in, const int *__restrict__ hyp_in, const float2 *__restrict__ Hmat,
                 long long n_sym, int iters,
-                float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out) {
+                float2 *__restrict__ eq_out, float *__restrict__ llr_out, uint8_t *__restrict__ hard_out,
+                const int *__restrict__ count_dev) {
+    if (count_dev != nullptr) {                              // see rx_chanest_kernel
+        n_sym = *count_dev < n_sym ? *count_dev : n_sym;
+        if (n_sym <= 0) return;
+    }
     OFDM_KERNEL_PROLOGUE(GROUPS)
     constexpr int N = C::N;
     const DataCtx<C, BPS> D(P, j);
@@ -1311,7 +1333,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
         return PIL ? cscale(c, AMP) : c;
     };
     // the last pass' twiddles live in registers where the transmitter has them to spare (N <= OFDM_TX_TWREG_MAX_LOG2N)
-    constexpr bool TWR = C::LOG2N <= OFDM_TX_TWREG_MAX_LOG2N && !C::CH;
+    constexpr bool TWR = C::LOG2N <= OFDM_TX_TWREG_MAX_LOG2N && C::CH == 0;
     float2 twreg[LastPassTw<C>::COUNT];
     if constexpr (TWR) LastPassTw<C>::load(twreg, tws, j);
     const BinMap map = make_bin_map<T, PPT>(P.ndb, j);

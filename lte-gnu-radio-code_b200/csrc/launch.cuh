@@ -85,7 +85,8 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
 #define OFDM_LAUNCH_RXF_C(CC, GG, PIL, CFO, EPI, CPP, Q)                                                               \
     {                                                                                                                \
         constexpr auto k = rx_frames_kernel<CC, BPS, GG, PIL, GSM, SB, CFO, EPI, CPP>;                               \
-        int SM = Smem<CC, GG, false, PIL, GSM, SB>::BYTES + (PIL ? 0 : GG * (Q.ls_stride * 4 + Q.es_stride * 8));    \
+        int SM = Smem<CC, GG, false, PIL, GSM, SB, (EPI == EPI_BULK ? OFDM_PF_DEPTH_BULK : OFDM_PF_DEPTH)>::BYTES +    \
+                 (PIL ? 0 : GG * (Q.ls_stride * 4 + Q.es_stride * 8));                                               \
         cudaError_t e = plan_launch<k>(CC::T * GG, SM, GG, n_frames, sms, d);                                        \
         if (e != cudaSuccess) return e;                                                                              \
         k<<<d.grid, CC::T * GG, SM, st>>>(Q, x, n_samples, first, frame_stride, n_frames, d.iters, delay, peak,      \
@@ -96,7 +97,7 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     DevParams Qp = P;
     Qp.es_stride = 0;
     if (P.bulk_rows && !(P.bps == 6 && LOG2N <= 6)) Qp.ls_stride = 0;
-    const bool bulk_ok = P.bulk_rows && !P.pil_k && !P.n_cfo && ((reinterpret_cast<unsigned long long>(eq) & 15ull) == 0) &&
+    const bool bulk_ok = P.bulk_rows && !P.pil_k && !P.n_cfo && eq != nullptr && ((reinterpret_cast<unsigned long long>(eq) & 15ull) == 0) &&
                          ((reinterpret_cast<unsigned long long>(llr) & 15ull) == 0);
     const bool dense = (long long)P.ndb * 64 >= (long long)OFDM_DENSE_MIN_FILL64 * C::N;
     const bool cpp = P.cp_extra != 0;                           // CP pattern: never together with pilots / hypothesis bank
@@ -107,10 +108,11 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
         else if (P.n_cfo) OFDM_LAUNCH_RXF(false, true, EPI_SPARSE, Qp)
         else {
             bool bulk = false;
-            if constexpr (BPS == 6) {
+            // (bulk-row kernels exist from N = 1024 on; below that the plan never asks for them)
+            if constexpr (LOG2N >= 10) {
                 if (bulk_ok) {
                     LaunchDims db, dp;
-                    int smb = Smem<C, G, false, false, GSM, SB>::BYTES + G * (P.ls_stride * 4 + P.es_stride * 8);
+                    int smb = Smem<C, G, false, false, GSM, SB, OFDM_PF_DEPTH_BULK>::BYTES + G * (P.ls_stride * 4 + P.es_stride * 8);
                     int smp = Smem<C, G, false, false, GSM, SB>::BYTES + G * Qp.ls_stride * 4;
                     const cudaError_t eb = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, EPI_BULK>>(TH, smb, G, n_frames, sms, db);
                     const cudaError_t ep = plan_launch<rx_frames_kernel<C, BPS, G, false, GSM, SB, false, EPI_SPARSE>>(TH, smp, G, n_frames, sms, dp);
@@ -137,7 +139,7 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
 template <int LOG2N>
 cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_samples, const long long *start,
                             const int *delay, const int *hrow, const int *hyp, const float2 *H, long long n_sym,
-                            float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms) {
+                            float2 *eq, float *llr, uint8_t *hard, cudaStream_t st, int sms, const int *count_dev) {
     using C = CfgRx<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
     int SM = Smem<C, G>::BYTES;
@@ -148,7 +150,7 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
             constexpr auto k = rx_demod_kernel<C, BPS, G, true>;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
-            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard);
+            k<<<d.grid, TH, SM, st>>>(P, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard, count_dev);
         } else {
             constexpr auto k = rx_demod_kernel<C, BPS, G, false>;
             DevParams Q = P;
@@ -157,7 +159,7 @@ cudaError_t launch_rx_demod(const DevParams &P, const float2 *x, long long n_sam
             SM += G * Q.ls_stride * 4;
             cudaError_t e = plan_launch<k>(TH, SM, G, n_sym, sms, d);
             if (e != cudaSuccess) return e;
-            k<<<d.grid, TH, SM, st>>>(Q, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard);
+            k<<<d.grid, TH, SM, st>>>(Q, x, n_samples, start, delay, hrow, hyp, H, n_sym, d.iters, eq, llr, hard, count_dev);
         }
         count_launch();
     })
@@ -215,7 +217,7 @@ cudaError_t launch_sync_search(const DevParams &P, const float2 *x, long long n_
 template <int LOG2N>
 cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samples, const long long *pos,
                            const int *delay, const int *hyp, long long n_locks, float2 *H, float2 *htime,
-                           float2 *synch_eq, cudaStream_t st, int sms) {
+                           float2 *synch_eq, cudaStream_t st, int sms, const int *row, const int *count_dev) {
     using C = CfgRx<LOG2N>;
     constexpr int G = GroupsFor<C>::value, TH = C::T * G;
     int SM = Smem<C, G>::BYTES;
@@ -224,7 +226,7 @@ cudaError_t launch_chanest(const DevParams &P, const float2 *x, long long n_samp
     LaunchDims d;
     cudaError_t e = plan_launch<k>(TH, SM, G, n_locks, sms, d);
     if (e != cudaSuccess) return e;
-    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, pos, delay, hyp, n_locks, d.iters, H, htime, synch_eq);
+    k<<<d.grid, TH, SM, st>>>(P, x, n_samples, pos, delay, hyp, n_locks, d.iters, H, htime, synch_eq, row, count_dev);
     count_launch();
     return cudaGetLastError();
 }
@@ -234,12 +236,13 @@ struct KernelSet {
     cudaError_t (*rx_frames)(const DevParams &, const float2 *, long long, long long, long long, long long, int *,
                              float *, uint8_t *, int *, float2 *, float2 *, float *, uint8_t *, cudaStream_t, int);
     cudaError_t (*rx_demod)(const DevParams &, const float2 *, long long, const long long *, const int *, const int *,
-                            const int *, const float2 *, long long, float2 *, float *, uint8_t *, cudaStream_t, int);
+                            const int *, const float2 *, long long, float2 *, float *, uint8_t *, cudaStream_t, int,
+                            const int *);
     cudaError_t (*tx)(const DevParams &, const uint8_t *, float2 *, long long, cudaStream_t, int);
     cudaError_t (*sync_search)(const DevParams &, const float2 *, long long, long long, long long, long long, float *,
                                int *, int *, cudaStream_t, int);
     cudaError_t (*chanest)(const DevParams &, const float2 *, long long, const long long *, const int *, const int *,
-                           long long, float2 *, float2 *, float2 *, cudaStream_t, int);
+                           long long, float2 *, float2 *, float2 *, cudaStream_t, int, const int *, const int *);
 };
 
 #define OFDM_DEFINE_KERNELSET(LOG2N)                                                               \

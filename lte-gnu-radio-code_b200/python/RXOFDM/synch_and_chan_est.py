@@ -19,14 +19,25 @@ class synch_and_chan_est(RxBlockBase):
     compat = "rxofdm"
 
     def __init__(self, num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr,
-                 directory_name, file_name_cest, diagnostics, genie, *, modulation=2, zc_root=None, device=None):
+                 directory_name, file_name_cest, diagnostics, genie, *, modulation=2, zc_root=None, device=None,
+                 fused=None):
         gr.sync_block.__init__(self, name="SynchAndChanEst", in_sig=[np.complex64], out_sig=[np.complex64])
         self.diagnostics = diagnostics
         self._setup(num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr, 0.4,
                     directory_name, file_name_cest, diagnostics, genie, modulation, zc_root, rows=100,
-                    device=device)
+                    device=device, fused=fused)
         self.cor_obs = -1
         self.time_synch_ref = np.zeros((self.max_num_corr, 3))
+
+    def work_fused(self, in0):
+        """Loops A and B in one C-ABI call (ofdm_rx_block_work, mode 1)."""
+        r = self._fused_call(in0)
+        k = r.obs_after_search + 1
+        if k > 0:
+            self.time_synch_ref[:k] = np.ctypeslib.as_array(r.time_synch_ref, (k, 3))
+        if r.n_new_locks and self.diagnostics == 1:
+            stamp = datetime.datetime.now().strftime("%Y_%m_%d_%Hh_%Mm")
+            self._dump_chan(self._last_chan_time[-1], str(self.directory_name) + stamp + str(self.file_name_cest) + ".pckl")
 
     def work(self, input_items, output_items):
         in0 = input_items[0]
@@ -34,6 +45,9 @@ class synch_and_chan_est(RxBlockBase):
         c = self.cfg
         n = len(in0)
         N, CP, L = c.nfft, c.cp_len, c.sym_len
+        if self._blk:
+            self.work_fused(in0)
+            return self._pack(out, output_items)
         rx = self._upload(in0)
 
         # loop A (:146-221): every trial on the GPU; the accept rule is sequential but tiny
@@ -67,6 +81,10 @@ class synch_and_chan_est(RxBlockBase):
                 delays.append(int(self.time_synch_ref[r][1]))
         self._demod_into(rx, rows, starts, delays, rows)
 
+        return self._pack(out, output_items)
+
+    def _pack(self, out, output_items):
+        c = self.cfg
         corr_size = min(int(self.num_ofdm_symb / c.frame_syms), self.rows)      # :253 made integral
         data_out = self.est_data_freq[0:corr_size].reshape(-1)
         self.last_written = 0

@@ -22,6 +22,15 @@ class OfdmParams(C.Structure):
     ]
 
 
+class RxBlockResult(C.Structure):
+    """struct ofdm_rx_block_result"""
+    _fields_ = [
+        ("n_new_locks", C.c_int32), ("n_demod", C.c_int32), ("obs_after_search", C.c_int32), ("n_state_rows", C.c_int32),
+        ("time_synch_ref", C.POINTER(C.c_int64)), ("new_rows", C.POINTER(C.c_int32)), ("chan_time", C.POINTER(C.c_float)),
+        ("synch_freq", C.POINTER(C.c_float)), ("demod_rows", C.POINTER(C.c_int32)), ("data_freq", C.POINTER(C.c_float)),
+    ]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 SIGNATURES = {
@@ -50,6 +59,10 @@ SIGNATURES = {
     "ofdm_channel_awgn": (C.c_int, [_P, _P, _P, _I64, _P, C.c_int32, C.c_int32, C.c_float, C.c_uint64, _P]),
     "ofdm_rx_frames_host": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "ofdm_tx_modulate_host": (C.c_int, [_P, _P, _P, _I64]),
+    "ofdm_rx_block_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "ofdm_rx_block_destroy": (C.c_int, [_P]),
+    "ofdm_rx_block_work": (C.c_int, [_P, _P, _I64, C.POINTER(RxBlockResult)]),
+    "ofdm_rx_block_chan_freq": (C.c_int, [_P, _P, C.c_int32]),
 }
 
 _lib = None
@@ -72,7 +85,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.ofdm_abi_version() != 3:
+        if l.ofdm_abi_version() != 4:
             raise OfdmError("libofdm_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -204,25 +204,25 @@ class Modem:
 
     # ---- RX, framed (throughput path) --------------------------------------------------------
     def rx_frames(self, rx, n_frames, first=0, frame_stride=None, want_llr=True, want_hard=True, want_h=False,
-                  out=None):
+                  out=None, want_eq=True):
         torch = _torch()
         cfg = self.cfg
         rx = self._c64(rx)
         fs = cfg.frame_len if frame_stride is None else frame_stride
         nd = n_frames * cfg.d
         o = out if out is not None else {}
-        if "eq" not in o:
+        if "delay" not in o:
             o["delay"] = self.empty((n_frames,), torch.int32)
             o["peak"] = self.empty((n_frames,), torch.float32)
             o["locked"] = self.empty((n_frames,), torch.uint8)
-            o["eq"] = self.empty((nd, cfg.payload_bins), torch.complex64)
+            o["eq"] = self.empty((nd, cfg.payload_bins), torch.complex64) if want_eq else None
             o["llr"] = self.empty((nd, cfg.payload_bins * cfg.bps), torch.float32) if want_llr else None
             o["hard"] = self.empty((nd, cfg.hard_stride), torch.uint8) if want_hard else None
             o["h"] = self.empty((n_frames, cfg.nfft), torch.complex64) if want_h else None
             o["hyp"] = self.empty((n_frames,), torch.int32) if self.n_cfo else None
         _lib.check(_lib.lib().ofdm_rx_frames_cfo(
             self._h, _ptr(rx), rx.numel(), first, fs, n_frames, _ptr(o["delay"]), _ptr(o["peak"]),
-            _ptr(o["locked"]), _ptr(o.get("hyp")), _ptr(o.get("h")), _ptr(o["eq"]), _ptr(o.get("llr")),
+            _ptr(o["locked"]), _ptr(o.get("hyp")), _ptr(o.get("h")), _ptr(o.get("eq")), _ptr(o.get("llr")),
             _ptr(o.get("hard")), self._stream()))
         return o
 
@@ -326,17 +326,20 @@ class Modem:
         return out
 
     # ---- host-buffer entry points (numpy in, numpy out; copies inside the call) -----------------
-    def rx_frames_host(self, rx_np, n_frames, first=0, frame_stride=None, out=None, want_llr=True, want_hard=True):
+    def rx_frames_host(self, rx_np, n_frames, first=0, frame_stride=None, out=None, want_llr=True, want_hard=True,
+                       want_eq=True):
+        """Outputs that are not asked for (want_* False, or a None entry in a caller-supplied `out`) are neither
+        computed nor copied back; at least one of eq / llr / hard is needed."""
         cfg = self.cfg
         assert rx_np.dtype == np.complex64 and rx_np.flags.c_contiguous
         fs = cfg.frame_len if frame_stride is None else frame_stride
         nd = n_frames * cfg.d
         o = out if out is not None else {}
-        if "eq" not in o:
+        if "delay" not in o:
             o["delay"] = np.empty(n_frames, np.int32)
             o["peak"] = np.empty(n_frames, np.float32)
             o["locked"] = np.empty(n_frames, np.uint8)
-            o["eq"] = np.empty((nd, cfg.payload_bins), np.complex64)
+            o["eq"] = np.empty((nd, cfg.payload_bins), np.complex64) if want_eq else None
             o["llr"] = np.empty((nd, cfg.payload_bins * cfg.bps), np.float32) if want_llr else None
             o["hard"] = np.empty((nd, cfg.hard_stride), np.uint8) if want_hard else None
 
@@ -344,7 +347,7 @@ class Modem:
             return C.c_void_p(0) if a is None else C.c_void_p(a.ctypes.data)
         with _torch().cuda.device(self.device):
             _lib.check(_lib.lib().ofdm_rx_frames_host(self._h, p(rx_np), rx_np.size, first, fs, n_frames, p(o["delay"]),
-                                                      p(o["peak"]), p(o["locked"]), p(o["eq"]), p(o.get("llr")),
+                                                      p(o["peak"]), p(o["locked"]), p(o.get("eq")), p(o.get("llr")),
                                                       p(o.get("hard"))))
         return o
 

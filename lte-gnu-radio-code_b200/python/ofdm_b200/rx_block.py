@@ -3,10 +3,12 @@ utsa_ofdm.SynchAndChanEst): host<->device staging for one work() call and the lo
 which stays on the host because it is a handful of scalar decisions per call
 (GRR/gr-utsa_ofdm/python/SynchAndChanEst.py:166-175, GRR/gr-RXOFDM/python/synch_and_chan_est.py:170-179).
 All arithmetic on samples runs in the CUDA kernels."""
+import ctypes as C
 import pickle
 
 import numpy as np
 
+from . import _lib
 from .gr_compat import gr
 from .modem import Modem, ModemConfig
 
@@ -15,7 +17,7 @@ class RxBlockBase(gr.sync_block):
     compat = "utsa"
 
     def _setup(self, num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr, gate,
-               directory_name, file_name_cest, diagnostics, genie, modulation, zc_root, rows, device):
+               directory_name, file_name_cest, diagnostics, genie, modulation, zc_root, rows, device, fused=None):
         import torch
         self._torch = torch
         self.num_ofdm_symb = int(num_ofdm_symb)
@@ -47,11 +49,62 @@ class RxBlockBase(gr.sync_block):
         self.est_data_freq = np.zeros((rows, c.num_data_bins), dtype=complex)
         self.count = 0
         self.last_written = 0
+        # One C-ABI call per work() (ofdm_rx_block_work: upload, search, lock rule on the device, estimate, demodulate,
+        # one synchronisation) for the two live blocks; `fused=False` keeps the call-by-call path that the legacy
+        # blocks with a hypothesis bank use (and that tools/bench_blocks.py times beside it).
+        self._blk = None
+        if fused is None:
+            fused = self.compat in ("utsa", "rxofdm") and type(self).work_fused is not None
+        if fused:
+            h = C.c_void_p()
+            with torch.cuda.device(self.modem.device):
+                _lib.check(_lib.lib().ofdm_rx_block_create(self.modem._h, 0 if self.compat == "utsa" else 1, rows, C.byref(h)))
+            self._blk = h
+            self._res = _lib.RxBlockResult()
+
+    work_fused = None          # set by the subclasses that have a fused path
+
+    def close(self):
+        if getattr(self, "_blk", None):
+            _lib.lib().ofdm_rx_block_destroy(self._blk)
+            self._blk = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # state the reference keeps as a NumPy array; here it lives on the device and is read on demand
     @property
     def est_chan_freq_P(self):
+        if self._blk:
+            out = np.empty((self.rows, self.cfg.nfft), np.complex64)
+            _lib.check(_lib.lib().ofdm_rx_block_chan_freq(self._blk, C.c_void_p(out.ctypes.data), self.rows))
+            return out.astype(complex)
         return self._d_H.cpu().numpy().astype(complex)
+
+    def _fused_call(self, in0):
+        """ofdm_rx_block_work on the scheduler's buffer; mirrors the per-call results into the NumPy state the
+        reference exposes (est_chan_time, est_synch_freq, est_data_freq) and returns the result struct."""
+        c = self.cfg
+        a = in0 if (isinstance(in0, np.ndarray) and in0.dtype == np.complex64 and in0.flags.c_contiguous) \
+            else np.ascontiguousarray(in0, dtype=np.complex64)
+        r = self._res
+        _lib.check(_lib.lib().ofdm_rx_block_work(self._blk, C.c_void_p(a.ctypes.data), len(a), C.byref(r)))
+        if r.n_new_locks:
+            k = r.n_new_locks
+            rows = np.ctypeslib.as_array(r.new_rows, (k,))
+            ht = np.ctypeslib.as_array(r.chan_time, (k, 2 * c.nfft)).view(np.complex64)
+            se = np.ctypeslib.as_array(r.synch_freq, (k, 2 * c.mm)).view(np.complex64)
+            self.est_chan_time[rows] = ht
+            self.est_synch_freq[rows] = se
+            self._last_chan_time = ht
+        if r.n_demod:
+            k = r.n_demod
+            rows = np.ctypeslib.as_array(r.demod_rows, (k,))
+            self.est_data_freq[rows] = np.ctypeslib.as_array(r.data_freq, (k, 2 * c.num_data_bins)).view(np.complex64)
+        return r
 
     def _upload(self, in0):
         torch = self._torch

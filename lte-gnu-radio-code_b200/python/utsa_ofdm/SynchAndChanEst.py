@@ -18,17 +18,24 @@ class SynchAndChanEst(RxBlockBase):
 
     def __init__(self, num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr,
                  scale_factor_gate, directory_name, file_name_cest, diagnostics, genie, channel="Fading", *,
-                 modulation=2, zc_root=None, device=None):
+                 modulation=2, zc_root=None, device=None, fused=None):
         gr.sync_block.__init__(self, name="SynchAndChanEst", in_sig=[np.complex64], out_sig=[np.complex64])
         self.channel = channel
         self.scale_factor_gate = scale_factor_gate
         self.diagnostic = diagnostics
         self._setup(num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr, scale_factor_gate,
                     directory_name, file_name_cest, diagnostics, genie, modulation, zc_root,
-                    rows=int(num_ofdm_symb), device=device)
+                    rows=int(num_ofdm_symb), device=device, fused=fused)
         self.SNR_lin = 10 ** (self.SNR / 20)
         self.corr_obs = -1
         self.time_synch_ref = np.zeros(3)
+
+    def work_fused(self, in0):
+        """Loops A and B in one C-ABI call (ofdm_rx_block_work, mode 0); the lock record comes back with it."""
+        r = self._fused_call(in0)
+        self.time_synch_ref[:] = [r.time_synch_ref[0], r.time_synch_ref[1], r.time_synch_ref[2]]
+        if r.n_new_locks and self.diagnostic == 1:
+            self._dump_chan(self._last_chan_time[0], str(self.directory_name) + "_" + str(self.file_name_cest))
 
     def work(self, input_items, output_items):
         in0 = input_items[0]
@@ -38,6 +45,9 @@ class SynchAndChanEst(RxBlockBase):
         N, CP, L, fsyms = c.nfft, c.cp_len, c.sym_len, c.frame_syms
         n_unique_symb = n // L
         n_data_symb = int(n_unique_symb * (c.d / fsyms))
+        if self._blk:
+            self.work_fused(in0)
+            return self._pack(out, output_items, n_data_symb)
         rx = self._upload(in0)
 
         # loop A: all trials on the GPU, then the first acceptable lock (:143-219)
@@ -67,6 +77,10 @@ class SynchAndChanEst(RxBlockBase):
                     starts.append(base + L * k)
         self._demod_into(rx, rows, starts, [d] * len(rows), [0] * len(rows))
 
+        return self._pack(out, output_items, n_data_symb)
+
+    def _pack(self, out, output_items, n_data_symb):
+        c, fsyms = self.cfg, self.cfg.frame_syms
         # packing (:249-262)
         data_demod = np.delete(self.est_data_freq, list(range(3, self.rows, fsyms)), axis=0)
         data_out = data_demod.reshape(-1)[: n_data_symb * c.num_data_bins]

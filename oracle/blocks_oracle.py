@@ -306,3 +306,122 @@ class SynchEstFOAndDSSSOracle(SynchEstAndFOOracle):
         self.count += 1
         self.cor_obs = 0
         return len(out)
+
+
+class SynchronizeAndEstimateOracle:
+    """work() of the pointer-tracking receiver, GRR/LEGACY/gr-ofdm-rx/python/SynchronizeAndEstimate.py
+    (ctor :31-180, work :186-441), case 0 ('4G5GSISO-TU': NFFT 64, CP 16, 62 synch / 60 data bins, synch_data [1, 3],
+    Zadoff-Chu root 23, SNR 100 used as a linear regulariser).
+
+    Unlike the sliding-search blocks this one STEERS its window: it strides by ceil(CP/2) until the first lock, then
+    jumps a frame at a time, and from the sixth lock on predicts the next frame start from a straight-line fit through
+    the last five (pointer + delay) observations (:231-236, :333-351).  Reproduced as written, because they change what
+    the block computes:
+      * dmax_ind = argmax - 1 (:278), so a peak at delay 0 gives -1: the channel estimate then picks the LAST column of
+        the delay bank (p_mat[:, -1], :354) while the data symbols are de-rotated by a true -1 (:425);
+      * after a pointer adjustment the transform is repeated on the window gathered BEFORE the adjustment (:293-297 reads
+        self.rx_buffer_time, which is not refilled), so the repeat returns the same peak and delay; the lock is
+        recorded at the adjusted pointer, the estimate comes from the unadjusted window;
+      * the 'previous lock' of the spacing test is row max(corr_obs, 1) (:326), i.e. the all-zero row 1 while the
+        first lock is the only one;
+      * a data symbol is demodulated when sum(time_synch_ref row) + NFFT < len (pointer + delay + peak, :403), each one
+        is rescaled by the power of est_data_freq row p -- not its own row (:434-437) -- and written to out[0:60]
+        (:440-441), so the output buffer ends up holding the LAST demodulated symbol;
+      * corr_obs restarts at -1 on every call (:213): the block keeps no lock across calls.
+    Not reproduced: d_long[loop_count] (:279) indexes one past the end of a diagnostic array on the last iteration
+    of the loop when a window still fits; the state arrays are sized for 12 locks (num_symbols[0] = 48), further locks
+    raise IndexError in the reference and are dropped here."""
+
+    def __init__(self, case=0, literal=False):
+        assert case == 0, "case 1 is the 2x2 MIMO profile (out of scope)"
+        self.prm = oo.ModemParams(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, snr=100,
+                                  compat="rxofdm", zc_root=23)
+        self.literal = literal
+        p = self.prm
+        self.zc = oo.zc_for(p)
+        self.bank = oo.delay_bank(p)
+        self.lmax_s, self.lmax_d = 12, 36                                    # :139-140 with num_symbols[0] = 48
+        self.time_synch_ref = np.zeros((250, 3))                             # :177
+        self.est_chan_freq_p = np.zeros((self.lmax_s, p.nfft), dtype=complex)
+        self.est_chan_impulse = np.zeros((self.lmax_s, p.nfft), dtype=complex)
+        self.est_synch_freq = np.zeros((self.lmax_s, p.mm), dtype=complex)
+        self.est_data_freq = np.zeros((self.lmax_d, p.num_data_bins), dtype=complex)
+        self.corr_obs = -1
+        self.last_written = 0
+
+    def trial(self, in0, ptr):
+        """(argmax, max, synchdat) of the window that opens at ptr: :239-276"""
+        return oo.sync_trial(in0, int(ptr), self.prm, self.zc, self.bank, self.literal)
+
+    def work(self, in0, out):
+        p = self.prm
+        N, CP, L, fsum, n = p.nfft, p.cp_len, p.sym_len, p.frame_syms, len(in0)
+        stride = int(np.ceil(CP / 2))                                        # :203
+        start_samp = (CP - 4) - 1                                            # :216
+        total_loops = int(np.ceil(n / stride))                               # :218
+        self.corr_obs = -1                                                   # :213
+        ptr_frame, b, xp = 0, 0, []
+        ptr_adj, loop_count, sym_count = 0, 0, 0
+        tap_delay = 5
+        x = np.zeros(tap_delay)
+        ptr_synch0 = np.zeros(1000)
+        while loop_count <= total_loops:                                     # :229
+            if self.corr_obs == -1:
+                ptr_frame = loop_count * stride + start_samp + ptr_adj
+            elif self.corr_obs < 5:
+                ptr_frame += fsum * L
+            else:
+                ptr_frame = (np.ceil(np.dot(xp[-1:], b) - CP / 4))[0]        # :236
+            if (p.m0 - 1) * L + N + ptr_frame < n:                           # :239
+                d0, dmax, sd = self.trial(in0, ptr_frame)
+                dmax_ind = d0 - 1                                            # :278
+                if dmax > 0.5 * p.mm or self.corr_obs > -1:                  # :281
+                    if dmax_ind > np.ceil(0.75 * CP):                        # :283-289; the repeat (:291-318) changes nothing
+                        if self.corr_obs == -1:
+                            ptr_adj += np.ceil(0.5 * CP)
+                            ptr_frame = loop_count * stride + start_samp + ptr_adj
+                        elif self.corr_obs < 5:
+                            ptr_frame += np.ceil(0.5 * CP)
+                    time_synch_ind = self.time_synch_ref[max(self.corr_obs, 1), 0]          # :326
+                    if ptr_frame - time_synch_ind > (2 * CP + N) or self.corr_obs == -1:
+                        if self.corr_obs + 1 >= self.lmax_s:
+                            loop_count += 1
+                            continue                                         # IndexError in the reference
+                        self.corr_obs += 1
+                        r = self.corr_obs
+                        self.time_synch_ref[r] = (ptr_frame, dmax_ind, dmax)               # :331-333
+                        ptr_synch0[sym_count % tap_delay] = ptr_frame + dmax_ind           # :335
+                        x[sym_count % tap_delay] = sym_count * fsum
+                        sym_count += 1
+                        x2 = x[0:min(r, tap_delay)]
+                        x_plus = np.concatenate((x2, np.atleast_1d(sym_count * fsum)))
+                        xp = np.zeros((len(x_plus), 2))
+                        xp[:, 0] = 1.0
+                        xp[:, 1] = x_plus
+                        if r > 3:                                            # :345-351
+                            y = ptr_synch0[0:min(tap_delay, r)]
+                            X = np.zeros((len(x2), 2))
+                            X[:, 0] = 1.0
+                            X[:, 1] = x2
+                            b = np.linalg.lstsq(X, y, rcond=None)[0]
+                        ce, ce1, dr = oo.chan_est(sd, dmax_ind, p, self.zc, self.bank, self.literal)      # :354-366
+                        self.est_chan_freq_p[r] = ce1
+                        tim, esf = oo.chan_est_aux(ce, ce1, dr, p)           # :381-389
+                        self.est_chan_impulse[r] = tim
+                        self.est_synch_freq[r] = esf
+            loop_count += 1
+        # data symbols of every lock (:398-441)
+        self.last_written = 0
+        for r in range(self.corr_obs + 1):
+            for k in range(p.d):
+                if np.sum(self.time_synch_ref[r]) + N < n:                   # :403
+                    data_ptr = int(self.time_synch_ref[r, 0] + (k + 1) * L)
+                    row = r * p.d + k
+                    self.est_data_freq[row] = oo.demod_symbol(in0, data_ptr, self.time_synch_ref[r, 1],
+                                                              self.est_chan_freq_p[r], p, self.literal)
+                    data = self.est_data_freq[r]                             # :434: row p, not row p*D + data_sym
+                    p_est1 = np.sum(data * np.conj(data)) / len(data)
+                    self.est_data_freq[row] = self.est_data_freq[row] / np.sqrt(p_est1)
+                    out[0:p.num_data_bins] = self.est_data_freq[row]         # :440-441
+                    self.last_written = p.num_data_bins
+        return len(out)

@@ -30,7 +30,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export: " + n
     assert set(_lib.SIGNATURES) == set(names)
     lib.ofdm_abi_version.restype = ctypes.c_int
-    assert lib.ofdm_abi_version() == 3
+    want = int(re.search(r"#define\s+OFDM_B200_ABI_VERSION\s+(\d+)", open(HEADER).read()).group(1))
+    assert lib.ofdm_abi_version() == want == 4
+
+
+def test_block_result_struct_matches_header():
+    from ofdm_b200 import _lib
+    txt = open(HEADER).read()
+    body = txt[txt.index("typedef struct ofdm_rx_block ofdm_rx_block;"):txt.index("} ofdm_rx_block_result;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"^\s*(?:const\s+)?(?:int32_t|int64_t|float)\s+\*?(\w+);", body, flags=re.M)
+    assert fields == [f[0] for f in _lib.RxBlockResult._fields_]
+    assert ctypes.sizeof(_lib.RxBlockResult) == 4 * 4 + 6 * ctypes.sizeof(ctypes.c_void_p)
 
 
 def test_params_struct_matches_header():
@@ -108,6 +119,12 @@ def test_grc_descriptors_keep_ids_and_make_templates():
         "TXOFDM_tx_signal_transmitter.block.yml": ("TXOFDM_tx_signal_transmitter", "TXOFDM.tx_signal_transmitter(", 3),
         "utsa_ofdm_SynchAndChanEst.block.yml": ("utsa_ofdm_SynchAndChanEst", "utsa_ofdm.SynchAndChanEst(", 13),
         "utsa_ofdm_TxSignalTransmitter.block.yml": ("utsa_ofdm_TxSignalTransmitter", "utsa_ofdm.TxSignalTransmitter(", 2),
+        # the legacy receiver module (GRR/LEGACY/gr-ofdm-rx/grc)
+        "OFDMReceiver_BitRecovery.block.yml": ("OFDMReceiver_BitRecovery", "OFDMReceiver.BitRecovery(", 3),
+        "OFDMReceiver_SynchEstAndFO.block.yml": ("OFDMReceiver_SynchEstAndFO", "OFDMReceiver.SynchEstAndFO(", 5),
+        "OFDMReceiver_SynchEstFOAndDSSS.block.yml": ("OFDMReceiver_SynchEstFOAndDSSS", "OFDMReceiver.SynchEstFOAndDSSS(", 5),
+        "OFDMReceiver_SynchronizeAndEstimate.block.yml": ("OFDMReceiver_SynchronizeAndEstimate",
+                                                          "OFDMReceiver.SynchronizeAndEstimate(", 1),
     }
     for fn, (bid, make, nargs) in want.items():
         d = yaml.safe_load(open(os.path.join(grc, fn)))
@@ -122,6 +139,16 @@ def test_sharding_helpers():
     blocks = [shard.frame_block(10, r, 4) for r in range(4)]
     assert blocks == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert shard.summarize([2, 100, 1.0, 4.0, 9, 10, 0, 0])["ber"] == 0.02
+
+
+def test_bench_arms_print_the_same_config():
+    """the reference arm's `config` must be the repo arm's, the sample size a separate key."""
+    import bench
+    for name in bench.WORKLOADS:
+        a, b = bench.config_for(name, 1), bench.config_for(name, 1)
+        assert a == b and a["workload"] == name and "frames_per_gpu" in a
+    assert bench.config_for("rx_n64_16qam_1m", 8)["frames_total"] == 8 * 333334
+    assert bench.config_for("rx_lte20_streams", 8)["frames_total"] == 40960
 
 
 def test_bench_frame_length_matches_the_host_numerology():

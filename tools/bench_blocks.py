@@ -16,6 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "lte-gnu-radio-code_b200", "python"))
+from bench import ClockSampler  # noqa: E402
 from oracle import ofdm_oracle as oo  # noqa: E402  (CPU baseline leg only)
 from oracle.blocks_oracle import RxofdmBlockOracle, UtsaBlockOracle  # noqa: E402
 
@@ -50,23 +51,31 @@ def run(name, n_samples):
     rx = waveform(n_samples)
     nsym = n_samples // 80
     if name == "utsa":
-        mk_b = lambda: utsa_ofdm.SynchAndChanEst(nsym, 64, 16, 62, [1, 3], 60, 100, 0.7, "/tmp/", "cest.pckl", 0, 0)
+        mk = lambda fused: (lambda: utsa_ofdm.SynchAndChanEst(nsym, 64, 16, 62, [1, 3], 60, 100, 0.7, "/tmp/", "cest.pckl", 0, 0, fused=fused))
         mk_o = lambda: UtsaBlockOracle(nsym, 64, 16, 62, [1, 3], 60, 100, 0.7, literal=True)
     else:
-        mk_b = lambda: RXOFDM.synch_and_chan_est(nsym, 64, 16, 62, [1, 3], 60, 100, "/tmp/", "output_file", 0, 0, zc_root=23)
+        mk = lambda fused: (lambda: RXOFDM.synch_and_chan_est(nsym, 64, 16, 62, [1, 3], 60, 100, "/tmp/", "output_file", 0, 0, zc_root=23, fused=fused))
         mk_o = lambda: RxofdmBlockOracle(nsym, 64, 16, 62, [1, 3], 60, 100, zc_root=23, literal=True)
     out_b = np.zeros(n_samples, np.complex64)
+    out_m = np.zeros(n_samples, np.complex64)
     out_o = np.zeros(n_samples, np.complex64)
-    second_call_seconds(mk_b, rx, out_b, 2)              # warm the library (plan tables, first launches)
-    t_b, blk = second_call_seconds(mk_b, rx, out_b, 20)
+    second_call_seconds(mk(True), rx, out_b, 2)          # warm the library (plan tables, first launches)
+    second_call_seconds(mk(False), rx, out_m, 2)
+    sampler = ClockSampler(0)
+    sampler.start()
+    t_b, blk = second_call_seconds(mk(True), rx, out_b, 50)      # one C-ABI call per work() (ofdm_rx_block_work)
+    t_m, blk_m = second_call_seconds(mk(False), rx, out_m, 20)   # the call-by-call path of round 1
+    clocks = sampler.stop()
     t_o, ora = second_call_seconds(mk_o, rx, out_o, 3)
     n = ora.last_written
-    assert blk.last_written == n
+    assert blk.last_written == n and blk_m.last_written == n
     err = float(np.max(np.abs(out_b[:n] - out_o[:n])) / (np.sqrt(np.mean(np.abs(out_o[:n]) ** 2)) + 1e-30)) if n else 0.0
     print(json.dumps(dict(block=name, samples_per_call=n_samples, written_per_call=int(n),
-                          ms_per_call_b200=1e3 * t_b, ms_per_call_oracle_1core=1e3 * t_o, speedup=t_o / t_b,
+                          ms_per_call_b200=1e3 * t_b, ms_per_call_b200_modular=1e3 * t_m,
+                          ms_per_call_oracle_1core=1e3 * t_o, speedup=t_o / t_b,
                           msamples_per_s_b200=n_samples / t_b / 1e6, msamples_per_s_oracle=n_samples / t_o / 1e6,
-                          rel_err_vs_oracle=err)), flush=True)
+                          rel_err_vs_oracle=err, one_call_identical_to_modular=bool(np.array_equal(out_b[:n], out_m[:n])),
+                          clocks=clocks)), flush=True)
 
 
 if __name__ == "__main__":

@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "lte-gnu-radio-code_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
+from bench import ClockSampler  # noqa: E402
 from ofdm_b200 import Modem, ModemConfig  # noqa: E402
 from quick_bench import time_it  # noqa: E402
 from oracle import ofdm_oracle as oo  # noqa: E402  (CPU baseline leg only)
@@ -60,14 +61,17 @@ def run(name, cpu_seconds):
     n = rx.numel()
     n_trials = (n - cfg.m0 * cfg.sym_len - cfg.nfft - cfg.cp_len - 1) // stride + 1
     peak, delay = m.sync_search(rx, cfg.cp_len, stride, n_trials)
-    t_ms, _ = time_it(lambda: m.sync_search(rx, cfg.cp_len, stride, n_trials), iters=8)
+    sampler = ClockSampler(0)
+    sampler.start()
+    t_ms, _ = time_it(lambda: m.sync_search(rx, cfg.cp_len, stride, n_trials), iters=12)
+    clocks = sampler.stop()
     pk = peak.cpu().numpy()
     # every frame start must show up as a gated peak at the trial that lands on it
     hits = int((pk > cfg.gate * cfg.mm).sum())
     res = dict(case=name, nfft=cfg.nfft, cp_len=cfg.cp_len, stride=stride, samples=n, trials=n_trials, ms=t_ms,
                trials_per_s=n_trials / t_ms * 1e3, samples_per_s=n / t_ms * 1e3,
                dram_GBs=(n * 8 + n_trials * 8) / t_ms / 1e6, window_GBs=n_trials * cfg.m0 * cfg.nfft * 8 / t_ms / 1e6,
-               gated_trials=hits, frames=nf)
+               gated_trials=hits, frames=nf, clocks=clocks)
     if cpu_seconds > 0:
         h = rx[: min(n, 1 << 20)].cpu().numpy()
         res["cpu_literal_trials_per_s_1core"] = cpu_rate(cfg, h, stride, True, cpu_seconds)

@@ -34,7 +34,7 @@ CASES = {
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(CASES)
-    reps = 2
+    reps = int(os.environ.get("PROF_REPS", "2"))
     for name in which:
         cfg, nf = CASES[name]
         m = Modem(cfg)

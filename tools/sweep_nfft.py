@@ -11,6 +11,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "lte-gnu-radio-code_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, ROOT)
+from bench import ClockSampler  # noqa: E402
 from ofdm_b200 import Modem, ModemConfig  # noqa: E402
 from quick_bench import time_it  # noqa: E402
 
@@ -31,15 +33,19 @@ for n in (64, 128, 256, 512, 1024, 2048, 4096):
         taps = torch.tensor([0.3977, 0.7954 - 0.3977j, -0.1988, 0.0994, -0.0398], dtype=torch.complex64, device="cuda")
         rx = m.channel_awgn(tx, nf, taps / torch.linalg.norm(taps), 0.01, 3)
         out = m.rx_frames(rx, nf)
-        t_rx, _ = time_it(lambda: m.rx_frames(rx, nf, out=out), iters=8)
-        t_tx, _ = time_it(lambda: m.tx_modulate(bits, nf, out=tx), iters=8)
+        sampler = ClockSampler(0)
+        sampler.start()
+        t_rx, _ = time_it(lambda: m.rx_frames(rx, nf, out=out), iters=12)
+        t_tx, _ = time_it(lambda: m.tx_modulate(bits, nf, out=tx), iters=12)
+        clocks = sampler.stop()
         cnt = m.counters(bits, nf, bits_rx=out["hard"], eq=out["eq"], locked=out["locked"]).cpu().numpy()
         nsym = nf * cfg.d
         rx_b = nf * cfg.frame_len * 8 + nsym * ndb * (8 + 4 * bps) + nsym * cfg.hard_stride + nf * 9
         tx_b = nsym * cfg.hard_stride + nf * cfg.frame_len * 8
         r = dict(nfft=n, bps=bps, ndb=ndb, frames=nf, rx_ms=t_rx, rx_GBs=rx_b / t_rx / 1e6, rx_frac=rx_b / t_rx / 1e6 / PEAK,
                  rx_Msym_s=nsym / t_rx / 1e3, tx_ms=t_tx, tx_GBs=tx_b / t_tx / 1e6, tx_frac=tx_b / t_tx / 1e6 / PEAK,
-                 tx_Msym_s=nf * cfg.frame_syms / t_tx / 1e3, ber=cnt[0] / cnt[1], locked=cnt[4] / cnt[5])
+                 tx_Msym_s=nf * cfg.frame_syms / t_tx / 1e3, ber=cnt[0] / cnt[1], locked=cnt[4] / cnt[5], peak_GBs=PEAK,
+                 clocks=clocks)
         rows.append(r)
         print(json.dumps(r), flush=True)
         del m, bits, tx, rx, out
