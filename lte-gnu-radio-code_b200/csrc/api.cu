@@ -447,8 +447,17 @@ rx_sync_search_td8_kernel(const DevParams P, const float2 *__restrict__ x, long 
 // ------------------------------------------------------------------------------------------------
 using namespace ofdm;
 
+// Round 2: with the butterflies on the packed FP32 pipe and the power-table twiddles, the per-lane kernel with 16 points
+// per thread overtook the bulk-row kernel on the only grid where the rows fit beside the transform (LTE 20 MHz, 1200 of
+// 2048 bins, 64-QAM: 0.643 ms per-lane vs 0.677 ms bulk rows at prefetch depth 2, 0.672 at depth 1, same box; round 1,
+// scalar butterflies: 0.760 vs 0.708).  For 16-QAM / QPSK the rows never won (LTE grid 16-QAM 0.524 -> 0.610 ms, N=4096
+// 0.403 -> 0.406 ms).  The variant stays selectable (OFDM_BULK_MIN_N / OFDM_BULK16_MIN_N / OFDM_BULK4_MIN_N) and
+// covered by the parity and stress tests, but no plan asks for it by default.
+#ifndef OFDM_BULK_MIN_N_DEFAULT
+#define OFDM_BULK_MIN_N_DEFAULT 8192
+#endif
 #ifndef OFDM_BULK16_MIN_N_DEFAULT
-#define OFDM_BULK16_MIN_N_DEFAULT 8192          // off until measured
+#define OFDM_BULK16_MIN_N_DEFAULT 8192
 #endif
 #ifndef OFDM_BULK4_MIN_N_DEFAULT
 #define OFDM_BULK4_MIN_N_DEFAULT 8192
@@ -668,7 +677,7 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
         // SM) stall on exactly that (ncu, N=4096 16-QAM: 26 % long-scoreboard on the demapper's register reuse).
         // OFDM_BULK16_MIN_N / OFDM_BULK4_MIN_N: smallest N whose 16-QAM / QPSK-BPSK rows leave through the async proxy.
         const char *eb = getenv("OFDM_BULK_MIN_N"), *eb16 = getenv("OFDM_BULK16_MIN_N"), *eb4 = getenv("OFDM_BULK4_MIN_N");
-        const int bulk_min = p->bps == 6 ? (eb ? atoi(eb) : 1024)
+        const int bulk_min = p->bps == 6 ? (eb ? atoi(eb) : OFDM_BULK_MIN_N_DEFAULT)
                                          : (p->bps == 4 ? (eb16 ? atoi(eb16) : OFDM_BULK16_MIN_N_DEFAULT)
                                                         : (eb4 ? atoi(eb4) : OFDM_BULK4_MIN_N_DEFAULT));
         if (pk == 0 && N >= bulk_min && ((ndb * p->bps) & 3) == 0 && (ndb & 1) == 0) {

@@ -181,6 +181,10 @@ template <int LOG2N> struct PptTx {
 #ifndef OFDM_TX_LAY_PAD
 #define OFDM_TX_LAY_PAD 1
 #endif
+// N = 64: exchange through warp shuffles instead of shared memory (see Pass::run).  B200 A/B in DESIGN.md 3.11.
+#ifndef OFDM_EXCH_SHFL_64
+#define OFDM_EXCH_SHFL_64 0
+#endif
 #ifndef OFDM_RX_LAY_PAD
 #define OFDM_RX_LAY_PAD 0
 #endif
@@ -421,40 +425,48 @@ __device__ __forceinline__ void bfly_strided(float2 (&v)[PPT], int b) {
     }
 }
 
-// One pass P of the transform, fully unrolled through template recursion.  Butterfly b of a thread
-// works on registers b + q*B (B = PPT/R butterflies per thread), i.e. on elements j + b*T + q*N/R.
-// TWR: the twiddles of the LAST pass depend only on the thread (its element j + b*T never leaves the first Ns of the
-// pass), so a kernel with registers to spare keeps them in twreg[b*(R-1) + q-1] instead of reading the table.
-template <class C, bool INV, int GROUPS, int P, bool SB = false, bool TWR = false, bool MZ = false> struct Pass {
-    static __device__ __forceinline__ void run(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1,
-                                               int j, int gid, int &pp, const float2 *twreg = nullptr) {
-        constexpr int R = C::radix(P), Ns = C::ns(P), B = C::PPT / R;
-        if (P > 0 && TWR && P == C::NPASS - 1) {
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-#pragma unroll
-                for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], twreg[b * (R - 1) + q - 1]);
-            }
-        } else if (P > 0) {
+// Split-phase group barrier (mbarrier).  An exchange is "write my outputs -- everybody has written -- read my inputs".
+// With bar.sync a warp that has written sits idle until the slowest warp of the group arrives; the LTE receiver spends a
+// fifth of its warp cycles there (ncu: barrier 1.58 of 7.6 cycles per issued instruction, two CTAs of eight warps per
+// SM).  Arriving on an mbarrier does not block: the thread arrives, fetches the NEXT pass' twiddle row and forms its
+// powers (work that does not depend on the exchanged data), and only then waits for the phase to complete.
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ unsigned long long mbar_arrive(unsigned bar) {
+    unsigned long long tok;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(tok) : "r"(bar) : "memory");
+    return tok;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned long long tok) {
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "l"(tok) : "memory");
+    } while (!done);
+}
+
+// Twiddles of pass P for one thread: B butterflies x (R-1) multipliers, from the full, chained or power table.
+template <class C, int P> struct PassTw {
+    static constexpr int R = C::radix(P), Ns = C::ns(P), B = C::PPT / (R > 0 ? R : 1);
+    static constexpr int COUNT = (P > 0 && P < C::NPASS) ? B * (R - 1) : 1;
+    static __device__ __forceinline__ void load(float2 (&wo)[COUNT], const float2 *tws, int j) {
+        if constexpr (P > 0 && P < C::NPASS) {
             constexpr int off = C::tw_off(P);
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 const float2 *t = tws + off + ((j + b * C::T) & (Ns - 1));
+                float2 w[R];
                 if constexpr (C::CH == 0) {
 #pragma unroll
-                    for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], t[(q - 1) * Ns]);
+                    for (int q = 1; q < R; ++q) w[q] = t[(q - 1) * Ns];
                 } else if constexpr (C::CH == 2) {
                     // one row: W^r; every other multiplier is a product of two smaller ones (depth log2 R)
-                    float2 w[R];
                     w[1] = t[0];
 #pragma unroll
                     for (int q = 2; q < R; ++q) w[q] = cmul(w[q / 2], w[q - q / 2]);
-#pragma unroll
-                    for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], w[q]);
                 } else {
-                    // rows hold W^(1*r), W^(2*r), W^(4*r), ..; multiplier q = 2^a + rest is built as w[2^a] * w[rest],
-                    // visiting q in an order that lets every product be used and dropped at once
-                    float2 w[R];
+                    // rows hold W^(1*r), W^(2*r), W^(4*r), ..; multiplier q = 2^a + rest is built as w[2^a] * w[rest]
 #pragma unroll
                     for (int a = 0; (1 << a) < R; ++a) w[1 << a] = t[a * Ns];
 #pragma unroll
@@ -462,14 +474,66 @@ template <class C, bool INV, int GROUPS, int P, bool SB = false, bool TWR = fals
                         const int hi = 1 << (31 - __builtin_clz((unsigned)q));
                         if (q != hi) w[q] = cmul(w[hi], w[q - hi]);
                     }
-#pragma unroll
-                    for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], w[q]);
                 }
+#pragma unroll
+                for (int q = 1; q < R; ++q) wo[b * (R - 1) + q - 1] = w[q];
+            }
+        }
+    }
+    template <bool INV> static __device__ __forceinline__ void apply(float2 (&v)[C::PPT], const float2 *w) {
+        if constexpr (P > 0 && P < C::NPASS) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[b + q * B] = twmul<INV>(v[b + q * B], w[b * (R - 1) + q - 1]);
+            }
+        }
+    }
+};
+
+// One pass P of the transform, fully unrolled through template recursion.  Butterfly b of a thread
+// works on registers b + q*B (B = PPT/R butterflies per thread), i.e. on elements j + b*T + q*N/R.
+// TWR: the twiddles of the LAST pass depend only on the thread (its element j + b*T never leaves the first Ns of the
+// pass), so a kernel with registers to spare keeps them in twreg[b*(R-1) + q-1] instead of reading the table.
+// SPLIT: exchanges wait on the group's mbarrier (address `mbar`) after preparing the next pass' twiddles; TWDONE: this
+// pass' twiddles were applied by the caller (the previous pass, in its split-phase exchange).
+template <class C, bool INV, int GROUPS, int P, bool SB = false, bool TWR = false, bool MZ = false, bool SPLIT = false,
+          bool TWDONE = false>
+struct Pass {
+    static __device__ __forceinline__ void run(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1,
+                                               int j, int gid, int &pp, const float2 *twreg = nullptr, unsigned mbar = 0) {
+        constexpr int R = C::radix(P), Ns = C::ns(P), B = C::PPT / R;
+        if constexpr (P > 0 && !TWDONE) {
+            if constexpr (TWR && P == C::NPASS - 1) {
+                PassTw<C, P>::template apply<INV>(v, twreg);
+            } else {
+                float2 w[PassTw<C, P>::COUNT];
+                PassTw<C, P>::load(w, tws, j);
+                PassTw<C, P>::template apply<INV>(v, w);
             }
         }
 #pragma unroll
         for (int b = 0; b < B; ++b) bfly_strided<INV, R, B, C::PPT, (MZ && P == 0)>(v, b);
-        if (P < C::NPASS - 1) {
+        if constexpr (P < C::NPASS - 1 && C::LOG2N == 6 && OFDM_EXCH_SHFL_64 != 0) {
+            // N = 64: the one exchange is an 8 x 8 transpose between the 8 lanes of the group and their 8 registers
+            // (element 8j + q leaves thread j, arrives in register j of thread q).  Shuffle form, for the A/B against the
+            // shared-memory form (OFDM_EXCH_SHFL_64, default 0): three stages, lane distance 4, 2, 1; per stage four
+            // register pairs swap their off-diagonal halves with one 64-bit shuffle each.
+#pragma unroll
+            for (int D = 4; D >= 1; D >>= 1) {
+                const bool up = (j & D) != 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if (r & D) continue;
+                    const float2 send = up ? v[r] : v[r | D];
+                    float2 recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, D);
+                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, D);
+                    if (up) v[r] = recv; else v[r | D] = recv;
+                }
+            }
+            Pass<C, INV, GROUPS, P + 1, SB, TWR, MZ, SPLIT>::run(v, tws, buf0, buf1, j, gid, pp, twreg, mbar);
+        } else if constexpr (P < C::NPASS - 1) {
             // only full-radix passes are followed by an exchange (B == 1)
             // SB: one buffer, so a second barrier keeps the next exchange's writes behind these reads
             float2 *buf = SB ? buf0 : ((pp & 1) ? buf1 : buf0);
@@ -477,26 +541,38 @@ template <class C, bool INV, int GROUPS, int P, bool SB = false, bool TWR = fals
             const int e = (j / Ns) * (Ns * C::PPT) + (j & (Ns - 1));
 #pragma unroll
             for (int q = 0; q < C::PPT; ++q) buf[lay<C, P>(e + q * Ns)] = pin(v[q]);
-            group_sync<C::T, GROUPS>(gid);
+            if constexpr (SPLIT && !SB && C::T > 32 && !(TWR && P + 1 == C::NPASS - 1)) {
+                const unsigned long long tok = mbar_arrive(mbar);
+                float2 wn[PassTw<C, P + 1>::COUNT];
+                PassTw<C, P + 1>::load(wn, tws, j);
+                mbar_wait(mbar, tok);
 #pragma unroll
-            for (int m = 0; m < C::PPT; ++m) v[m] = buf[lay<C, P>(j + m * C::T)];
-            if (SB) group_sync<C::T, GROUPS>(gid);
-            Pass<C, INV, GROUPS, P + 1, SB, TWR, MZ>::run(v, tws, buf0, buf1, j, gid, pp, twreg);
+                for (int m = 0; m < C::PPT; ++m) v[m] = buf[lay<C, P>(j + m * C::T)];
+                PassTw<C, P + 1>::template apply<INV>(v, wn);
+                Pass<C, INV, GROUPS, P + 1, SB, TWR, MZ, SPLIT, true>::run(v, tws, buf0, buf1, j, gid, pp, twreg, mbar);
+            } else {
+                group_sync<C::T, GROUPS>(gid);
+#pragma unroll
+                for (int m = 0; m < C::PPT; ++m) v[m] = buf[lay<C, P>(j + m * C::T)];
+                if (SB) group_sync<C::T, GROUPS>(gid);
+                Pass<C, INV, GROUPS, P + 1, SB, TWR, MZ, SPLIT>::run(v, tws, buf0, buf1, j, gid, pp, twreg, mbar);
+            }
         }
     }
 };
-template <class C, bool INV, int GROUPS, bool SB, bool TWR, bool MZ> struct Pass<C, INV, GROUPS, 4, SB, TWR, MZ> {
+template <class C, bool INV, int GROUPS, bool SB, bool TWR, bool MZ, bool SPLIT, bool TWDONE>
+struct Pass<C, INV, GROUPS, 4, SB, TWR, MZ, SPLIT, TWDONE> {
     static __device__ __forceinline__ void run(float2 (&)[C::PPT], const float2 *, float2 *, float2 *, int, int, int &,
-                                               const float2 * = nullptr) {}
+                                               const float2 * = nullptr, unsigned = 0) {}
 };
 
 // In-place transform of the group's symbol.  pp is the running ping-pong selector (kept across
 // calls so that consecutive transforms never need a second barrier per exchange).
-template <class C, bool INV, int GROUPS, bool SB = false, bool TWR = false, bool MZ = false>
+template <class C, bool INV, int GROUPS, bool SB = false, bool TWR = false, bool MZ = false, bool SPLIT = false>
 __device__ __forceinline__ void fft_group(float2 (&v)[C::PPT], const float2 *tws, float2 *buf0, float2 *buf1, int j,
-                                          int gid, int &pp, const float2 *twreg = nullptr) {
+                                          int gid, int &pp, const float2 *twreg = nullptr, unsigned mbar = 0) {
     static_assert(!MZ || (C::PPT == 16 && C::radix(0) == 16), "MZ prunes the first radix-16 pass");
-    Pass<C, INV, GROUPS, 0, SB, TWR, MZ>::run(v, tws, buf0, buf1, j, gid, pp, twreg);
+    Pass<C, INV, GROUPS, 0, SB, TWR, MZ, SPLIT>::run(v, tws, buf0, buf1, j, gid, pp, twreg, mbar);
 }
 
 // ------------------------------------------------------------------------------------------------

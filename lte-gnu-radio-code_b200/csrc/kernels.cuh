@@ -415,8 +415,13 @@ __device__ __forceinline__ void pack_bits(const uint8_t *hb, unsigned *pk, uint8
 #ifndef OFDM_PF_DEPTH
 #define OFDM_PF_DEPTH 1
 #endif
-// ... and for the bulk-row variant (64-QAM, N >= 1024), whose 2 CTAs x 8 warps per SM leave DRAM latency exposed: two
-// symbols ahead.  B200, LTE 20 MHz 64-QAM: 0.697 -> 0.662 ms; the per-lane kernels lose 2-3 % with it and stay at 1.
+// Framed receiver: transforms from this size on exchange through split-phase (mbarrier) barriers; 13 = never.
+#ifndef OFDM_SPLIT_MIN_LOG2N
+#define OFDM_SPLIT_MIN_LOG2N 13
+#endif
+// ... and for the bulk-row variant (64-QAM, N >= 1024), whose 2 CTAs x 8 warps per SM leave DRAM latency exposed: three
+// symbols ahead.  B200, LTE 20 MHz 64-QAM, one box, ms per launch (depth 1 / 2 / 3): 0.672 / 0.677 / 0.648 with the
+// power-table twiddles, 0.697 / 0.652 / -- with chained rows; the per-lane kernels lose 2-3 % at depth 2 and stay at 1.
 #ifndef OFDM_PF_DEPTH_BULK
 #define OFDM_PF_DEPTH_BULK 2
 #endif
@@ -432,7 +437,7 @@ struct Smem {
     static constexpr int FFT_BYTES = GROUPS * GSTRIDE * 8;
     static constexpr int TW_BYTES = C::TW_ENTRIES * 8;                              // pass twiddles, shared by the CTA
     static constexpr int STAGE_BYTES = TXK ? 0 : PFD * THREADS * C::PPT * 8;   // symbols in flight: PPT samples per thread each (RX)
-    static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8;             // 64 floats + 16 u64 per group
+    static constexpr int RED_BYTES = GROUPS * 64 * 4 + GROUPS * 16 * 8 + GROUPS * 16; // 64 floats + 16 u64 + one mbarrier (16-byte slot) per group
     static constexpr int PK_BYTES = TXK ? 0 : 3 * C::N / 4 + 16;                    // packed row staged for aligned stores
     static constexpr int TX_ROW_BYTES = 3 * C::N / 4 + 16;                          // one packed payload row at any 16-byte phase (TX)
     static_assert((3 * C::N / 4 + 30) / 16 <= C::T, "one 16-byte chunk per thread must cover a payload row");
@@ -465,6 +470,9 @@ struct Smem {
     }
     __device__ static float *redf(unsigned char *s, int gid) {
         return reinterpret_cast<float *>(s + OFF_RED + GROUPS * 16 * 8) + gid * 64;
+    }
+    __device__ static unsigned long long *mbar(unsigned char *s, int gid) {
+        return reinterpret_cast<unsigned long long *>(s + OFF_RED + GROUPS * 16 * 8 + GROUPS * 64 * 4) + 2 * gid;
     }
     __device__ static uint8_t *hb(unsigned char *s, int gid) { return s + OFF_HB + gid * HB_STRIDE; }
     __device__ static float2 *lut(unsigned char *s) { return reinterpret_cast<float2 *>(s + OFF_LUT); }
@@ -548,14 +556,14 @@ __device__ __forceinline__ void sync_accumulate(const DevParams &P, const float2
 }
 
 // c[] holds the correlation sums on entry and is overwritten by the delay bank.
-template <class C, int GROUPS, bool SB = false>
+template <class C, int GROUPS, bool SB = false, bool SPLIT = false>
 __device__ __forceinline__ void sync_finish(const DevParams &P, float2 (&c)[C::PPT], float pw, const float2 *tws,
                                             float2 *b0, float2 *b1, float *redf, unsigned long long *redu, int j,
-                                            int gid, int &pp, float &p_est, float &peak, int &delay) {
+                                            int gid, int &pp, float &p_est, float &peak, int &delay, unsigned mbar = 0) {
     constexpr int T = C::T, PPT = C::PPT;
     pw = group_sum<T, GROUPS>(pw, redf, j, gid);
     p_est = pw > 0.f ? sqrtf((float)P.mm / pw) : 0.f;
-    fft_group<C, true, GROUPS, SB>(c, tws, b0, b1, j, gid, pp);
+    fft_group<C, true, GROUPS, SB, false, false, SPLIT>(c, tws, b0, b1, j, gid, pp, nullptr, mbar);
     unsigned long long key = 0ull;
 #pragma unroll
     for (int m = 0; m < PPT; ++m) {
@@ -871,7 +879,9 @@ __device__ __forceinline__ void data_epilogue_pilot(const DevParams &P, const Da
     float2 *hp = S::hp(smem_raw, gid);                                                 \
     float *ls = P.ls_stride ? reinterpret_cast<float *>(smem_raw + S::BYTES) + gid * P.ls_stride : nullptr; \
     float2 *es = reinterpret_cast<float2 *>(smem_raw + S::BYTES + GROUPS * P.ls_stride * 4) + gid * P.es_stride; \
-    (void)redu; (void)redf; (void)stage; (void)hp; (void)ls; (void)es;                 \
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(S::mbar(smem_raw, gid));   \
+    if (j == 0) mbar_init(mbar, T);                      /* split-phase exchanges (fft_core.cuh, Pass SPLIT) */ \
+    (void)redu; (void)redf; (void)stage; (void)hp; (void)ls; (void)es; (void)mbar;      \
     for (int i = j; i < S::HB_STRIDE; i += T) hb[i] = 0;                               \
     fill_twiddles<C>(S::tws(smem_raw), P.tw, tid, S::THREADS);                              \
     __syncthreads();                                                                   \
@@ -946,6 +956,8 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                  float2 *__restrict__ H_out, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
                  uint8_t *__restrict__ hard_out) {
     constexpr int DEPTH = EPI == EPI_BULK ? OFDM_PF_DEPTH_BULK : OFDM_PF_DEPTH;
+    // exchanges that wait on an mbarrier after preparing the next pass' twiddles instead of bar.sync (fft_core.cuh)
+    constexpr bool SPLIT = C::LOG2N >= OFDM_SPLIT_MIN_LOG2N && !SB;
     OFDM_KERNEL_PROLOGUE_(GROUPS, false, PIL, GSM, SB, DEPTH)
     constexpr int N = C::N;
     const int L = N + P.cp, fs = P.m0 + P.d;
@@ -1016,7 +1028,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
             }
             if (!CFO || s >= P.m0) {                 // with a CFO bank the preamble is transformed per hypothesis below
                 if (CFO) rotate_pts<T, PPT>(P, cur, hyp, pos + wcur, j);
-                fft_group<C, false, GROUPS, SB>(cur, tws, b0, b1, j, gid, pp);
+                fft_group<C, false, GROUPS, SB, false, false, SPLIT>(cur, tws, b0, b1, j, gid, pp, nullptr, mbar);
             }
             if (s < P.m0) {
                 if (!CFO) sync_accumulate<C>(P, cur, s, j, ys, ydup, pw);
@@ -1038,13 +1050,13 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                                 float2 v[C::PPT];
                                 load_pts<T, PPT>(v, x, pos + (long long)s2 * L, n_samples, j);
                                 rotate_pts<T, PPT>(P, v, hh, pos + (long long)s2 * L, j);
-                                fft_group<C, false, GROUPS, SB>(v, tws, b0, b1, j, gid, pp);
+                                fft_group<C, false, GROUPS, SB, false, false, SPLIT>(v, tws, b0, b1, j, gid, pp, nullptr, mbar);
                                 sync_accumulate<C>(P, v, s2, j, ys, ydup, pw);
                             }
                             if (h < P.n_cfo) {
                                 float pe, pk;
                                 int dl;
-                                sync_finish<C, GROUPS, SB>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, pe, pk, dl);
+                                sync_finish<C, GROUPS, SB, SPLIT>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, pe, pk, dl, mbar);
                                 if (pk > peak) {
                                     peak = pk;
                                     p_est = pe;
@@ -1061,7 +1073,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                     for (int m = 0; m < PPT; ++m) {
                         if (GSM) G.s[m * T] = ys[m]; else keep[GSM ? 0 : m] = ys[m];
                     }
-                    if (!CFO) sync_finish<C, GROUPS, SB>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay);
+                    if (!CFO) sync_finish<C, GROUPS, SB, SPLIT>(P, ys, pw, tws, b0, b1, redf, redu, j, gid, pp, p_est, peak, delay, mbar);
                     const float sc = p_est * P.chanest_scale;
 #pragma unroll
                     for (int m = 0; m < PPT; ++m) {

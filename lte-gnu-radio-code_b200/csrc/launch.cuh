@@ -97,7 +97,7 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
     DevParams Qp = P;
     Qp.es_stride = 0;
     if (P.bulk_rows && !(P.bps == 6 && LOG2N <= 6)) Qp.ls_stride = 0;
-    const bool bulk_ok = P.bulk_rows && !P.pil_k && !P.n_cfo && eq != nullptr && ((reinterpret_cast<unsigned long long>(eq) & 15ull) == 0) &&
+    const bool bulk_ok = P.bulk_rows && !P.pil_k && !P.n_cfo && ((reinterpret_cast<unsigned long long>(eq) & 15ull) == 0) &&
                          ((reinterpret_cast<unsigned long long>(llr) & 15ull) == 0);
     const bool dense = (long long)P.ndb * 64 >= (long long)OFDM_DENSE_MIN_FILL64 * C::N;
     const bool cpp = P.cp_extra != 0;                           // CP pattern: never together with pilots / hypothesis bank

@@ -20,12 +20,14 @@ class synch_and_chan_est(RxBlockBase):
 
     def __init__(self, num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr,
                  directory_name, file_name_cest, diagnostics, genie, *, modulation=2, zc_root=None, device=None,
-                 fused=None):
+                 fused=None, carry_over=False):
         gr.sync_block.__init__(self, name="SynchAndChanEst", in_sig=[np.complex64], out_sig=[np.complex64])
         self.diagnostics = diagnostics
         self._setup(num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr, 0.4,
                     directory_name, file_name_cest, diagnostics, genie, modulation, zc_root, rows=100,
                     device=device, fused=fused)
+        self.carry_over = bool(carry_over)
+        self._init_stream()
         self.cor_obs = -1
         self.time_synch_ref = np.zeros((self.max_num_corr, 3))
 
@@ -34,12 +36,14 @@ class synch_and_chan_est(RxBlockBase):
         r = self._fused_call(in0)
         k = r.obs_after_search + 1
         if k > 0:
-            self.time_synch_ref[:k] = np.ctypeslib.as_array(r.time_synch_ref, (k, 3))
+            self.time_synch_ref[:k] = self._tsr_view[:k]
         if r.n_new_locks and self.diagnostics == 1:
             stamp = datetime.datetime.now().strftime("%Y_%m_%d_%Hh_%Mm")
             self._dump_chan(self._last_chan_time[-1], str(self.directory_name) + stamp + str(self.file_name_cest) + ".pckl")
 
     def work(self, input_items, output_items):
+        if self.carry_over:                                  # additive streaming mode, see ofdm_b200/rx_block.py
+            return self._work_carry_over(input_items, output_items)
         in0 = input_items[0]
         out = output_items[0]
         c = self.cfg

@@ -61,6 +61,9 @@ class RxBlockBase(gr.sync_block):
                 _lib.check(_lib.lib().ofdm_rx_block_create(self.modem._h, 0 if self.compat == "utsa" else 1, rows, C.byref(h)))
             self._blk = h
             self._res = _lib.RxBlockResult()
+            self._res_ref = C.byref(self._res)
+            self._work_fn = _lib.lib().ofdm_rx_block_work
+            self._views = None
 
     work_fused = None          # set by the subclasses that have a fused path
 
@@ -91,19 +94,24 @@ class RxBlockBase(gr.sync_block):
         a = in0 if (isinstance(in0, np.ndarray) and in0.dtype == np.complex64 and in0.flags.c_contiguous) \
             else np.ascontiguousarray(in0, dtype=np.complex64)
         r = self._res
-        _lib.check(_lib.lib().ofdm_rx_block_work(self._blk, C.c_void_p(a.ctypes.data), len(a), C.byref(r)))
-        if r.n_new_locks:
-            k = r.n_new_locks
-            rows = np.ctypeslib.as_array(r.new_rows, (k,))
-            ht = np.ctypeslib.as_array(r.chan_time, (k, 2 * c.nfft)).view(np.complex64)
-            se = np.ctypeslib.as_array(r.synch_freq, (k, 2 * c.mm)).view(np.complex64)
-            self.est_chan_time[rows] = ht
-            self.est_synch_freq[rows] = se
-            self._last_chan_time = ht
-        if r.n_demod:
-            k = r.n_demod
-            rows = np.ctypeslib.as_array(r.demod_rows, (k,))
-            self.est_data_freq[rows] = np.ctypeslib.as_array(r.data_freq, (k, 2 * c.num_data_bins)).view(np.complex64)
+        _lib.check(self._work_fn(self._blk, a.ctypes.data, len(a), self._res_ref))
+        if self._views is None:
+            # the result pointers address pinned memory owned by the block object and never move: wrap them once
+            ml, ms = (1, self.rows) if self.compat == "utsa" else (100, 100)
+            as_arr = np.ctypeslib.as_array
+            self._views = (as_arr(r.new_rows, (ml,)), as_arr(r.chan_time, (ml, 2 * c.nfft)).view(np.complex64),
+                           as_arr(r.synch_freq, (ml, 2 * c.mm)).view(np.complex64), as_arr(r.demod_rows, (ms,)),
+                           as_arr(r.data_freq, (ms, 2 * c.num_data_bins)).view(np.complex64),
+                           as_arr(r.time_synch_ref, (r.n_state_rows, 3)))
+        new_rows, ht, se, dm_rows, eq, self._tsr_view = self._views
+        k = r.n_new_locks
+        if k:
+            self.est_chan_time[new_rows[:k]] = ht[:k]
+            self.est_synch_freq[new_rows[:k]] = se[:k]
+            self._last_chan_time = ht[:k]
+        k = r.n_demod
+        if k:
+            self.est_data_freq[dm_rows[:k]] = eq[:k]
         return r
 
     def _upload(self, in0):
@@ -213,3 +221,79 @@ class RxBlockBase(gr.sync_block):
         dv = self._to_device(i64=(start,), i32=(delay, hrow) if hyp is None else (delay, hrow, hyp))
         eq, _, _ = self.modem.demod(rx, dv[0], dv[1], dv[2], self._d_H, hyp=None if hyp is None else dv[3])
         self.est_data_freq[np.asarray(rows)] = eq.cpu().numpy()
+
+    # ---- streaming mode (additive; SURVEY.md 5, "partial frames") ------------------------------------------------
+    # The reference looks at each scheduler buffer on its own: a trial needs its whole window inside the buffer
+    # (SynchAndChanEst.py:144, synch_and_chan_est.py:147) and a data symbol likewise (:223 / :226), so a frame that
+    # straddles two work() calls is lost, and frames are re-demodulated when buffers overlap.  With the keyword-only
+    # constructor argument carry_over=True the block treats successive buffers as ONE stream instead: it keeps the
+    # samples it could not finish (from the first incomplete frame, or from the first trial whose window did not fit),
+    # prepends them to the next buffer, and emits every frame exactly once -- loop A's trial arithmetic and lock rule
+    # (every acceptable lock, each more than 2CP+N samples after the one before), the LS estimate of that lock, and
+    # loop B's equaliser for the frame's D data symbols with that lock's estimate.  Output: the equalised data symbols
+    # of the frames completed in this call, in stream order, at out[0:last_written].  The result does not depend on
+    # how the stream is cut into buffers (tests/test_gpu_blocks.py: chunked == whole, bit for bit).
+    def _init_stream(self):
+        self._tail = np.zeros(0, np.complex64)
+        self._stream_prev = None           # window start of the last emitted lock, relative to the current tail
+        self.stream_frames = 0             # frames emitted so far
+        self.stream_locks = []             # (absolute window start, delay, int(peak)) of every emitted frame
+        self._stream_origin = 0            # absolute sample index of _tail[0]
+
+    def work_stream(self, in0):
+        """-> complex64 [frames * D, ndb]: equalised data symbols of the frames completed by this buffer."""
+        c = self.cfg
+        N, CP, L = c.nfft, c.cp_len, c.sym_len
+        buf = np.concatenate((self._tail, np.ascontiguousarray(in0, dtype=np.complex64)))
+        n = len(buf)
+        nv = self._n_valid_trials(n)
+        locks = []
+        cut = None                                               # where the kept tail starts
+        if nv > 0:
+            rx = self._upload(buf)
+            peak, delay = self._search(rx, n)[:2]
+            prev = self._stream_prev
+            for P in np.nonzero(peak > c.gate * c.mm)[0]:
+                start = int(P) * c.stride + CP
+                if prev is not None and start - prev <= 2 * CP + N:
+                    continue
+                if start + (c.m0 + c.d - 1) * L + N > n:         # the frame's last data window is not here yet
+                    cut = start - CP
+                    break
+                locks.append((start, int(delay[P]), int(peak[P])))
+                prev = start
+            self._stream_prev = prev
+        first_untried = nv * c.stride                            # start - CP of the first trial that did not fit
+        if cut is None:
+            cut = first_untried
+        if locks:
+            cut = max(cut, 0)
+        cut = max(0, min(cut, n))
+        out = np.zeros((0, c.num_data_bins), np.complex64)
+        if locks:
+            k = len(locks)
+            pos = [s for s, _, _ in locks]
+            dv = self._to_device(i64=(pos,), i32=([d for _, d, _ in locks],))
+            h, _, _ = self.modem.chanest(rx, dv[0], dv[1])
+            starts = [s + (c.m0 + j) * L for s in pos for j in range(c.d)]
+            dls = [d for _, d, _ in locks for _ in range(c.d)]
+            rows = [i for i in range(k) for _ in range(c.d)]
+            dv = self._to_device(i64=(starts,), i32=(dls, rows))
+            eq, _, _ = self.modem.demod(rx, dv[0], dv[1], dv[2], h)
+            out = eq.cpu().numpy()
+            self.stream_locks += [(self._stream_origin + s, d, p) for s, d, p in locks]
+            self.stream_frames += k
+        self._tail = buf[cut:].copy()
+        self._stream_origin += cut
+        if self._stream_prev is not None:
+            self._stream_prev -= cut
+        return out
+
+    def _work_carry_over(self, input_items, output_items):
+        out = output_items[0]
+        eq = self.work_stream(input_items[0]).reshape(-1)
+        m = min(len(out), eq.size)
+        out[0:m] = eq[:m]
+        self.last_written = m
+        self.count += 1
+        return len(out)

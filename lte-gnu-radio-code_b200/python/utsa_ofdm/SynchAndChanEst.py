@@ -18,7 +18,7 @@ class SynchAndChanEst(RxBlockBase):
 
     def __init__(self, num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr,
                  scale_factor_gate, directory_name, file_name_cest, diagnostics, genie, channel="Fading", *,
-                 modulation=2, zc_root=None, device=None, fused=None):
+                 modulation=2, zc_root=None, device=None, fused=None, carry_over=False):
         gr.sync_block.__init__(self, name="SynchAndChanEst", in_sig=[np.complex64], out_sig=[np.complex64])
         self.channel = channel
         self.scale_factor_gate = scale_factor_gate
@@ -26,6 +26,9 @@ class SynchAndChanEst(RxBlockBase):
         self._setup(num_ofdm_symb, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, snr, scale_factor_gate,
                     directory_name, file_name_cest, diagnostics, genie, modulation, zc_root,
                     rows=int(num_ofdm_symb), device=device, fused=fused)
+        self.carry_over = bool(carry_over)
+        self._init_stream()
+        self._keep_rows = None
         self.SNR_lin = 10 ** (self.SNR / 20)
         self.corr_obs = -1
         self.time_synch_ref = np.zeros(3)
@@ -33,11 +36,13 @@ class SynchAndChanEst(RxBlockBase):
     def work_fused(self, in0):
         """Loops A and B in one C-ABI call (ofdm_rx_block_work, mode 0); the lock record comes back with it."""
         r = self._fused_call(in0)
-        self.time_synch_ref[:] = [r.time_synch_ref[0], r.time_synch_ref[1], r.time_synch_ref[2]]
+        self.time_synch_ref[:] = self._tsr_view[0]
         if r.n_new_locks and self.diagnostic == 1:
             self._dump_chan(self._last_chan_time[0], str(self.directory_name) + "_" + str(self.file_name_cest))
 
     def work(self, input_items, output_items):
+        if self.carry_over:                                  # additive streaming mode, see ofdm_b200/rx_block.py
+            return self._work_carry_over(input_items, output_items)
         in0 = input_items[0]
         out = output_items[0]
         c = self.cfg
@@ -82,7 +87,9 @@ class SynchAndChanEst(RxBlockBase):
     def _pack(self, out, output_items, n_data_symb):
         c, fsyms = self.cfg, self.cfg.frame_syms
         # packing (:249-262)
-        data_demod = np.delete(self.est_data_freq, list(range(3, self.rows, fsyms)), axis=0)
+        if self._keep_rows is None:                         # np.delete(est_data_freq, range(3, rows, M0+D), axis=0), :249
+            self._keep_rows = np.setdiff1d(np.arange(self.rows), np.arange(3, self.rows, fsyms))
+        data_demod = self.est_data_freq[self._keep_rows]
         data_out = data_demod.reshape(-1)[: n_data_symb * c.num_data_bins]
         self.last_written = 0
         if self.count > 0:

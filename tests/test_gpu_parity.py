@@ -115,6 +115,62 @@ def test_rx_frames_matches_oracle(kw):
     assert rel_err(got["llr"].cpu().numpy(), ref_llr) < RTOL
 
 
+BULK_CASES = [      # (numerology, environment that selects the bulk-row epilogue for it)
+    (dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=3, bps=6), {"OFDM_BULK_MIN_N": "1024"}),
+    (dict(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=8, bps=6),
+     {"OFDM_BULK_MIN_N": "1024"}),
+    (dict(nfft=1024, cp_len=72, num_synch_bins=1022, num_data_bins=600, m0=2, d=2, bps=4), {"OFDM_BULK16_MIN_N": "1024"}),
+    (dict(nfft=4096, cp_len=288, num_synch_bins=4094, num_data_bins=2400, m0=1, d=2, bps=2), {"OFDM_BULK4_MIN_N": "1024"}),
+]
+
+
+@pytest.mark.parametrize("kw,env", BULK_CASES, ids=lambda v: "N%d_b%d" % (v["nfft"], v["bps"]) if "nfft" in v else "")
+def test_bulk_row_variant_matches_oracle_and_the_per_lane_kernel(kw, env, monkeypatch):
+    """The bulk-row epilogue (rows assembled in shared memory, one cp.async.bulk per row) is no longer any plan's
+    default (csrc/api.cu: the per-lane kernels overtook it in round 2) but stays selectable through the environment:
+    parity against the oracle, hard bits identical to the per-lane kernel's, and -- guard bands -- nothing written
+    outside the output windows."""
+    lane = make(dict(kw, snr=100, gate=0.5, noise_var=0.01))
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m = make(dict(kw, snr=100, gate=0.5, noise_var=0.01))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    n_frames = 5
+    rng = np.random.default_rng(7)
+    per_sym = cfg.num_data_bins * cfg.bps
+    bits = rng.integers(0, 2, n_frames * cfg.d * per_sym)
+    tx = oo.tx_modulate(bits, prm, n_frames)
+    rx = oo.add_awgn(oo.apply_channel(tx, oo.reference_channel(cfg.nfft))[:len(tx)], 1e-4, rng).astype(np.complex64)
+    ref = oo.rx_frames(rx, n_frames, prm)
+    d_rx = torch.from_numpy(rx).cuda()
+    nd = n_frames * cfg.d
+    G = 256                                                    # sentinel floats either side of every output
+    raw = {k: torch.full((n + 2 * G,), -7.5, dtype=torch.float32, device="cuda")
+           for k, n in (("eq", nd * cfg.num_data_bins * 2), ("llr", nd * per_sym))}
+    hard_raw = torch.full((nd * cfg.hard_stride + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+    out = dict(delay=torch.empty(n_frames, dtype=torch.int32, device="cuda"), peak=torch.empty(n_frames, device="cuda"),
+               locked=torch.empty(n_frames, dtype=torch.uint8, device="cuda"), h=None, hyp=None,
+               eq=torch.view_as_complex(raw["eq"][G:-G].view(nd, cfg.num_data_bins, 2)),
+               llr=raw["llr"][G:-G].view(nd, per_sym), hard=hard_raw[G:-G].view(nd, cfg.hard_stride))
+    before = __import__("ofdm_b200").launch_count()
+    m.rx_frames(d_rx, n_frames, out=out)
+    torch.cuda.synchronize()
+    assert __import__("ofdm_b200").launch_count() == before + 1
+    for k in ("eq", "llr"):
+        assert bool((raw[k][:G] == -7.5).all()) and bool((raw[k][-G:] == -7.5).all()), k
+    assert bool((hard_raw[:G] == 0xA5).all()) and bool((hard_raw[-G:] == 0xA5).all())
+    assert np.array_equal(out["delay"].cpu().numpy(), ref["delay"])
+    assert rel_err(out["eq"].cpu().numpy().reshape(ref["eq"].shape), ref["eq"]) < RTOL
+    ref_llr = oo.maxlog_llr(ref["eq"].reshape(nd, -1), cfg.bps, 1.0 / cfg.noise_var)
+    assert rel_err(out["llr"].cpu().numpy(), ref_llr) < RTOL
+    got_bits = unpack_symbols(out["hard"].cpu().numpy(), per_sym)
+    assert np.array_equal(got_bits, oo.hard_bits(ref["eq"].reshape(-1), cfg.bps))
+    other = lane.rx_frames(d_rx, n_frames)
+    assert np.array_equal(other["hard"].cpu().numpy(), out["hard"].cpu().numpy())
+    assert rel_err(other["eq"].cpu().numpy(), out["eq"].cpu().numpy()) < 1e-5
+
+
 PILOT_CASES = [
     dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2, pilot_spacing=6),
     dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4, pilot_spacing=4, pilot_offset=1),
