@@ -440,6 +440,203 @@ rx_sync_search_td8_kernel(const DevParams P, const float2 *__restrict__ x, long 
     }
 }
 
+
+// General form of the register-blocked search: M0 synch symbols (template, 1 or 2) and / or the frequency-offset
+// hypothesis bank (SynchEstAndFO.py:247-277), still without a transform per trial.  Derivation and CPU restatement:
+// oracle/ofdm_oracle.py sync_search_time_domain(..., nus=...).  With u = e^{j2pi nu} (row h of the bank is u^n):
+//   c_h[d; p] / p_est = u^d sum_s phi_s [ r_s(q_s) + sum_{i=1..d} ( x[q_s-i] Hp_s[i] - x[q_s-i+N] Hm_s[N-i] ) ],   q_s = p + sL + d,
+//   r_s(q) = sum_m x[q+m] Hm_s[m],   Hm_s[m] = phi_s h_s[m] u^m,   Hp_s[i] = phi_s h_s[N-i] u^{-i},
+// |u^d| = 1 drops out of the magnitude; phi_s = 1 for the reference's window-local phasor and u^{sL} when the phasor
+// is continued from the buffer origin (the common factor u^p drops out as well).  The power of the rotated window in
+// the synch bins is N sum|x|^2 - |sum_n x[p+n] u^n|^2 - |sum_n x[p+n] (-u)^n|^2 per synch symbol, the two sums slid from
+// position to position as X(q+1) = (X(q) - x[q]) / u' + x[q+N] u'^{N-1}, u' = +-u.  Hypotheses are evaluated one after
+// the other (their taps are rebuilt in shared memory from h_s and the bank row); the first maximum of the peak wins,
+// like np.argmax over the hypotheses.  Needs L = N + CP to be a multiple of 8 (the transposed staging layout).
+template <int M0>
+__global__ void __launch_bounds__(TD_THREADS)
+rx_sync_search_tdg_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
+                          long long n_trials, float *__restrict__ peak_out, int *__restrict__ delay_out,
+                          int *__restrict__ hyp_out) {
+    extern __shared__ __align__(16) unsigned char td_smem[];
+    const int N = P.nfft, CP = P.cp, L = N + CP, t = threadIdx.x;
+    const int A = (CP + 7) & ~7;
+    const int TP = TD_TQ - CP;
+    const int XW = TD_TQ + N + A + (M0 - 1) * L;                        // a multiple of 8
+    const int S = XW / 8 + 1, SB = TD_TQ / 8 + 1, CPA = CP + 1;
+    float2 *Xs = reinterpret_cast<float2 *>(td_smem);
+    float2 *Hm = Xs + 8 * S;                                            // [M0][N]
+    float2 *Hp = Hm + M0 * N;                                           // [M0][CPA], entry 0 unused
+    float2 *Er = Hp + M0 * CPA;                                         // [N] u^n
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(Er + N);
+    float *pw = reinterpret_cast<float *>(best + 8 * SB);
+    float2 *phi = reinterpret_cast<float2 *>(pw + 8 * SB);              // [M0]
+    const long long tile0 = (long long)blockIdx.x * TP;
+    const long long q0 = first_start + tile0;
+    const long long last_trial = n_trials - 1;
+    for (int i = t; i < XW; i += TD_THREADS) {
+        const long long g = q0 - A + i;
+        Xs[(i & 7) * S + (i >> 3)] = (g >= 0 && g < n_samples) ? __ldg(x + g) : make_float2(0.f, 0.f);
+    }
+    const int n_hyp = P.n_cfo > 0 ? P.n_cfo : 1;
+    float bpk[8];
+    int bdl[8], bhy[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        bpk[u] = -1.f;
+        bdl[u] = bhy[u] = 0;
+    }
+    for (int h = 0; h < n_hyp; ++h) {
+        __syncthreads();                                                // previous hypothesis is done with the tables
+        const float2 *row = P.n_cfo > 0 ? P.cfo + (long long)h * N : nullptr;
+        if (t < M0) {
+            float2 f = make_float2(1.f, 0.f);
+            if (P.n_cfo > 0 && P.cfo_continuous) {
+                double a = P.cfo_nu[h] * (double)(t * L);
+                a -= floor(a);
+                double sn, cs;
+                sincospi(2.0 * a, &sn, &cs);
+                f = make_float2((float)cs, (float)sn);
+            }
+            phi[t] = f;
+        }
+        for (int i = t; i < 8 * SB; i += TD_THREADS) best[i] = 0ull;
+        __syncthreads();
+        for (int i = t; i < M0 * N; i += TD_THREADS) {
+            const int m = i & (N - 1);
+            float2 v = cmul(__ldg(P.h_td + i), phi[i / N]);
+            if (row) v = cmul(v, __ldg(row + m));
+            Hm[i] = v;
+        }
+        for (int i = t; i < M0 * CPA; i += TD_THREADS) {
+            const int s = i / CPA, d = i - s * CPA;
+            float2 v = make_float2(0.f, 0.f);
+            if (d > 0) {
+                v = cmul(__ldg(P.h_td + s * N + N - d), phi[s]);
+                if (row) v = cmulc(v, __ldg(row + d));                   // u^{-d}
+            }
+            Hp[i] = v;
+        }
+        for (int i = t; i < N; i += TD_THREADS) Er[i] = row ? __ldg(row + i) : make_float2(1.f, 0.f);
+        __syncthreads();
+        const float2 uinv = row ? make_float2(Er[1].x, -Er[1].y) : make_float2(1.f, 0.f);
+        const float2 un1 = row ? Er[N - 1] : make_float2(1.f, 0.f);
+        const float2 *xt = Xs + A / 8 + t;
+        float2 acc[8], W[M0][8], U[M0][8], s0[M0], s1[M0];
+        float en = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < M0; ++s) {
+            const float2 *xs = xt + s * (L / 8);
+            auto LD = [&](int c) -> float2 { return xs[(c & 7) * S + (c >> 3)]; };
+            const float2 *hm = Hm + s * N;
+            s0[s] = s1[s] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) W[s][j] = LD(j);
+            for (int M = 0; M < N; M += 8) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float2 hh = hm[M + r];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = cmul_acc(acc[j], W[s][(r + j) & 7], hh);
+                    const float2 a0 = W[s][r];
+                    en = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, en));
+                    const float2 ae = row ? cmul(a0, Er[M + r]) : a0;
+                    s0[s] = cadd(s0[s], ae);
+                    s1[s] = (r & 1) ? csub(s1[s], ae) : cadd(s1[s], ae);
+                    W[s][r] = LD(M + r + 8);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) U[s][j] = LD(j);
+        }
+        unsigned long long K[8];
+        auto key_of = [&](int j, int i) -> unsigned long long {
+            return ((unsigned long long)__float_as_uint(cabs2(acc[j])) << 32) | (unsigned)(0x7fffffff - i);
+        };
+        auto flush = [&](unsigned long long key, int c) {
+            const int pl = 8 * t + c;
+            if (pl >= 0 && pl < TP && tile0 + pl <= last_trial) atomicMax(best + (pl & 7) * SB + (pl >> 3), key);
+        };
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float p = (float)N * en;
+#pragma unroll
+            for (int s = 0; s < M0; ++s) p -= cabs2(s0[s]) + cabs2(s1[s]);
+            const int pq = 8 * t + j;
+            pw[(pq & 7) * SB + (pq >> 3)] = p;
+            K[j] = key_of(j, 0);
+#pragma unroll
+            for (int s = 0; s < M0; ++s) {                              // slide the window sums to the next position
+                const float2 a = U[s][j], b = W[s][j];
+                en += cabs2(b) - cabs2(a);
+                const float2 bu = cmul(b, un1);
+                s0[s] = cadd(cmul(csub(s0[s], a), uinv), bu);
+                const float2 m1 = cadd(cmul(csub(s1[s], a), uinv), bu);
+                s1[s] = make_float2(-m1.x, -m1.y);
+            }
+        }
+        flush(K[7], 7);
+        for (int I = 0; I < CP; I += 8) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = I + r + 1;
+                if (i <= CP) {
+                    K[7 - r] = 0ull;
+#pragma unroll
+                    for (int s = 0; s < M0; ++s) {
+                        const float2 *xs = xt + s * (L / 8);
+                        auto LD = [&](int c) -> float2 { return xs[(c & 7) * S + (c >> 3)]; };
+                        const float2 hp = Hp[s * CPA + i], hm = Hm[s * N + N - i];
+                        const float2 nhm = make_float2(-hm.x, -hm.y);
+                        U[s][7 - r] = LD(-i);
+                        W[s][7 - r] = LD(N - i);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            acc[j] = cmul_acc(cmul_acc(acc[j], U[s][(j - r - 1) & 7], hp), W[s][(j - r - 1) & 7], nhm);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const unsigned long long key = key_of(j, i);
+                        K[(j - r - 1) & 7] = key > K[(j - r - 1) & 7] ? key : K[(j - r - 1) & 7];
+                    }
+                    flush(K[(6 - r) & 7], 7 - i);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = ((u - (-CP & 7)) & 7) - CP;
+            if (c <= 6 - CP) flush(K[u], c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int pl = t + TD_THREADS * u;
+            if (pl < TP && tile0 + pl <= last_trial) {
+                const unsigned long long key = best[(pl & 7) * SB + (pl >> 3)];
+                const float p = pw[(pl & 7) * SB + (pl >> 3)];
+                const float p_est = p > 0.f ? sqrtf((float)P.mm / p) : 0.f;
+                const float pk = p_est * sqrtf(__uint_as_float((unsigned)(key >> 32)));
+                if (pk > bpk[u]) {                                      // first maximum over the hypotheses
+                    bpk[u] = pk;
+                    bdl[u] = 0x7fffffff - (int)(key & 0xffffffffu);
+                    bhy[u] = h;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int pl = t + TD_THREADS * u;
+        if (pl < TP && tile0 + pl <= last_trial) {
+            peak_out[tile0 + pl] = bpk[u];
+            delay_out[tile0 + pl] = bdl[u];
+            if (hyp_out != nullptr) hyp_out[tile0 + pl] = bhy[u];
+        }
+    }
+}
+
 }  // namespace ofdm
 
 // ------------------------------------------------------------------------------------------------
@@ -585,29 +782,30 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     }
     // taps of the time-domain acquisition kernel (rx_sync_search_td_kernel): h[m] = sum_idx conj(zc[idx]) e^{-j2pi k m/N},
     // only for the configuration it serves (one synch symbol on every bin but DC and the band edge)
-    const bool td_ok = (m0 == 1 && nsb == N - 2);
-    std::vector<float2> h_td(N, make_float2(0.f, 0.f));
+    const bool td_ok = (m0 <= 2 && nsb == N - 2);
+    std::vector<float2> h_td((size_t)m0 * N, make_float2(0.f, 0.f));
     if (td_ok) {
         std::vector<double> cs(N), sn(N);
         for (int k = 0; k < N; ++k) {
             cs[k] = cos(two_pi * (double)k / (double)N);
             sn[k] = sin(two_pi * (double)k / (double)N);
         }
-        for (int m = 0; m < N; ++m) {
-            double ar = 0.0, ai = 0.0;
-            for (int idx = 0; idx < nsb; ++idx) {
-                const int sbin = idx < h ? idx - h : idx - h + 1;
-                const int k = ((sbin % N) + N) % N;
-                const int e2 = (int)(((long long)k * m) % N);            // e^{-j2pi km/N} = cs - j sn
-                ar += zr[idx] * cs[e2] - zi[idx] * sn[e2];               // conj(zc) = zr - j zi
-                ai += -zr[idx] * sn[e2] - zi[idx] * cs[e2];
+        for (int s = 0; s < m0; ++s)
+            for (int m = 0; m < N; ++m) {
+                double ar = 0.0, ai = 0.0;
+                for (int idx = 0; idx < nsb; ++idx) {
+                    const int sbin = idx < h ? idx - h : idx - h + 1;
+                    const int k = ((sbin % N) + N) % N;
+                    const int e2 = (int)(((long long)k * m) % N);            // e^{-j2pi km/N} = cs - j sn
+                    ar += zr[s * nsb + idx] * cs[e2] - zi[s * nsb + idx] * sn[e2];     // conj(zc) = zr - j zi
+                    ai += -zr[s * nsb + idx] * sn[e2] - zi[s * nsb + idx] * cs[e2];
+                }
+                h_td[(size_t)s * N + m] = make_float2((float)ar, (float)ai);
             }
-            h_td[m] = make_float2((float)ar, (float)ai);
-        }
     }
     const size_t b_tw = sizeof(float2) * N, b_zb = sizeof(float2) * m0 * N, b_w = sizeof(float) * N,
                  b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * m0 * N, b_pt = sizeof(float2) * N,
-                 b_ht = sizeof(float2) * N;
+                 b_ht = sizeof(float2) * m0 * N;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt) + al(b_pt) + al(b_ht);
     e = cudaMalloc(&pl->d_tables, total);
@@ -777,7 +975,32 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
     const int td_mode = td_env ? atoi(td_env) : OFDM_SYNC_TD_DEFAULT;
     // (a tile yields TD_TQ - CP trials for TD_TQ N-tap correlations: only worth it -- and only well-defined -- while
     // the prefix is at most half a tile; longer prefixes fall through to the per-trial transforms)
-    if (td_mode != 0 && stride == 1 && pl->dev.h_td && !pl->dev.n_cfo && first_start >= 0 && 2 * pl->prm.cp_len <= TD_TQ) {
+    // M0 = 2 and / or a hypothesis bank: the general time-domain kernel (OFDM_SYNC_TDG=0 keeps the per-trial transforms)
+    const char *tdg_env = getenv("OFDM_SYNC_TDG");
+    if (td_mode != 0 && (!tdg_env || atoi(tdg_env) != 0) && stride == 1 && pl->dev.h_td && (pl->dev.n_cfo || pl->prm.m0 == 2) &&
+        first_start >= 0 && 2 * pl->prm.cp_len <= TD_TQ && (pl->prm.nfft + pl->prm.cp_len) % 8 == 0) {
+        const int N = pl->prm.nfft, CP = pl->prm.cp_len, M0 = pl->prm.m0, L = N + CP, TP = TD_TQ - CP, A = (CP + 7) & ~7;
+        const int XW = TD_TQ + N + A + (M0 - 1) * L, SB = TD_TQ / 8 + 1, CPA = CP + 1;
+        const int smem = 8 * (XW / 8 + 1) * 8 + M0 * N * 8 + M0 * CPA * 8 + (N + 1) * 8 + 8 * SB * 12 + M0 * 8 + 16;
+        if (smem <= 200 * 1024) {
+            if (smem > pl->tdg_smem_set) {
+                CU(cudaFuncSetAttribute(rx_sync_search_tdg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "ofdm_rx_sync_search(attr)");
+                CU(cudaFuncSetAttribute(rx_sync_search_tdg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "ofdm_rx_sync_search(attr)");
+                pl->tdg_smem_set = smem;
+            }
+            const long long tiles = (n_trials + TP - 1) / TP;
+            if (M0 == 1)
+                rx_sync_search_tdg_kernel<1><<<(unsigned)tiles, TD_THREADS, smem, (cudaStream_t)stream>>>(
+                    pl->dev, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay, d_hyp);
+            else
+                rx_sync_search_tdg_kernel<2><<<(unsigned)tiles, TD_THREADS, smem, (cudaStream_t)stream>>>(
+                    pl->dev, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay, d_hyp);
+            count_launch();
+            CU(cudaGetLastError(), "ofdm_rx_sync_search(tdg)");
+            return OFDM_OK;
+        }
+    }
+    if (td_mode != 0 && stride == 1 && pl->dev.h_td && pl->prm.m0 == 1 && !pl->dev.n_cfo && first_start >= 0 && 2 * pl->prm.cp_len <= TD_TQ) {
         const int N = pl->prm.nfft, CP = pl->prm.cp_len, TP = TD_TQ - CP, A = (CP + 7) & ~7;
         const int smem = td_mode == 2 ? 8 * ((TD_TQ + N + A) / 8 + 1) * 8 + N * 8 + 8 * (TD_TQ / 8 + 1) * 12
                                       : (TD_TQ + N + CP) * 8 + N * 8 + TD_TQ * 8 + TD_TQ * 4;

@@ -119,6 +119,13 @@ template <int T, int PPT> __device__ __forceinline__ int bin_out(const BinMap &b
 
 // The framed receiver's epilogue is branch-free (see data_epilogue, DENSE) when at least this many 64ths of the FFT bins
 // carry data; 65 = never.  B200: +3..10 % at a 94 % fill for every size, slower at the LTE fill of 59 %.
+// tuning aid: 1 compiles the receiver's optional equalised-symbol output as always present (A/B of the run-time switch)
+#ifndef OFDM_EPI_MASKS
+#define OFDM_EPI_MASKS 3          // 0: `used && wanted` per bin; 1: the eq output through its own mask; 3: all three outputs
+#endif
+#ifndef OFDM_EQ_ALWAYS
+#define OFDM_EQ_ALWAYS 0
+#endif
 #ifndef OFDM_EPI_CHUNK_SPARSE
 #define OFDM_EPI_CHUNK_SPARSE 0
 #endif
@@ -634,7 +641,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     const float pw = group_sum<T, GROUPS>(pw2.x + pw2.y, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     // every output is optional: a caller that only decodes wants LLRs or hard bits, not the equalised symbols
-    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr), weq = (eq_out != nullptr);
+    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr), weq = OFDM_EQ_ALWAYS ? true : (eq_out != nullptr);
     // 64-QAM: a bin's six LLRs are 24 bytes, so per-lane stores would leave every 32-byte sector
     // half-written by each instruction (2.9x the sector writes at L2, ncu).  The row is assembled in
     // shared memory instead and written with full 16-byte lanes.
@@ -648,6 +655,11 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     // divergence), otherwise all CH bins are computed branch-free and only the stores are predicated.  CH = PPT is the
     // fully dense form; CH = 0 keeps the per-lane branches of the loop further down.
     constexpr int CH = DENSE ? PPT : OFDM_EPI_CHUNK_SPARSE;
+    // The optional outputs are folded into per-output copies of the bin mask, so a bin's store keeps ONE bit test as its
+    // predicate: testing `used && wanted` per bin cost the branch-free epilogue 6-11 % (B200: N=2048 16-QAM 0.601 -> 0.540 ms,
+    // N=4096 0.777 -> 0.701 ms with the equalised-symbol switch compiled out; OFDM_EPI_MASKS=0 rebuilds that form).
+    const unsigned emask = weq ? mask : 0u, smask = soft ? mask : 0u, hmask = hard ? mask : 0u;
+    (void)emask; (void)smask; (void)hmask;
     if (CH > 0) {
 #pragma unroll
         for (int c = 0; c < PPT; c += (CH > 0 ? CH : PPT)) {
@@ -656,12 +668,12 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
                 for (int m = c; m < c + CH; ++m) {
                     const bool used = (mask & (1u << m)) != 0;
                     const float2 z = cscale(cmul(G.get(m), v[m]), p0);
-                    if (used && weq) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
+                    if (OFDM_EPI_MASKS >= 1 ? (emask & (1u << m)) != 0 : (used && weq)) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
                     float Lb[BPS];
                     unsigned bits;
                     D.dem.run(z, Lb, bits);
                     float *q = (m < PPT / 2 ? lp : ln) + m * T * BPS;
-                    if (used && soft) {
+                    if (OFDM_EPI_MASKS >= 3 ? (smask & (1u << m)) != 0 : (used && soft)) {
                         if (BPS == 1) {
                             st_out<CS>(q, Lb[0]);
                         } else if (BPS == 4) {
@@ -675,7 +687,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
                                 st_out<CS>(reinterpret_cast<float2 *>(q + b), make_float2(Lb[b], Lb[b + 1]));
                         }
                     }
-                    if (used && hard) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
+                    if (OFDM_EPI_MASKS >= 3 ? (hmask & (1u << m)) != 0 : (used && hard)) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
                 }
             }
         }
@@ -931,11 +943,19 @@ template <class C> struct MinBlocksTx {
 #ifndef OFDM_MINB_RXF_4096
 #define OFDM_MINB_RXF_4096 0
 #endif
-template <class C, bool GSM> struct MinBlocksRxF {
+// The branch-free (dense) epilogue at N = 2048 with 16 points per thread gains from a third resident CTA (168 registers
+// per thread, a few spilled words): B200, 1920-bin grid 16-QAM 0.627 -> 0.596 ms; the sparse LTE-grid kernel loses
+// with it (64-QAM 0.645 -> 0.654 ms) and keeps two.
+#ifndef OFDM_MINB_RXFD_2048
+#define OFDM_MINB_RXFD_2048 3
+#endif
+template <class C, bool GSM, bool DENSE = false> struct MinBlocksRxF {
     static constexpr int THREADS = C::T >= 128 ? C::T : 128;
     static constexpr int REGS = (C::PPT == 16 && !GSM) ? 255 : 128;
     static constexpr int byregs = 65536 / (THREADS * REGS);
-    static constexpr int forced = C::LOG2N == 10 ? OFDM_MINB_RXF_1024 : (C::LOG2N == 11 ? OFDM_MINB_RXF_2048 : (C::LOG2N == 12 ? OFDM_MINB_RXF_4096 : 0));
+    static constexpr int forced = C::LOG2N == 10 ? OFDM_MINB_RXF_1024
+                                  : (C::LOG2N == 11 ? ((DENSE && C::PPT == 16 && OFDM_MINB_RXF_2048 == 0) ? OFDM_MINB_RXFD_2048 : OFDM_MINB_RXF_2048)
+                                                    : (C::LOG2N == 12 ? OFDM_MINB_RXF_4096 : 0));
     static constexpr int value = C::LOG2N <= 9 ? OFDM_MINB_SMALL : (forced > 0 ? forced : (byregs < 1 ? 1 : byregs));
 };
 
@@ -949,7 +969,7 @@ enum { EPI_SPARSE = 0, EPI_BULK = 1, EPI_DENSE = 2 };
 // CPP: the plan has a CP pattern (DevParams::cp_extra); instantiated without comb pilots and hypothesis bank only, so
 // that the reference's uniform prefix pays nothing for it.
 template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO, int EPI = EPI_SPARSE, bool CPP = false>
-__global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM>::value)
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM, EPI == 2>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
                  float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, int *__restrict__ hyp_out,

@@ -31,6 +31,7 @@ struct ofdm_plan {
     size_t stage_bytes[NSLOT];
     void *small;                   // per-frame results of the host-buffer receiver (delay, peak, locked)
     size_t small_bytes;
+    int tdg_smem_set;              // the same for the general (M0 = 2 / hypothesis bank) kernel
     int td_smem_set;               // dynamic shared memory the time-domain search kernel has been allowed on this device
 };
 

@@ -476,7 +476,7 @@ def sync_trial(in0, start, prm: ModemParams, zc=None, bank=None, literal=False, 
     return int(np.argmax(mag)), float(np.max(mag)), sd
 
 
-def sync_search_time_domain(in0, first_start, stride, n_trials, prm: ModemParams):
+def sync_search_time_domain(in0, first_start, stride, n_trials, prm: ModemParams, nus=None, continuous=False):
     """Every trial of the sliding search (sync_trial at first_start + t*stride) WITHOUT a transform per trial.
 
     Derivation (M0 windows s = 0..M0-1 at p + s*L, synch bins S, y_k = X_k conj(zc_k)):
@@ -489,7 +489,18 @@ def sync_search_time_domain(in0, first_start, stride, n_trials, prm: ModemParams
     few unused bins (DC and the band edge).  Same numbers as sync_trial up to rounding; this is the specification of
     the fast acquisition path, not what the reference executes.
     Returns (peak[n_trials], delay[n_trials]).  Windows past the end are zero-padded like np.fft.fft.
+
+    With ``nus`` (cycles per sample of each row of cfo_bank(), SynchEstAndFO.py:196,:247-277) every hypothesis is
+    evaluated and the first maximum of the peak wins; a third array, hyp[n_trials], is returned.  The window-local
+    phasor e^{j2pi nu n} multiplies sample n of each window, so with u = e^{j2pi nu}
+        c[d; p] / p_est = u^d * sum_s phi_s [ r_s(q_s) + sum_{i=1..d} ( x[q_s-i] h_s[N-i] u^{-i} - x[q_s-i+N] h_s[N-i] u^{N-i} ) ],
+        r_s(q) = sum_m x[q+m] h_s[m] u^m,   q_s = p + s*L + d,
+    (|u^d| = 1 drops out of the magnitude; phi_s = 1, or u^{s*L} up to a common factor when the phasor is continued
+    from the buffer origin, ``continuous``), and the unused bins DC / band edge become the sliding sums
+    sum_n x[p+n] (+-u)^n.
     """
+    if nus is not None:
+        return _sync_search_time_domain_cfo(in0, first_start, stride, n_trials, prm, nus, continuous)
     N, CP, L, M0, nsb = prm.nfft, prm.cp_len, prm.sym_len, prm.m0, prm.num_synch_bins
     assert nsb < N, "the +-N/2 alias case (num_synch_bins == nfft) keeps the transform path"
     sb = bins_used(nsb, N)
@@ -539,6 +550,66 @@ def sync_search_time_domain(in0, first_start, stride, n_trials, prm: ModemParams
         delay[t] = int(np.argmax(mags))
         peak[t] = p_est * mags[delay[t]]
     return peak, delay
+
+
+def _sync_search_time_domain_cfo(in0, first_start, stride, n_trials, prm: ModemParams, nus, continuous):
+    """The hypothesis-bank form of sync_search_time_domain (see its docstring for the derivation)."""
+    N, CP, L, M0, nsb = prm.nfft, prm.cp_len, prm.sym_len, prm.m0, prm.num_synch_bins
+    assert nsb < N
+    sb = bins_used(nsb, N)
+    zc = zc_for(prm)
+    last = first_start + (n_trials - 1) * stride
+    span = last - first_start + 1
+    need = last + CP + (M0 - 1) * L + 2 * N + 1
+    x = np.zeros(max(need, len(in0)), dtype=complex)
+    x[:len(in0)] = np.asarray(in0, dtype=complex)
+    n_q = span + CP
+    nn = np.arange(N)
+    unused = np.setdiff1d(np.arange(N), sb)
+    best_pk = np.full(n_trials, -1.0)
+    best_dl = np.zeros(n_trials, dtype=np.int32)
+    best_h = np.zeros(n_trials, dtype=np.int32)
+    for hi, nu in enumerate(nus):
+        u = np.exp(2j * np.pi * nu)
+        num = np.zeros((n_q, CP + 1), dtype=complex)
+        pw = np.zeros(span)
+        for s in range(M0):
+            Z = np.zeros(N, dtype=complex)
+            Z[sb] = np.conj(zc[s * nsb:(s + 1) * nsb])
+            g = N * np.fft.ifft(Z)
+            h = g[(-nn) % N]
+            phi = np.exp(2j * np.pi * ((nu * s * L) % 1.0)) if continuous else 1.0
+            hm = phi * h * u ** nn                                       # main taps h_s[m] u^m
+            hp = np.array([0.0] + [phi * h[N - i] * u ** (-i) for i in range(1, CP + 1)])     # prefix taps, index i
+            xs = x[s * L:]
+            seg = xs[first_start:first_start + n_q + N - 1]
+            r = np.correlate(seg, np.conj(hm), mode="valid")
+            for qi in range(n_q):
+                q = first_start + qi
+                acc = r[qi]
+                num[qi, 0] += acc
+                for i in range(1, CP + 1):
+                    a = q - i
+                    lo = xs[a] if a >= 0 else 0.0
+                    hi_ = xs[a + N] if a + N >= 0 else 0.0
+                    acc = acc + lo * hp[i] - hi_ * hm[N - i]
+                    num[qi, i] += acc
+            e = np.abs(xs[first_start:first_start + span - 1 + N]) ** 2
+            ce = np.concatenate(([0.0], np.cumsum(e)))
+            pw += N * (ce[N:N + span] - ce[:span])
+            for k in unused:
+                ph = np.exp(-2j * np.pi * k * nn / N) * u ** nn
+                for pi in range(span):
+                    pw[pi] -= abs(np.dot(xs[first_start + pi:first_start + pi + N], ph)) ** 2
+        for t in range(n_trials):
+            pi = t * stride
+            mags = np.array([abs(num[pi + d, d]) for d in range(CP + 1)])
+            p_est = np.sqrt(prm.mm / pw[pi]) if pw[pi] > 0 else 0.0
+            d_i = int(np.argmax(mags))
+            pk = p_est * mags[d_i]
+            if pk > best_pk[t]:                                          # first maximum over the hypotheses
+                best_pk[t], best_dl[t], best_h[t] = pk, d_i, hi
+    return best_pk, best_dl, best_h
 
 
 def sync_trial_cfo(in0, start, prm: ModemParams, cfo, zc=None, bank=None, literal=False, nus=None):

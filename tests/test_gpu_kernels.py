@@ -270,3 +270,61 @@ def test_time_domain_acquisition_equals_transform_search(kw, n_frames, monkeypat
         assert np.mean(dl1 == dl0) > 0.99, mode              # elsewhere only near-ties between noise lags may differ
         assert rel_err(pk1[:n_chk], rp) < RTOL, mode
         assert np.array_equal(dl1[:n_chk][s2], rd[s2]), mode
+
+
+@pytest.mark.parametrize("kw,bank,continuous", [
+    (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=2, d=2, bps=2), None, False),
+    (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2), "small", False),
+    (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=2, d=2, bps=2), "large", False),
+    (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=2, d=2, bps=2), "large", True),
+    (dict(nfft=256, cp_len=24, num_synch_bins=254, num_data_bins=200, m0=2, d=2, bps=4), "large", True),
+    (dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=1, bps=2), "small", False),
+], ids=["N64_m2", "N64_bank", "N64_m2_bank", "N64_m2_bank_cont", "N256_m2_bank_cont", "N2048_bank"])
+def test_general_time_domain_acquisition(kw, bank, continuous, monkeypatch):
+    """M0 = 2 and / or the frequency-offset hypothesis bank (SynchEstAndFO.py:247-277) on the time-domain search:
+    against the per-trial transform kernel over a whole capture (windows running off the end included) and against
+    the oracle's derivation (sync_search_time_domain with nus) on a stretch of trials."""
+    m = make(dict(kw, snr=100, compat="utsa", zc_root=23))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    n_frames = 2 if cfg.nfft >= 2048 else 6
+    _, rx = synth(cfg, prm, n_frames, 9, noise=1e-3)
+    fs = 960000.0
+    step = 0.3 * fs / cfg.nfft
+    nus = None
+    if bank:
+        fo = [-75.0, -25.0, 0.0, 50.0] if bank == "small" else [-step, 0.0, step]
+        rx = (rx * np.exp(-2j * np.pi * fo[-1] / fs * np.arange(len(rx)))).astype(np.complex64)
+        nus = [f / fs for f in fo]
+        m.set_cfo_bank(fo, fs, phase_continuous=continuous)
+    d_rx = torch.from_numpy(rx).cuda()
+    n_trials = len(rx) - cfg.cp_len - 7
+    monkeypatch.setenv("OFDM_SYNC_TDG", "0")
+    r0 = [a.cpu().numpy() for a in m.sync_search(d_rx, cfg.cp_len, 1, n_trials)]
+    monkeypatch.setenv("OFDM_SYNC_TDG", "1")
+    r1 = [a.cpu().numpy() for a in m.sync_search(d_rx, cfg.cp_len, 1, n_trials)]
+    strong = r0[0] > 0.3 * prm.mm
+    assert strong.sum() >= n_frames
+    assert rel_err(r1[0], r0[0]) < RTOL
+    assert np.array_equal(r1[1][strong], r0[1][strong]) and np.mean(r1[1] == r0[1]) > 0.98
+    if bank == "large":                                     # hypotheses a third of a bin apart: one clear winner
+        assert np.array_equal(r1[2][strong], r0[2][strong]) and np.mean(r1[2] == r0[2]) > 0.95
+        if continuous:                                       # (the window-local phasor adds the two repeats incoherently)
+            top = r0[0] > 0.9 * r0[0].max()                   # the trials that land on a frame start
+            assert top.sum() >= n_frames - 1 and np.mean(r1[2][top] == 2) > 0.9
+    n_chk = min(200 if cfg.nfft <= 256 else 40, n_trials)
+    ref = oo.sync_search_time_domain(rx, cfg.cp_len, 1, n_chk, prm, nus=nus, continuous=continuous)
+    s2 = ref[0] > 0.3 * prm.mm
+    assert rel_err(r1[0][:n_chk], ref[0]) < RTOL
+    assert np.array_equal(r1[1][:n_chk][s2], ref[1][s2])
+    if bank == "large":
+        assert np.array_equal(r1[2][:n_chk][s2], ref[2][s2])
+    elif bank:
+        # the reference's own example bank (range(-75, 75, 25) Hz at 960 kHz, SynchEstAndFO.py:157) turns a window by
+        # hundredths of a radian: the hypotheses' peaks differ in the 5th digit, so the winner is only defined up to
+        # rounding -- the chosen hypothesis must be within the tolerance of the best one
+        zc, dbank = oo.zc_for(prm), oo.delay_bank(prm)
+        cfo = oo.cfo_bank(fo, fs, cfg.nfft)
+        for t in np.flatnonzero(s2)[:25]:
+            per_h = [r[1] for r in oo.sync_trial_cfo(rx, cfg.cp_len + int(t), prm, cfo, zc, dbank)[3]]
+            assert per_h[r1[2][t]] > (1 - RTOL) * max(per_h)

@@ -281,3 +281,37 @@ def test_cp_pattern_many_frames_multi_iteration():
     ref = oo.rx_frames(ref_tx.astype(np.complex64), n_frames, prm)["eq"][sub]
     eq = got["eq"].cpu().numpy().reshape(n_frames, cfg.d, -1)[sub]
     assert rel_err(eq, ref) < RTOL
+
+
+WIDE_TX_CASES = [
+    dict(nfft=1024, cp_len=72, num_synch_bins=1022, num_data_bins=600, m0=1, d=2, bps=4),             # "middle zero" front
+    dict(nfft=1024, cp_len=256, num_synch_bins=1022, num_data_bins=960, m0=2, d=2, bps=1),            # prefix = N/4, two synch symbols
+    dict(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6),   # LTE, CP pattern
+    dict(nfft=2048, cp_len=512, num_synch_bins=2046, num_data_bins=1920, m0=2, d=3, bps=2),
+    dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1282, m0=1, d=2, bps=6),           # just above the 5/8 threshold
+    dict(nfft=4096, cp_len=288, num_synch_bins=4094, num_data_bins=2400, m0=1, d=2, bps=6),
+    dict(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=3, bps=4),
+]
+
+
+@pytest.mark.parametrize("kw", WIDE_TX_CASES, ids=lambda k: "N%d_n%d_b%d_m%d" % (k["nfft"], k["num_data_bins"], k["bps"], k["m0"]))
+def test_wide_transmitter_matches_oracle(kw, monkeypatch):
+    """The 64-point-per-thread transmitter (csrc/tx_wide.cuh) at every size it serves, forced on (OFDM_TX_WIDE=2), against
+    the oracle; the payload starts at an odd byte so the row staging is exercised off its 16-byte phase as well."""
+    monkeypatch.setenv("OFDM_TX_WIDE", "2")
+    m = make(dict(kw, snr=100))
+    cfg = m.cfg
+    prm = oracle_prm(cfg)
+    n_frames = 7
+    rng = np.random.default_rng(77)
+    per_sym = cfg.num_data_bins * cfg.bps
+    bits = rng.integers(0, 2, n_frames * cfg.d * per_sym)
+    ref = oo.tx_modulate(bits, prm, n_frames)
+    packed = pack_symbols(bits, n_frames * cfg.d, per_sym, cfg.hard_stride)
+    buf = torch.zeros(packed.size + 3, dtype=torch.uint8, device="cuda")
+    buf[3:] = torch.from_numpy(packed.reshape(-1)).cuda()
+    out = m.tx_modulate(buf[3:], n_frames).cpu().numpy()
+    assert rel_err(out, ref) < RTOL
+    monkeypatch.setenv("OFDM_TX_WIDE", "0")                   # the 16-point kernel on the same payload
+    out16 = m.tx_modulate(buf[3:], n_frames).cpu().numpy()
+    assert rel_err(out16, ref) < RTOL and rel_err(out, out16) < RTOL

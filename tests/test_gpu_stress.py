@@ -124,3 +124,40 @@ def test_search_estimate_and_symbol_list_kernels_are_bit_identical_across_launch
         assert same(h, h0) and same(ht, ht0) and same(se, se0), rep
         e, l, b = m.demod(rx, starts, dls, rows, h0, want_llr=True, want_hard=True)
         assert same(e, e0) and same(l, l0) and same(b, b0), rep
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nfft=1024, cp_len=72, num_synch_bins=1022, num_data_bins=600, m0=1, d=3, bps=4),
+    dict(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6),
+    dict(nfft=2048, cp_len=512, num_synch_bins=2046, num_data_bins=1920, m0=2, d=3, bps=2),
+    dict(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=3, bps=6),
+], ids=["n1024", "lte_cpp", "n2048_m0_2", "n4096"])
+def test_wide_transmitter_is_bit_identical_across_launches(kw, monkeypatch):
+    """tx_wide.cuh: one exchange buffer per group, reused symbol after symbol behind two group barriers, and (N = 4096)
+    alternating reduction slots between the two warps of a group."""
+    monkeypatch.setenv("OFDM_TX_WIDE", "2")
+    m = make(dict(kw, snr=100))
+    nf = frames_for(kw["nfft"], kw["d"])
+    g = torch.Generator(device="cuda")
+    g.manual_seed(41)
+    bits = torch.randint(0, 256, (nf * m.cfg.d * m.cfg.hard_stride,), dtype=torch.uint8, device="cuda", generator=g)
+    tx0 = m.tx_modulate(bits, nf).clone()
+    for rep in range(REPS):
+        assert same(m.tx_modulate(bits, nf), tx0), rep
+
+
+@pytest.mark.parametrize("m0,bank", [(2, False), (1, True), (2, True)], ids=["m0_2", "bank", "m0_2_bank"])
+def test_general_time_domain_search_is_bit_identical_across_launches(m0, bank):
+    """rx_sync_search_tdg_kernel: per-hypothesis tap tables rebuilt in shared memory between barriers, 64-bit shared
+    atomicMax per trial offset (order-independent), running best kept in registers."""
+    m = make(dict(nfft=256, cp_len=24, num_synch_bins=254, num_data_bins=200, m0=m0, d=2, bps=4, snr=100, gate=0.5,
+                  noise_var=0.02, compat="utsa", zc_root=23))
+    if bank:
+        m.set_cfo_bank([-3000.0, 0.0, 1500.0, 3000.0], 1.92e6, phase_continuous=(m0 == 2))
+    nf = max(24, (1 << 20) // m.cfg.frame_len)
+    bits, tx0, rx = build_batch(m, nf, 3)
+    n_trials = rx.numel() - m0 * m.cfg.sym_len - 256
+    r0 = [t.clone() for t in m.sync_search(rx, 24, 1, n_trials)]
+    for rep in range(REPS // 3):
+        r = m.sync_search(rx, 24, 1, n_trials)
+        assert all(same(a, b) for a, b in zip(r, r0)), rep

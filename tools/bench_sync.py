@@ -32,6 +32,14 @@ CASES = {
                                  compat="rxofdm", zc_root=23), 15, 1 << 26),
     "lte_stride1": (dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100),
                     1, 1 << 22),
+    # the general time-domain kernel (M0 = 2 and / or the frequency-offset hypothesis bank): a 4th tuple entry is the
+    # bank in cycles per sample; these cases also time the per-trial transform kernel on the same capture (OFDM_SYNC_TDG=0)
+    "n64_m2_stride1": (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=2, d=2, bps=2, snr=100,
+                            compat="utsa", zc_root=23), 1, 1 << 23),
+    "n64_bank7_stride1": (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2, snr=100,
+                               compat="utsa", zc_root=23), 1, 1 << 23, [f / 960000.0 for f in range(-75, 100, 25)]),
+    "lte_bank3_stride1": (dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100),
+                          1, 1 << 21, [-1e-5, 0.0, 1e-5]),
     "lte_stride143": (dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100),
                       143, 1 << 27),
 }
@@ -50,9 +58,12 @@ def cpu_rate(cfg, rx, stride, literal, seconds):
 
 
 def run(name, cpu_seconds):
-    kw, stride, n_samp = CASES[name]
+    kw, stride, n_samp = CASES[name][:3]
+    nus = CASES[name][3] if len(CASES[name]) > 3 else None
     cfg = ModemConfig(**kw)
     m = Modem(cfg)
+    if nus:
+        m.set_cfo_bank(nus, 1.0)
     nf = n_samp // cfg.frame_len
     bits = torch.randint(0, 256, (nf * cfg.d * cfg.hard_stride,), dtype=torch.uint8, device="cuda")
     tx = m.tx_modulate(bits, nf)
@@ -60,7 +71,7 @@ def run(name, cpu_seconds):
     rx = m.channel_awgn(tx, nf, taps / torch.linalg.norm(taps), 0.02, 11)
     n = rx.numel()
     n_trials = (n - cfg.m0 * cfg.sym_len - cfg.nfft - cfg.cp_len - 1) // stride + 1
-    peak, delay = m.sync_search(rx, cfg.cp_len, stride, n_trials)
+    peak, delay = m.sync_search(rx, cfg.cp_len, stride, n_trials)[:2]
     sampler = ClockSampler(0)
     sampler.start()
     t_ms, _ = time_it(lambda: m.sync_search(rx, cfg.cp_len, stride, n_trials), iters=12)
@@ -72,7 +83,14 @@ def run(name, cpu_seconds):
                trials_per_s=n_trials / t_ms * 1e3, samples_per_s=n / t_ms * 1e3,
                dram_GBs=(n * 8 + n_trials * 8) / t_ms / 1e6, window_GBs=n_trials * cfg.m0 * cfg.nfft * 8 / t_ms / 1e6,
                gated_trials=hits, frames=nf, clocks=clocks)
-    if cpu_seconds > 0:
+    if nus or cfg.m0 > 1:
+        os.environ["OFDM_SYNC_TDG"] = "0"
+        pk0 = m.sync_search(rx, cfg.cp_len, stride, n_trials)[0].cpu().numpy()
+        t0_ms, _ = time_it(lambda: m.sync_search(rx, cfg.cp_len, stride, n_trials), iters=4, warm=1)
+        os.environ["OFDM_SYNC_TDG"] = "1"
+        res.update(m0=cfg.m0, hypotheses=len(nus) if nus else 0, ms_per_trial_transforms=t0_ms, speedup_vs_transforms=t0_ms / t_ms,
+                   peak_rel_err_vs_transforms=float(np.max(np.abs(pk - pk0)) / np.max(np.abs(pk0))))
+    if cpu_seconds > 0 and not nus:
         h = rx[: min(n, 1 << 20)].cpu().numpy()
         res["cpu_literal_trials_per_s_1core"] = cpu_rate(cfg, h, stride, True, cpu_seconds)
         res["cpu_vectorised_trials_per_s_1core"] = cpu_rate(cfg, h, stride, False, cpu_seconds)

@@ -78,6 +78,18 @@ if __name__ == "__main__":
             ndb = int(0.9375 * n) // 4 * 4
             run("N%d_16qam" % n, ModemConfig(nfft=n, cp_len=n // 4, num_synch_bins=n - 2, num_data_bins=ndb, m0=1,
                                              d=3, bps=4, snr=100, noise_var=0.01), max(64, (1 << 26) // (4 * n * 5 // 4)))
+    if which in ("ab",):                                    # round-2 A/B set: LTE, the N=4096 sweep points, two HBM-bound sizes
+        run("LTE_64qam", ModemConfig(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13,
+                                     bps=6, snr=100, noise_var=0.01), 4096)
+        for bps, nm in ((2, "qpsk"), (4, "16qam"), (6, "64qam")):
+            run("N4096_" + nm, ModemConfig(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=3,
+                                           bps=bps, snr=100, noise_var=0.01), 6553)
+        run("N2048_16qam", ModemConfig(nfft=2048, cp_len=512, num_synch_bins=2046, num_data_bins=1920, m0=1, d=3,
+                                       bps=4, snr=100, noise_var=0.01), 13107)
+        run("N512_16qam", ModemConfig(nfft=512, cp_len=128, num_synch_bins=510, num_data_bins=480, m0=1, d=3,
+                                      bps=4, snr=100, noise_var=0.01), 52428)
+        run("N64_qpsk", ModemConfig(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2,
+                                    snr=100, noise_var=0.01), 419430)
     if which in ("all", "n64"):
         run("N64_16qam", ModemConfig(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4,
                                      snr=100, noise_var=0.01), 333334)
