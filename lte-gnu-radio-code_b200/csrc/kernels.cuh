@@ -621,7 +621,7 @@ template <class C, int BPS> struct DataCtx {
 };
 
 // equalise + demap + store one data symbol held in v[] (FFT output).  SynchAndChanEst.py:232-248.
-template <class C, int BPS, int GROUPS, bool GSM, bool DENSE = false>
+template <class C, int BPS, int GROUPS, bool GSM, bool DENSE = false, bool EQC = false>
 __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<C, BPS> &D, const float2 (&v)[C::PPT],
                                               const Gains<C, GSM> &G, long long row, float *redf, uint8_t *hb, float *ls,
                                               int j, int gid, float2 *__restrict__ eq_out, float *__restrict__ llr_out,
@@ -641,7 +641,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     const float pw = group_sum<T, GROUPS>(pw2.x + pw2.y, redf, j, gid);
     const float p0 = pw > 0.f ? D.sqrt_ndb * rsqrtf(pw) : 0.f;        // sqrt(ndb / sum|Y|^2), :233
     // every output is optional: a caller that only decodes wants LLRs or hard bits, not the equalised symbols
-    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr), weq = OFDM_EQ_ALWAYS ? true : (eq_out != nullptr);
+    const bool soft = (llr_out != nullptr), hard = (hard_out != nullptr), weq = (OFDM_EQ_ALWAYS || EQC) ? true : (eq_out != nullptr);
     // 64-QAM: a bin's six LLRs are 24 bytes, so per-lane stores would leave every 32-byte sector
     // half-written by each instruction (2.9x the sector writes at L2, ncu).  The row is assembled in
     // shared memory instead and written with full 16-byte lanes.
@@ -660,7 +660,10 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     // N=4096 0.777 -> 0.701 ms with the equalised-symbol switch compiled out; OFDM_EPI_MASKS=0 rebuilds that form).
     const unsigned emask = weq ? mask : 0u, smask = soft ? mask : 0u, hmask = hard ? mask : 0u;
     (void)emask; (void)smask; (void)hmask;
-    if (CH > 0) {
+    // EQC: the kernel variant launched when the equalised symbols ARE wanted (the default call) has that switch compiled
+    // out and tests `used && wanted` for the other two -- the form ptxas schedules best at N = 512..2048 (see launch.cuh).
+    // (Two copies of the block behind a uniform "all outputs wanted" branch were slower than either: N=2048 0.578 -> 0.625 ms.)
+    if constexpr (CH > 0) {
 #pragma unroll
         for (int c = 0; c < PPT; c += (CH > 0 ? CH : PPT)) {
             if (CH == PPT || __any_sync(0xffffffffu, ((mask >> c) & ((1u << CH) - 1u)) != 0u)) {
@@ -668,12 +671,12 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
                 for (int m = c; m < c + CH; ++m) {
                     const bool used = (mask & (1u << m)) != 0;
                     const float2 z = cscale(cmul(G.get(m), v[m]), p0);
-                    if (OFDM_EPI_MASKS >= 1 ? (emask & (1u << m)) != 0 : (used && weq)) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
+                    if ((OFDM_EPI_MASKS >= 1 && !EQC) ? (emask & (1u << m)) != 0 : (used && weq)) st_out<CS>((m < PPT / 2 ? eqp : eqn) + m * T, z);
                     float Lb[BPS];
                     unsigned bits;
                     D.dem.run(z, Lb, bits);
                     float *q = (m < PPT / 2 ? lp : ln) + m * T * BPS;
-                    if (OFDM_EPI_MASKS >= 3 ? (smask & (1u << m)) != 0 : (used && soft)) {
+                    if ((OFDM_EPI_MASKS >= 3 && !EQC) ? (smask & (1u << m)) != 0 : (used && soft)) {
                         if (BPS == 1) {
                             st_out<CS>(q, Lb[0]);
                         } else if (BPS == 4) {
@@ -687,7 +690,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
                                 st_out<CS>(reinterpret_cast<float2 *>(q + b), make_float2(Lb[b], Lb[b + 1]));
                         }
                     }
-                    if (OFDM_EPI_MASKS >= 3 ? (hmask & (1u << m)) != 0 : (used && hard)) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
+                    if ((OFDM_EPI_MASKS >= 3 && !EQC) ? (hmask & (1u << m)) != 0 : (used && hard)) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
                 }
             }
         }
@@ -965,11 +968,11 @@ template <class C, bool GSM, bool DENSE = false> struct MinBlocksRxF {
 // data window of the frame before the FFT.
 // EPI selects the data-symbol epilogue: EPI_SPARSE per-lane stores with unused bins skipped, EPI_BULK rows through the
 // async proxy (data_epilogue_bulk), EPI_DENSE per-lane stores with branch-free arithmetic (data_epilogue, DENSE).
-enum { EPI_SPARSE = 0, EPI_BULK = 1, EPI_DENSE = 2 };
+enum { EPI_SPARSE = 0, EPI_BULK = 1, EPI_DENSE = 2, EPI_DENSE_EQ = 3 };   // EPI_DENSE_EQ: dense, eq output compiled in (data_epilogue, EQC)
 // CPP: the plan has a CP pattern (DevParams::cp_extra); instantiated without comb pilots and hypothesis bank only, so
 // that the reference's uniform prefix pays nothing for it.
 template <class C, int BPS, int GROUPS, bool PIL, bool GSM, bool SB, bool CFO, int EPI = EPI_SPARSE, bool CPP = false>
-__global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM, EPI == 2>::value)
+__global__ void __launch_bounds__(C::T *GROUPS, MinBlocksRxF<C, GSM, EPI >= 2>::value)
 rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first,
                  long long frame_stride, long long n_frames, int iters, int *__restrict__ delay_out,
                  float *__restrict__ peak_out, uint8_t *__restrict__ locked_out, int *__restrict__ hyp_out,
@@ -1123,7 +1126,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                 data_epilogue_bulk<C, BPS, GROUPS, GSM>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, es, j, gid, eq_out,
                                                        llr_out, hard_out);
             } else {
-                data_epilogue<C, BPS, GROUPS, GSM, EPI == EPI_DENSE>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, j, gid,
+                data_epilogue<C, BPS, GROUPS, GSM, EPI >= EPI_DENSE, EPI == EPI_DENSE_EQ>(P, D, cur, G, f * P.d + (s - P.m0), redf, hb, ls, j, gid,
                                                                      eq_out, llr_out, hard_out);
             }
         }

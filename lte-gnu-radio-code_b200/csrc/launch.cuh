@@ -68,6 +68,10 @@ static inline cudaError_t plan_launch(int threads, int &smem, int groups, long l
         default: return cudaErrorInvalidValue; \
     }
 
+// sizes (bit log2 N) whose dense receiver takes the EPI_DENSE_EQ variant when the equalised symbols are wanted
+#ifndef OFDM_EQC_SIZES_DEFAULT
+#define OFDM_EQC_SIZES_DEFAULT 0x0e00u
+#endif
 template <int LOG2N>
 cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_samples, long long first,
                              long long frame_stride, long long n_frames, int *delay, float *peak, uint8_t *locked,
@@ -124,7 +128,13 @@ cudaError_t launch_rx_frames(const DevParams &P, const float2 *x, long long n_sa
                 else if (bulk) OFDM_LAUNCH_RXF(false, false, EPI_BULK, P)
             }
             // densely filled grids take the branch-free epilogue (same shared-memory footprint as the sparse one)
-            if (!bulk && dense && cpp) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE, true, Qp)
+            // (EPI_DENSE_EQ: the equalised symbols are wanted and this size runs faster with that switch compiled out --
+            // OFDM_EQC_SIZES: bit log2 N set = use it at that size)
+            static const unsigned eqc_sizes = getenv("OFDM_EQC_SIZES") ? (unsigned)strtoul(getenv("OFDM_EQC_SIZES"), nullptr, 0) : OFDM_EQC_SIZES_DEFAULT;
+            const bool eqc = eq != nullptr && ((eqc_sizes >> LOG2N) & 1u);
+            if (!bulk && dense && cpp && eqc) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE_EQ, true, Qp)
+            else if (!bulk && dense && eqc) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE_EQ, false, Qp)
+            else if (!bulk && dense && cpp) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE, true, Qp)
             else if (!bulk && dense) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_DENSE, false, Qp)
             else if (!bulk && cpp) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_SPARSE, true, Qp)
             else if (!bulk) OFDM_LAUNCH_RXF_C(CD, GD, false, false, EPI_SPARSE, false, Qp)
