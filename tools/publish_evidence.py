@@ -19,8 +19,15 @@ for src, dst in (("bench_n64.json", "bench_n64"), ("bench_reference.json", "benc
                  ("bench_sync_search.jsonl", "bench_sync_search"), ("bench_blocks.jsonl", "bench_blocks")):
     ext = os.path.splitext(src)[1]
     shutil.copy(os.path.join(EV, src), os.path.join(PR, "%s_%s%s" % (TAG, dst, ext)))
+for rep in ("prof_final", "prof_sync"):                                   # raw pages of the .ncu-rep files brought back
+    if os.path.exists(os.path.join(EV, rep + ".ncu-rep")) and not os.path.exists(os.path.join(EV, rep + "_raw.csv")):
+        with open(os.path.join(EV, rep + "_raw.csv"), "w") as f:
+            subprocess.check_call(["ncu", "-i", os.path.join(EV, rep + ".ncu-rep"), "--page", "raw", "--csv"], stdout=f)
 subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_export.py"), os.path.join(EV, "prof_final_raw.csv"),
                        os.path.join(PR, "%s_ncu_full_rx_tx_n64_lte.csv" % TAG)])
+if os.path.exists(os.path.join(EV, "prof_sync_raw.csv")):
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_export.py"), os.path.join(EV, "prof_sync_raw.csv"),
+                           os.path.join(PR, "%s_ncu_full_sync_search.csv" % TAG)])
 
 rows = list(csv.reader(l for l in open(os.path.join(EV, "launches_bench_n64.csv")) if l.startswith('"')))
 hdr = rows[0]
@@ -40,7 +47,9 @@ acc = {}
 for r in raw[2:]:
     if "rx_frames_kernel" not in r[ki]:
         continue
-    key = "rx_n64_16qam_1m" if "FftCfg<6" in r[ki] else "rx_lte20_64qam"
+    key = "rx_n64_16qam_1m" if "FftCfg<6" in r[ki] else ("rx_lte20_64qam" if "FftCfg<11" in r[ki] else None)
+    if key is None:
+        continue
     b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
     acc.setdefault(key, []).append(b)
 traffic = {k: int(round(sum(v) / len(v))) for k, v in acc.items()}

@@ -9,6 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "lte-gnu-radio-code_b200", "python"))
+sys.path.insert(0, ROOT)
 from ofdm_b200 import Modem, ModemConfig  # noqa: E402
 
 
@@ -27,6 +28,7 @@ def time_it(fn, iters=10, warm=3):
 
 
 def run(name, cfg, n_frames, llr=True, hard=True):
+    from bench import ClockSampler                      # SM clock and throttle reasons sampled over the timed region
     m = Modem(cfg)
     bits = torch.randint(0, 256, (n_frames * cfg.d * cfg.hard_stride,), dtype=torch.uint8, device="cuda")
     tx = m.tx_modulate(bits, n_frames)
@@ -34,8 +36,11 @@ def run(name, cfg, n_frames, llr=True, hard=True):
     taps = taps / torch.linalg.norm(taps)
     rx = m.channel_awgn(tx, n_frames, taps, 0.05, 2024)
     out = m.rx_frames(rx, n_frames, want_llr=llr, want_hard=hard)
+    sampler = ClockSampler(0)
+    sampler.start()
     t_tx, t_tx_min = time_it(lambda: m.tx_modulate(bits, n_frames, out=tx))
     t_rx, t_rx_min = time_it(lambda: m.rx_frames(rx, n_frames, out=out))
+    clocks = sampler.stop()
     cnt = m.counters(bits, n_frames, bits_rx=out["hard"], eq=out["eq"], locked=out["locked"]).cpu().numpy()
     L = cfg.sym_len
     nsym = n_frames * cfg.d
@@ -49,7 +54,7 @@ def run(name, cfg, n_frames, llr=True, hard=True):
                rx_ms=t_rx, rx_GBs=rx_bytes / t_rx / 1e6, rx_Msym_s=nsym / t_rx / 1e3,
                tx_ms=t_tx, tx_GBs=tx_bytes / t_tx / 1e6, tx_Msym_s=nsym / t_tx / 1e3,
                ber=cnt[0] / max(cnt[1], 1), evm=float(np.sqrt(cnt[2] / max(cnt[3], 1e-30))),
-               locked=cnt[4] / max(cnt[5], 1))
+               locked=cnt[4] / max(cnt[5], 1), clocks=clocks)
     print(json.dumps(res))
     return res
 
