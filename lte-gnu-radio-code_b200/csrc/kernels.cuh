@@ -249,6 +249,9 @@ __device__ __forceinline__ unsigned neg_bit(float x) { return __float_as_uint(x)
 // append the sign bit of x to an MSB-first bit accumulator: one funnel shift per bit
 __device__ __forceinline__ unsigned push_sign(unsigned acc, float x) { return __funnelshift_l(__float_as_uint(x), acc, 1); }
 
+#ifndef OFDM_DEMAP64_PACKED
+#define OFDM_DEMAP64_PACKED 0    // B200: LTE RX 0.643 -> 0.640 ms, N=4096 64-QAM 0.922 -> 0.955 ms: instruction count is not what bounds them
+#endif
 template <int BPS> struct Demapper {
     static constexpr float A = BPS == 2 ? 0.70710678118654752440f
                                         : (BPS == 4 ? 0.31622776601683793320f : 0.15430334996209191026f);
@@ -275,8 +278,24 @@ template <int BPS> struct Demapper {
             // with m2 = max(t-2a,0), m4 = max(t-4a,0), m6 = max(t-6a,0):
             //   b0: -sgn(x) c (t + m2 + m4 + m6)    b1: c (2t - 6a - m2 + m6)    b2: c (2 m4 - t + 2a)
             float a0[2], a1[2], a2[2];
-            const float xs[2] = {z.x, z.y};
             const float c2 = 2.f * c, k1 = -6.f * A * c, k2 = 2.f * A * c;
+#if OFDM_F32X2 && OFDM_DEMAP64_PACKED
+            // both axes at once on the packed pipe: the same IEEE operations in the same order as the scalar form below
+            // (bit-identical results), 22 instead of 32 instructions per bin; only |x| and max(., 0) stay scalar
+            const float2 t = make_float2(fabsf(z.x), fabsf(z.y));
+            const float2 u2 = __fadd2_rn(t, make_float2(-2.f * A, -2.f * A)), u4 = __fadd2_rn(t, make_float2(-4.f * A, -4.f * A)),
+                         u6 = __fadd2_rn(t, make_float2(-6.f * A, -6.f * A));
+            const float2 m2 = make_float2(fmaxf(u2.x, 0.f), fmaxf(u2.y, 0.f)), m4 = make_float2(fmaxf(u4.x, 0.f), fmaxf(u4.y, 0.f)),
+                         m6 = make_float2(fmaxf(u6.x, 0.f), fmaxf(u6.y, 0.f));
+            const float2 s0 = __fmul2_rn(make_float2(c, c), __fadd2_rn(__fadd2_rn(t, m2), __fadd2_rn(m4, m6)));
+            a0[0] = flip_sign_of(s0.x, z.x);
+            a0[1] = flip_sign_of(s0.y, z.y);
+            const float2 b1 = __ffma2_rn(make_float2(c, c), __fadd2_rn(m6, make_float2(-m2.x, -m2.y)),
+                                         __ffma2_rn(make_float2(c2, c2), t, make_float2(k1, k1)));
+            const float2 b2 = __ffma2_rn(make_float2(c2, c2), m4, __ffma2_rn(make_float2(-c, -c), t, make_float2(k2, k2)));
+            a1[0] = b1.x; a1[1] = b1.y; a2[0] = b2.x; a2[1] = b2.y;
+#else
+            const float xs[2] = {z.x, z.y};
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const float t = fabsf(xs[i]);
@@ -285,6 +304,7 @@ template <int BPS> struct Demapper {
                 a1[i] = fmaf(c, m6 - m2, fmaf(c2, t, k1));
                 a2[i] = fmaf(c2, m4, fmaf(-c, t, k2));
             }
+#endif
             L[0] = a0[0]; L[1] = a0[1]; L[2] = a1[0]; L[3] = a1[1]; L[4] = a2[0]; L[5] = a2[1];
             bits = push_sign(push_sign(push_sign(push_sign(push_sign(push_sign(0u, z.x), z.y), a1[0]), a1[1]), a2[0]), a2[1]) ^ 15u;
         }
@@ -1321,6 +1341,10 @@ rx_demod_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sam
 // Both normalisations are scale factors derived from two sums over the L = N+CP output samples
 // (CP samples count twice), so the symbol is written to HBM once, already normalised.
 // ------------------------------------------------------------------------------------------------
+// transmitter sizes from this one on exchange through split-phase (mbarrier) barriers; 13 = never (A/B in DESIGN.md 3.11)
+#ifndef OFDM_SPLIT_TX_MIN_LOG2N
+#define OFDM_SPLIT_TX_MIN_LOG2N 11    // B200: LTE TX 0.317 -> 0.314 ms, N=4096 (16 points per thread) 0.197 -> 0.193 ms; N=1024 0.148 -> 0.150 ms
+#endif
 #ifndef OFDM_TX_MIDZERO
 #define OFDM_TX_MIDZERO 1                 // see tx_kernel: guard band compiled out for grids below 5/8 fill (LTE)
 #endif
@@ -1507,7 +1531,7 @@ tx_kernel(const DevParams P, const uint8_t *__restrict__ bits, float2 *__restric
 #pragma unroll
                         for (int m = 0; m < PPT; ++m) v[m] = __ldg(z + m * T);
                     }
-                    fft_group<C, true, GROUPS, false, TWR, MZ>(v, tws, b0, b1, j, gid, pp, twreg);
+                    fft_group<C, true, GROUPS, false, TWR, MZ, (C::LOG2N >= OFDM_SPLIT_TX_MIN_LOG2N)>(v, tws, b0, b1, j, gid, pp, twreg, mbar);
                 };
                 constexpr bool MZ_OK = OFDM_TX_MIDZERO != 0 && PPT == 16 && T >= 32;
                 if constexpr (MZ_OK) {

@@ -73,3 +73,41 @@ def test_outputs_stay_inside_their_buffers(kw, shift):
         lo //= b.element_size()
         outside = torch.cat((b[:lo], b[lo + w.numel():]))
         assert bool((outside == fill).all()), "guard band of %s overwritten" % name
+
+
+TX_GUARD_CASES = [
+    dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=4),
+    dict(nfft=512, cp_len=36, num_synch_bins=510, num_data_bins=300, m0=2, d=2, bps=6),
+    dict(nfft=1024, cp_len=256, num_synch_bins=1022, num_data_bins=960, m0=1, d=2, bps=2),
+    dict(nfft=2048, cp_len=144, cp_first=160, slot_syms=7, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6),
+    dict(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=2, bps=4),
+]
+
+
+@pytest.mark.parametrize("kw", TX_GUARD_CASES, ids=lambda k: "N%d_b%d_n%d" % (k["nfft"], k["bps"], k["num_data_bins"]))
+@pytest.mark.parametrize("wide", ["0", "2"])
+def test_transmitter_output_stays_inside_its_buffer(kw, wide, monkeypatch):
+    """Both transmitter kernels (16 and 64 points per thread; OFDM_TX_WIDE) write the waveform -- body and cyclic-prefix
+    copies, incl. the longer first prefix of a slot -- into a window of a sentinel-filled buffer: the window must equal a
+    run into a plain buffer and every sentinel around it must be intact.  The grid is oversubscribed by a non-multiple
+    of the group count, so the tail groups that redo the last symbol are exercised as well."""
+    import numpy as np
+    import torch
+    from ofdm_b200 import Modem, ModemConfig
+    monkeypatch.setenv("OFDM_TX_WIDE", wide)
+    cfg = ModemConfig(snr=100, **kw)
+    m = Modem(cfg)
+    nf = 2 * 148 * 2 // (cfg.m0 + cfg.d) + 3
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    bits = torch.randint(0, 256, (nf * cfg.d * cfg.hard_stride,), dtype=torch.uint8, device="cuda", generator=g)
+    ref = m.tx_modulate(bits, nf).clone()
+    n = nf * cfg.frame_len
+    pad = 2 * cfg.nfft + 5
+    sent = complex(12345.0, -54321.0)
+    big = torch.full((n + 2 * pad,), sent, dtype=torch.complex64, device="cuda")
+    m.tx_modulate(bits, nf, out=big[pad:pad + n])
+    torch.cuda.synchronize()
+    assert torch.equal(big[pad:pad + n], ref)
+    assert bool((big[:pad] == sent).all()) and bool((big[pad + n:] == sent).all())
+    assert float(ref.abs().max()) < 100.0 and bool(torch.isfinite(ref.abs()).all())
