@@ -221,7 +221,7 @@ __global__ void channel_kernel(const float2 *__restrict__ x, float2 *__restrict_
 // ------------------------------------------------------------------------------------------------
 constexpr int TD_R = 8, TD_THREADS = 128, TD_TQ = TD_R * TD_THREADS;
 #ifndef OFDM_SYNC_TD_DEFAULT
-#define OFDM_SYNC_TD_DEFAULT 2
+#define OFDM_SYNC_TD_DEFAULT 3
 #endif
 
 __global__ void __launch_bounds__(TD_THREADS)
@@ -354,9 +354,7 @@ rx_sync_search_td8_kernel(const DevParams P, const float2 *__restrict__ x, long 
             const float2 h = H[M + r];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float2 a = W[(r + j) & 7];
-                acc[j].x = fmaf(a.x, h.x, fmaf(-a.y, h.y, acc[j].x));
-                acc[j].y = fmaf(a.x, h.y, fmaf(a.y, h.x, acc[j].y));
+                acc[j] = cmul_acc(acc[j], W[(r + j) & 7], h);          // two packed FMAs per complex multiply-add
             }
             const float2 a0 = W[r];                                     // position 0's own sample n = m
             en = fmaf(a0.x, a0.x, fmaf(a0.y, a0.y, en));
@@ -412,9 +410,7 @@ rx_sync_search_td8_kernel(const DevParams P, const float2 *__restrict__ x, long 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float2 a = U[(j - r - 1) & 7], b = W[(j - r - 1) & 7];
-                    const float2 dl = make_float2(a.x - b.x, a.y - b.y);
-                    acc[j].x = fmaf(dl.x, hh.x, fmaf(-dl.y, hh.y, acc[j].x));
-                    acc[j].y = fmaf(dl.x, hh.y, fmaf(dl.y, hh.x, acc[j].y));
+                    acc[j] = cmul_acc(acc[j], csub(a, b), hh);
                     const unsigned long long key = key_of(j, i);
                     K[(j - r - 1) & 7] = key > K[(j - r - 1) & 7] ? key : K[(j - r - 1) & 7];
                 }
@@ -637,6 +633,178 @@ rx_sync_search_tdg_kernel(const DevParams P, const float2 *__restrict__ x, long 
     }
 }
 
+
+// Overlap-save form of the stride-1 search (one synch symbol, no hypothesis bank): the N-tap sliding correlation r(q) is
+// a FIR filter over the capture, so a block of NB >= 2N samples is filtered in the frequency domain -- forward transform,
+// multiply by the taps' spectrum G[k] = (1/NB) sum_m h[m] e^{+2 pi i k m / NB}, inverse transform -- and the NB - N + 1
+// outputs that did not wrap are r(q0 .. q0 + NB - N): about 2 NB log2 NB operations per block instead of N per
+// position (N = 2048: 2 x 4096-point transforms per 2048 positions).  Everything after r(q) is the register-blocked
+// kernel's second half unchanged: the CP+1 delays as a prefix sum per position, the circular register file of running
+// maxima, one shared-memory atomic per completed trial offset.  The window sums behind the unit-power factor (energy,
+// DC bin, band-edge bin) come from an exclusive prefix over 8-sample chunks of the staged stretch -- a window starting at
+// a multiple of 8 is a whole number of chunks -- and slide from there.  One CTA = one block; grid = tiles of
+// PB - CP trials.  Specification: oracle/ofdm_oracle.py sync_search_time_domain (same numbers up to rounding).
+template <int LOG2NB>
+__global__ void __launch_bounds__(CfgRxF<LOG2NB>::T)
+rx_sync_search_os_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
+                         long long n_trials, float *__restrict__ peak_out, int *__restrict__ delay_out,
+                         const float2 *__restrict__ gos, int PB) {
+    using C = CfgRxF<LOG2NB>;
+    constexpr int GROUPS = 1;
+    OFDM_KERNEL_PROLOGUE_(GROUPS, false, false, false, false, 0)
+    (void)total_groups; (void)gg;
+    const int N = P.nfft, CP = P.cp, t = tid;
+    const int A = (CP + 7) & ~7;
+    const int TP = PB - CP;                                             // trials per tile
+    const int XW = A + PB + N;                                          // staged samples q0 - A .. (a multiple of 8)
+    const int SX = XW / 8 + 1, SB = PB / 8 + 1, NC = XW / 8;
+    float2 *Xs = reinterpret_cast<float2 *>(smem_raw + S::BYTES);
+    float2 *Hh = Xs + 8 * SX;                                           // Hh[i] = h[N - i], i = 1..CP
+    float *pw = reinterpret_cast<float *>(Hh + ((CP + 2) & ~1));
+    float *cs = pw + 8 * SB;                                            // chunk prefixes: 5 arrays of NC + 1
+    // r(q) and the per-trial maxima live in the exchange buffers once the transforms are done
+    float2 *Rs = b0;
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(Rs + 8 * SB);
+    const long long tile0 = (long long)blockIdx.x * TP;
+    const long long q0 = first_start + tile0;
+    const long long last_trial = n_trials - 1;
+    for (int i = t; i < XW; i += T) {
+        const long long g = q0 - A + i;
+        Xs[(i & 7) * SX + (i >> 3)] = (g >= 0 && g < n_samples) ? __ldg(x + g) : make_float2(0.f, 0.f);
+    }
+    for (int i = t; i <= CP; i += T) Hh[i] = i ? __ldg(P.h_td + N - i) : make_float2(0.f, 0.f);
+    {
+        float2 v[PPT];
+        load_pts<T, PPT>(v, x, q0, n_samples, j);
+        fft_group<C, false, GROUPS>(v, tws, b0, b1, j, gid, pp);
+#pragma unroll
+        for (int m = 0; m < PPT; ++m) v[m] = cmul(v[m], __ldg(gos + j + m * T));
+        fft_group<C, true, GROUPS>(v, tws, b0, b1, j, gid, pp);
+        __syncthreads();                                                // every read of the last exchange is done
+#pragma unroll
+        for (int m = 0; m < PPT; ++m) {
+            const int n = j + m * T;
+            if (n < PB) Rs[(n & 7) * SB + (n >> 3)] = v[m];
+        }
+    }
+    for (int i = t; i < 8 * SB; i += T) best[i] = 0ull;
+    // chunk sums: chunk c = staged samples 8c .. 8c+7 (sign of the band-edge sum alternates from the chunk's first sample,
+    // which has an even staged index, like every window start this kernel looks at)
+    for (int c = t; c < NC; c += T) {
+        float e = 0.f;
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float2 a = Xs[r * SX + c];
+            e = fmaf(a.x, a.x, fmaf(a.y, a.y, e));
+            s0.x += a.x;
+            s0.y += a.y;
+            s1.x += (r & 1) ? -a.x : a.x;
+            s1.y += (r & 1) ? -a.y : a.y;
+        }
+        cs[c] = e;
+        cs[(NC + 1) + c] = s0.x;
+        cs[2 * (NC + 1) + c] = s0.y;
+        cs[3 * (NC + 1) + c] = s1.x;
+        cs[4 * (NC + 1) + c] = s1.y;
+    }
+    __syncthreads();
+    if (t < 32) {                                                       // exclusive prefix over the chunks, one warp
+        const int per = (NC + 1 + 31) / 32, lo = t * per, hi = min(lo + per, NC + 1);
+#pragma unroll 1
+        for (int a = 0; a < 5; ++a) {
+            float *arr = cs + a * (NC + 1);
+            float run = 0.f;
+            for (int c = lo; c < hi; ++c) {                             // local exclusive prefix, run = lane total
+                const float val = c < NC ? arr[c] : 0.f;
+                arr[c] = run;
+                run += val;
+            }
+            float incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (t >= o) incl += up;
+            }
+            const float off = incl - run;                               // total of the lanes before this one
+            for (int c = lo; c < hi; ++c) arr[c] += off;
+        }
+    }
+    __syncthreads();
+    if (8 * t < PB) {
+        const float2 *xt = Xs + A / 8 + t;
+        auto LD = [&](int c) -> float2 { return xt[(c & 7) * SX + (c >> 3)]; };
+        float2 acc[8], W[8], U[8];
+        const int c0 = A / 8 + t, c1 = c0 + N / 8;
+        float en = cs[c1] - cs[c0];
+        float2 s0 = make_float2(cs[(NC + 1) + c1] - cs[(NC + 1) + c0], cs[2 * (NC + 1) + c1] - cs[2 * (NC + 1) + c0]);
+        float2 s1 = make_float2(cs[3 * (NC + 1) + c1] - cs[3 * (NC + 1) + c0], cs[4 * (NC + 1) + c1] - cs[4 * (NC + 1) + c0]);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            acc[jj] = Rs[jj * SB + t];
+            U[jj] = LD(jj);
+            W[jj] = LD(N + jj);
+        }
+        auto put_pw = [&](int jj) {
+            pw[jj * SB + t] = (float)N * en - cabs2(s0) - cabs2(s1);
+        };
+        unsigned long long K[8];
+        auto key_of = [&](int jj, int i) -> unsigned long long {
+            return ((unsigned long long)__float_as_uint(cabs2(acc[jj])) << 32) | (unsigned)(0x7fffffff - i);
+        };
+        auto flush = [&](unsigned long long key, int c) {
+            const int pl = 8 * t + c;
+            if (pl >= 0 && pl < TP && tile0 + pl <= last_trial) atomicMax(best + (pl & 7) * SB + (pl >> 3), key);
+        };
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            put_pw(jj);
+            K[jj] = key_of(jj, 0);
+            const float2 a = U[jj], b = W[jj];
+            en += cabs2(b) - cabs2(a);
+            s0.x += b.x - a.x;
+            s0.y += b.y - a.y;
+            s1.x = -(s1.x - a.x + b.x);
+            s1.y = -(s1.y - a.y + b.y);
+        }
+        flush(K[7], 7);
+        for (int I = 0; I < CP; I += 8) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = I + r + 1;
+                if (i <= CP) {
+                    const float2 hh = Hh[i];
+                    U[7 - r] = LD(-i);
+                    W[7 - r] = LD(N - i);
+                    K[7 - r] = 0ull;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        acc[jj] = cmul_acc(acc[jj], csub(U[(jj - r - 1) & 7], W[(jj - r - 1) & 7]), hh);
+                        const unsigned long long key = key_of(jj, i);
+                        K[(jj - r - 1) & 7] = key > K[(jj - r - 1) & 7] ? key : K[(jj - r - 1) & 7];
+                    }
+                    flush(K[(6 - r) & 7], 7 - i);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = ((u - (-CP & 7)) & 7) - CP;
+            if (c <= 6 - CP) flush(K[u], c);
+        }
+    }
+    __syncthreads();
+    for (int pl = t; pl < TP; pl += T) {
+        const long long tr = tile0 + pl;
+        if (tr > last_trial) break;
+        const unsigned long long key = best[(pl & 7) * SB + (pl >> 3)];
+        const float pv = pw[(pl & 7) * SB + (pl >> 3)];
+        const float p_est = pv > 0.f ? sqrtf((float)P.mm / pv) : 0.f;
+        peak_out[tr] = p_est * sqrtf(__uint_as_float((unsigned)(key >> 32)));
+        delay_out[tr] = 0x7fffffff - (int)(key & 0xffffffffu);
+    }
+}
+
 }  // namespace ofdm
 
 // ------------------------------------------------------------------------------------------------
@@ -784,6 +952,7 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     // only for the configuration it serves (one synch symbol on every bin but DC and the band edge)
     const bool td_ok = (m0 <= 2 && nsb == N - 2);
     std::vector<float2> h_td((size_t)m0 * N, make_float2(0.f, 0.f));
+    std::vector<double> hd_r(N, 0.0), hd_i(N, 0.0);
     if (td_ok) {
         std::vector<double> cs(N), sn(N);
         for (int k = 0; k < N; ++k) {
@@ -801,13 +970,46 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
                     ai += -zr[s * nsb + idx] * sn[e2] - zi[s * nsb + idx] * cs[e2];
                 }
                 h_td[(size_t)s * N + m] = make_float2((float)ar, (float)ai);
+                if (s == 0) {
+                    hd_r[m] = ar;
+                    hd_i[m] = ai;
+                }
             }
+    }
+    // overlap-save search (one synch symbol, N <= 2048): block of NB = max(512, 4N) <= 4096 samples, its forward twiddles
+    // and G[k] = (1/NB) sum_m h[m] e^{+2 pi i k m / NB}
+    int os_log2nb = 0;
+    std::vector<float2> tw_os, gos;
+    // (B200, stride-1 search, ms per launch, N-tap kernel -> overlap-save: N=64 0.385 -> 0.502, N=256 0.703 -> 0.600, N=1024
+    // 1.67 -> 1.13, N=2048 2.05 -> 0.68: from N=256 on.  Its rounding error is relative to the largest sample of the BLOCK, not
+    // of the window -- 1e-6 of the strongest peak -- so trials on noise next to a burst agree with the N-tap kernel to 1e-3 only.)
+    if (td_ok && m0 == 1 && N >= 256 && N <= 2048) {
+        int NB = 4 * N < 512 ? 512 : 4 * N;
+        if (NB > 4096) NB = 4096;
+        while ((1 << os_log2nb) < NB) ++os_log2nb;
+        tw_os.resize(NB);
+        gos.resize(NB);
+        std::vector<double> cb(NB), sb2(NB);
+        for (int k = 0; k < NB; ++k) {
+            cb[k] = cos(two_pi * (double)k / (double)NB);
+            sb2[k] = sin(two_pi * (double)k / (double)NB);
+            tw_os[k] = make_float2((float)cb[k], (float)(-sb2[k]));
+        }
+        for (int k = 0; k < NB; ++k) {
+            double gr = 0.0, gi = 0.0;
+            for (int m = 0; m < N; ++m) {
+                const int e2 = (int)(((long long)k * m) % NB);                // e^{+j2pi km/NB} = cb + j sb2
+                gr += hd_r[m] * cb[e2] - hd_i[m] * sb2[e2];
+                gi += hd_r[m] * sb2[e2] + hd_i[m] * cb[e2];
+            }
+            gos[k] = make_float2((float)(gr / (double)NB), (float)(gi / (double)NB));
+        }
     }
     const size_t b_tw = sizeof(float2) * N, b_zb = sizeof(float2) * m0 * N, b_w = sizeof(float) * N,
                  b_zd = sizeof(float2) * m0 * 2, b_zt = sizeof(float2) * m0 * N, b_pt = sizeof(float2) * N,
-                 b_ht = sizeof(float2) * m0 * N;
+                 b_ht = sizeof(float2) * m0 * N, b_os = sizeof(float2) * tw_os.size();
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt) + al(b_pt) + al(b_ht);
+    const size_t total = al(b_tw) + al(b_zb) + al(b_w) + al(b_zd) + al(b_zt) + al(b_pt) + al(b_ht) + 2 * al(b_os);
     e = cudaMalloc(&pl->d_tables, total);
     if (e != cudaSuccess) {
         delete pl;
@@ -830,6 +1032,11 @@ int ofdm_plan_create(const ofdm_params *p, ofdm_plan **out) {
     D.pilot_tx = (const float2 *)put(pilot_tx.data(), b_pt);
     D.h_td = (const float2 *)put(h_td.data(), b_ht);
     if (!td_ok) D.h_td = nullptr;
+    pl->os_log2nb = os_log2nb;
+    if (os_log2nb) {
+        pl->d_tw_os = (const float2 *)put(tw_os.data(), b_os);
+        pl->d_gos = (const float2 *)put(gos.data(), b_os);
+    }
     if (e != cudaSuccess) {
         cudaFree(pl->d_tables);
         delete pl;
@@ -1000,9 +1207,52 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
             return OFDM_OK;
         }
     }
+    // one synch symbol, no bank, N <= 2048: the overlap-save kernel (OFDM_SYNC_TD=3, the default; 2 keeps the N-tap kernel)
+    if (td_mode == 3 && stride == 1 && pl->os_log2nb && pl->dev.h_td && pl->prm.m0 == 1 && !pl->dev.n_cfo && first_start >= 0 &&
+        pl->prm.nfft % 8 == 0) {
+        const int N = pl->prm.nfft, CP = pl->prm.cp_len, A = (CP + 7) & ~7, NB = 1 << pl->os_log2nb;
+        int T = 0, sbytes = 0;
+        switch (pl->os_log2nb) {
+            case 9: T = CfgRxF<9>::T; sbytes = Smem<CfgRxF<9>, 1, false, false, false, false, 0>::BYTES; break;
+            case 10: T = CfgRxF<10>::T; sbytes = Smem<CfgRxF<10>, 1, false, false, false, false, 0>::BYTES; break;
+            case 11: T = CfgRxF<11>::T; sbytes = Smem<CfgRxF<11>, 1, false, false, false, false, 0>::BYTES; break;
+            default: T = CfgRxF<12>::T; sbytes = Smem<CfgRxF<12>, 1, false, false, false, false, 0>::BYTES; break;
+        }
+        int PB = (NB - N + 1) & ~7;
+        if (PB > 8 * T) PB = 8 * T;
+        if (PB + 8 > NB) PB = NB - 8;
+        const int TP = PB - CP, XW = A + PB + N, SX = XW / 8 + 1, SB = PB / 8 + 1, NC = XW / 8;
+        const int smem = sbytes + 8 * SX * 8 + ((CP + 2) & ~1) * 8 + 8 * SB * 4 + 5 * (NC + 1) * 4 + 16;
+        if (TP > 0 && smem <= 220 * 1024) {
+            DevParams Q = pl->dev;
+            Q.tw = pl->d_tw_os;                                 // the block transform's own twiddles
+            const long long tiles = (n_trials + TP - 1) / TP;
+#define OFDM_OS_LAUNCH(L2)                                                                                                   \
+    {                                                                                                                        \
+        if (smem > pl->os_smem_set) {                                                                                        \
+            CU(cudaFuncSetAttribute(rx_sync_search_os_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),        \
+               "ofdm_rx_sync_search(attr)");                                                                                 \
+            pl->os_smem_set = smem;                                                                                          \
+        }                                                                                                                    \
+        rx_sync_search_os_kernel<L2><<<(unsigned)tiles, T, smem, (cudaStream_t)stream>>>(                                    \
+            Q, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay, pl->d_gos, PB);                    \
+    }
+            switch (pl->os_log2nb) {
+                case 9: OFDM_OS_LAUNCH(9) break;
+                case 10: OFDM_OS_LAUNCH(10) break;
+                case 11: OFDM_OS_LAUNCH(11) break;
+                default: OFDM_OS_LAUNCH(12) break;
+            }
+#undef OFDM_OS_LAUNCH
+            count_launch();
+            CU(cudaGetLastError(), "ofdm_rx_sync_search(os)");
+            if (d_hyp) CU(cudaMemsetAsync(d_hyp, 0, (size_t)n_trials * sizeof(int32_t), (cudaStream_t)stream), "ofdm_rx_sync_search(hyp)");
+            return OFDM_OK;
+        }
+    }
     if (td_mode != 0 && stride == 1 && pl->dev.h_td && pl->prm.m0 == 1 && !pl->dev.n_cfo && first_start >= 0 && 2 * pl->prm.cp_len <= TD_TQ) {
         const int N = pl->prm.nfft, CP = pl->prm.cp_len, TP = TD_TQ - CP, A = (CP + 7) & ~7;
-        const int smem = td_mode == 2 ? 8 * ((TD_TQ + N + A) / 8 + 1) * 8 + N * 8 + 8 * (TD_TQ / 8 + 1) * 12
+        const int smem = td_mode >= 2 ? 8 * ((TD_TQ + N + A) / 8 + 1) * 8 + N * 8 + 8 * (TD_TQ / 8 + 1) * 12
                                       : (TD_TQ + N + CP) * 8 + N * 8 + TD_TQ * 8 + TD_TQ * 4;
         if (smem > pl->td_smem_set) {                          // per plan, i.e. per device: the attribute belongs to the context
             CU(cudaFuncSetAttribute(rx_sync_search_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "ofdm_rx_sync_search(attr)");
@@ -1010,7 +1260,7 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
             pl->td_smem_set = smem;
         }
         const long long tiles = (n_trials + TP - 1) / TP;
-        if (td_mode == 2)
+        if (td_mode >= 2)
             rx_sync_search_td8_kernel<<<(unsigned)tiles, TD_THREADS, smem, (cudaStream_t)stream>>>(
                 pl->dev, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay);
         else

@@ -4,6 +4,7 @@
 #include "launch.cuh"
 
 namespace ofdm {
+typedef float2 float2_t;
 // error text returned by ofdm_last_error() (thread-local); both return the code they are given / OFDM_ECUDA
 int fail(int code, const char *fmt, const char *a = "", long long b = 0);
 int cuda_fail(cudaError_t e, const char *where);
@@ -31,6 +32,10 @@ struct ofdm_plan {
     size_t stage_bytes[NSLOT];
     void *small;                   // per-frame results of the host-buffer receiver (delay, peak, locked)
     size_t small_bytes;
+    // overlap-save search (api.cu, rx_sync_search_os_kernel): block size 2^os_log2nb (0: not available for this plan),
+    // positions per block, the block transform's twiddles and the taps' spectrum
+    int os_log2nb, os_pb, os_smem_set;
+    const ofdm::float2_t *d_tw_os, *d_gos;
     int tdg_smem_set;              // the same for the general (M0 = 2 / hypothesis bank) kernel
     int td_smem_set;               // dynamic shared memory the time-domain search kernel has been allowed on this device
 };

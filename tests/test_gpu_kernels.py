@@ -262,7 +262,7 @@ def test_time_domain_acquisition_equals_transform_search(kw, n_frames, monkeypat
     n_chk = min(300, n_trials)
     rp, rd = oo.sync_search_time_domain(rx, cfg.cp_len, 1, n_chk, prm)
     s2 = rp > 0.3 * prm.mm
-    for mode in ("1", "2"):                                  # plain and register-blocked time-domain kernels
+    for mode in ("1", "2", "3"):                             # plain / register-blocked time-domain kernels, overlap-save
         monkeypatch.setenv("OFDM_SYNC_TD", mode)
         pk1, dl1 = (a.cpu().numpy() for a in m.sync_search(d_rx, cfg.cp_len, 1, n_trials))
         assert rel_err(pk1, pk0) < RTOL, mode

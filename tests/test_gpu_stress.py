@@ -106,7 +106,7 @@ def test_search_estimate_and_symbol_list_kernels_are_bit_identical_across_launch
     nf = max(24, (1 << 21) // cfg.frame_len)
     bits, tx0, rx = build_batch(m, nf, 3)
     n_trials = (rx.numel() - cfg.sym_len - nfft - cp - 1) // stride + 1
-    for mode in (("2", "1", "0") if stride == 1 else ("0",)):          # register-blocked / plain time-domain, per-trial transforms
+    for mode in (("3", "2", "1", "0") if stride == 1 else ("0",)):     # overlap-save / register-blocked / plain time-domain, per-trial transforms
         monkeypatch.setenv("OFDM_SYNC_TD", mode)
         pk0, dl0 = (t.clone() for t in m.sync_search(rx, cp, stride, n_trials))
         for rep in range(REPS // 3):

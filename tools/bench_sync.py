@@ -30,6 +30,8 @@ CASES = {
                               compat="utsa", zc_root=23), 1, 1 << 24),
     "n64_rxofdm_stride15": (dict(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2, snr=100,
                                  compat="rxofdm", zc_root=23), 15, 1 << 26),
+    "n256_stride1": (dict(nfft=256, cp_len=64, num_synch_bins=254, num_data_bins=240, m0=1, d=3, bps=2, snr=100), 1, 1 << 23),
+    "n1024_stride1": (dict(nfft=1024, cp_len=256, num_synch_bins=1022, num_data_bins=960, m0=1, d=3, bps=2, snr=100), 1, 1 << 22),
     "lte_stride1": (dict(nfft=2048, cp_len=144, num_synch_bins=2046, num_data_bins=1200, m0=1, d=13, bps=6, snr=100),
                     1, 1 << 22),
     # the general time-domain kernel (M0 = 2 and / or the frequency-offset hypothesis bank): a 4th tuple entry is the
