@@ -648,7 +648,7 @@ template <int LOG2NB>
 __global__ void __launch_bounds__(CfgRxF<LOG2NB>::T)
 rx_sync_search_os_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
                          long long n_trials, float *__restrict__ peak_out, int *__restrict__ delay_out,
-                         const float2 *__restrict__ gos, int PB) {
+                         const float2 *__restrict__ gos, int PB, int alias_all) {
     using C = CfgRxF<LOG2NB>;
     constexpr int GROUPS = 1;
     OFDM_KERNEL_PROLOGUE_(GROUPS, false, false, false, false, 0)
@@ -660,11 +660,12 @@ rx_sync_search_os_kernel(const DevParams P, const float2 *__restrict__ x, long l
     const int SX = XW / 8 + 1, SB = PB / 8 + 1, NC = XW / 8;
     float2 *Xs = reinterpret_cast<float2 *>(smem_raw + S::BYTES);
     float2 *Hh = Xs + 8 * SX;                                           // Hh[i] = h[N - i], i = 1..CP
-    float *pw = reinterpret_cast<float *>(Hh + ((CP + 2) & ~1));
-    float *cs = pw + 8 * SB;                                            // chunk prefixes: 5 arrays of NC + 1
-    // r(q) and the per-trial maxima live in the exchange buffers once the transforms are done
+    // r(q) and the per-trial maxima live in the exchange buffers once the transforms are done; the window powers and the
+    // chunk prefixes as well where they fit (alias_all: NB = 4096, which brings the CTA under half an SM's shared memory)
     float2 *Rs = b0;
     unsigned long long *best = reinterpret_cast<unsigned long long *>(Rs + 8 * SB);
+    float *pw = alias_all ? reinterpret_cast<float *>(best + 8 * SB) : reinterpret_cast<float *>(Hh + ((CP + 2) & ~1));
+    float *cs = pw + 8 * SB;                                            // chunk prefixes: 5 arrays of NC + 1
     const long long tile0 = (long long)blockIdx.x * TP;
     const long long q0 = first_start + tile0;
     const long long last_trial = n_trials - 1;
@@ -1222,7 +1223,9 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
         if (PB > 8 * T) PB = 8 * T;
         if (PB + 8 > NB) PB = NB - 8;
         const int TP = PB - CP, XW = A + PB + N, SX = XW / 8 + 1, SB = PB / 8 + 1, NC = XW / 8;
-        const int smem = sbytes + 8 * SX * 8 + ((CP + 2) & ~1) * 8 + 8 * SB * 4 + 5 * (NC + 1) * 4 + 16;
+        const int tail = 8 * SB * 4 + 5 * (NC + 1) * 4;              // window powers + chunk prefixes
+        const int alias_all = 16 * (PB + 8) + tail <= 16 * NB ? 1 : 0;
+        const int smem = sbytes + 8 * SX * 8 + ((CP + 2) & ~1) * 8 + (alias_all ? 0 : tail) + 16;
         if (TP > 0 && smem <= 220 * 1024) {
             DevParams Q = pl->dev;
             Q.tw = pl->d_tw_os;                                 // the block transform's own twiddles
@@ -1235,7 +1238,7 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
             pl->os_smem_set = smem;                                                                                          \
         }                                                                                                                    \
         rx_sync_search_os_kernel<L2><<<(unsigned)tiles, T, smem, (cudaStream_t)stream>>>(                                    \
-            Q, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay, pl->d_gos, PB);                    \
+            Q, (const float2 *)d_time, n_samples, first_start, n_trials, d_peak, d_delay, pl->d_gos, PB, alias_all);         \
     }
             switch (pl->os_log2nb) {
                 case 9: OFDM_OS_LAUNCH(9) break;
