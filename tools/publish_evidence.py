@@ -39,6 +39,21 @@ with open(os.path.join(PR, "%s_launches_bench_n64.csv" % TAG), "w", newline="") 
         r2[1] = r2[1][:110]
         w.writerow(r2)
 
+# one row per kernel of the acquisition capture is enough (the launches of a case are identical)
+sp = os.path.join(PR, "%s_ncu_full_sync_search.csv" % TAG)
+if os.path.exists(sp):
+    rows_s = list(csv.reader(open(sp)))
+    seen, keep = set(), rows_s[:2]
+    ki_s = rows_s[0].index("Kernel Name")
+    gi_s = rows_s[0].index("Grid Size") if "Grid Size" in rows_s[0] else ki_s
+    for r in rows_s[2:]:
+        key = (r[ki_s], r[gi_s])
+        if key not in seen:
+            seen.add(key)
+            keep.append(r)
+    with open(sp, "w", newline="") as f:
+        csv.writer(f).writerows(keep)
+
 raw = list(csv.reader(open(os.path.join(EV, "prof_final_raw.csv"))))
 h, units = raw[0], raw[1]
 ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
