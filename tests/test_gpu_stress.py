@@ -161,3 +161,23 @@ def test_general_time_domain_search_is_bit_identical_across_launches(m0, bank):
     for rep in range(REPS // 3):
         r = m.sync_search(rx, 24, 1, n_trials)
         assert all(same(a, b) for a, b in zip(r, r0)), rep
+
+
+@pytest.mark.parametrize("nfft,cp,bps", [(512, 128, 4), (1024, 256, 6), (2048, 512, 2), (4096, 1024, 4), (64, 16, 6)])
+def test_output_selection_on_dense_grids_writes_identical_values(nfft, cp, bps):
+    """The dense receiver has two code forms for the optional outputs (csrc/kernels.cuh data_epilogue: the variant with
+    the eq switch compiled out, launched for N = 512..2048 when the equalised symbols are wanted, and the per-output bin
+    masks everywhere else): every output that both calls produce must be bit-identical, and nothing may be written
+    through a pointer that was not passed."""
+    ndb = int(0.9375 * nfft) // 4 * 4
+    m = make(dict(nfft=nfft, cp_len=cp, num_synch_bins=nfft - 2, num_data_bins=ndb, m0=1, d=3, bps=bps, snr=100, gate=0.5,
+                  noise_var=0.02))
+    nf = frames_for(nfft, 3)
+    bits, tx0, rx = build_batch(m, nf, 23)
+    full = {k: (None if v is None else v.clone()) for k, v in m.rx_frames(rx, nf).items()}
+    lean = m.rx_frames(rx, nf, want_eq=False)
+    assert lean["eq"] is None and same(lean["llr"], full["llr"]) and same(lean["hard"], full["hard"])
+    eq_only = m.rx_frames(rx, nf, want_llr=False, want_hard=False)
+    assert eq_only["llr"] is None and eq_only["hard"] is None and same(eq_only["eq"], full["eq"])
+    hard_only = m.rx_frames(rx, nf, want_eq=False, want_llr=False)
+    assert same(hard_only["hard"], full["hard"]) and same(hard_only["delay"], full["delay"]) and same(hard_only["peak"], full["peak"])
