@@ -51,8 +51,18 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
     return __ffma2_rn(cswap(a), make_float2(b.y, -b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }
+// (OFDM_F32X2_ADD=0: additions and subtractions as two scalar instructions each, multiplies packed -- an A/B of how the
+// two FP32 pipes share the work; B200: see DESIGN.md 3.11)
+#ifndef OFDM_F32X2_ADD
+#define OFDM_F32X2_ADD 1
+#endif
+#if OFDM_F32X2_ADD
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+#else
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 // a + s * b with a real s
 __device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return __ffma2_rn(b, make_float2(s, s), a); }
