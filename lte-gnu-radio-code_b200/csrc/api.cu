@@ -645,11 +645,11 @@ rx_sync_search_tdg_kernel(const DevParams P, const float2 *__restrict__ x, long 
 // a multiple of 8 is a whole number of chunks -- and slide from there.  One CTA = one block; grid = tiles of
 // PB - CP trials.  Specification: oracle/ofdm_oracle.py sync_search_time_domain (same numbers up to rounding).
 template <int LOG2NB>
-__global__ void __launch_bounds__(CfgRxF<LOG2NB>::T)
+__global__ void __launch_bounds__(CfgOs<LOG2NB>::T)
 rx_sync_search_os_kernel(const DevParams P, const float2 *__restrict__ x, long long n_samples, long long first_start,
                          long long n_trials, float *__restrict__ peak_out, int *__restrict__ delay_out,
                          const float2 *__restrict__ gos, int PB, int alias_all) {
-    using C = CfgRxF<LOG2NB>;
+    using C = CfgOs<LOG2NB>;
     constexpr int GROUPS = 1;
     OFDM_KERNEL_PROLOGUE_(GROUPS, false, false, false, false, 0)
     (void)total_groups; (void)gg;
@@ -1214,10 +1214,10 @@ int ofdm_rx_sync_search_cfo(ofdm_plan *pl, const float *d_time, int64_t n_sample
         const int N = pl->prm.nfft, CP = pl->prm.cp_len, A = (CP + 7) & ~7, NB = 1 << pl->os_log2nb;
         int T = 0, sbytes = 0;
         switch (pl->os_log2nb) {
-            case 9: T = CfgRxF<9>::T; sbytes = Smem<CfgRxF<9>, 1, false, false, false, false, 0>::BYTES; break;
-            case 10: T = CfgRxF<10>::T; sbytes = Smem<CfgRxF<10>, 1, false, false, false, false, 0>::BYTES; break;
-            case 11: T = CfgRxF<11>::T; sbytes = Smem<CfgRxF<11>, 1, false, false, false, false, 0>::BYTES; break;
-            default: T = CfgRxF<12>::T; sbytes = Smem<CfgRxF<12>, 1, false, false, false, false, 0>::BYTES; break;
+            case 9: T = CfgOs<9>::T; sbytes = Smem<CfgOs<9>, 1, false, false, false, false, 0>::BYTES; break;
+            case 10: T = CfgOs<10>::T; sbytes = Smem<CfgOs<10>, 1, false, false, false, false, 0>::BYTES; break;
+            case 11: T = CfgOs<11>::T; sbytes = Smem<CfgOs<11>, 1, false, false, false, false, 0>::BYTES; break;
+            default: T = CfgOs<12>::T; sbytes = Smem<CfgOs<12>, 1, false, false, false, false, 0>::BYTES; break;
         }
         int PB = (NB - N + 1) & ~7;
         if (PB > 8 * T) PB = 8 * T;

@@ -195,10 +195,17 @@ template <int LOG2N> struct PptTx {
 #ifndef OFDM_EXCH_SHFL_64
 #define OFDM_EXCH_SHFL_64 0
 #endif
+// (round 2, with the arithmetic on the packed pipe the address arithmetic of the XOR swizzles weighs more: padded layouts in the
+// receiver are now +1..3 % at almost every size -- sweep N=2048 0.746 / 0.830 / 0.770 -> 0.765 / 0.850 / 0.789, N=4096 QPSK 0.571 ->
+// 0.586, LTE 0.645 -> 0.637 ms -- and within +-1 % elsewhere; round 1 had measured 0..-1 %)
 #ifndef OFDM_RX_LAY_PAD
-#define OFDM_RX_LAY_PAD 0
+#define OFDM_RX_LAY_PAD 1
 #endif
 template <int LOG2N> using CfgRx = FftCfg<LOG2N, PptRx<LOG2N>::value, 0, OFDM_RX_LAY_PAD != 0>;
+// the overlap-save search (api.cu) keeps the unpadded buffers: its CTA must stay under half an SM's shared memory at NB = 4096
+template <int LOG2N>
+using CfgOs = FftCfg<LOG2N, (LOG2N <= 9 ? 8 : (LOG2N == 10 ? OFDM_PPT_RX_1024 : (LOG2N == 11 ? OFDM_PPT_RX_2048 : OFDM_PPT_RX_4096))),
+                     (LOG2N >= 10 ? 2 : 0), false>;
 
 // The fused framed receiver (rx_frames_kernel) has its own knobs, because it is the one kernel that
 // keeps per-frame state (the equaliser gains) alive across symbols:

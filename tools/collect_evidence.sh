@@ -14,9 +14,11 @@ python tools/prof_cases.py n64 lte n4096 > $O/prof_plain.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:"rx_frames_kernel|tx_kernel|tx_wide_kernel" -s 2 -c 18 -o $O/prof_final -f \
       python tools/prof_cases.py n64 lte n4096 > $O/prof_ncu.log 2>&1
 # acquisition kernels: N-tap kernel (N=64), overlap-save (LTE), general form (two synch symbols; hypothesis bank)
+if [ -z "${SKIP_SYNC_NCU:-}" ]; then
 python tools/bench_sync.py n64_utsa_stride1 lte_stride1 n64_m2_stride1 lte_bank3_stride1 --no-cpu > $O/prof_sync_plain.log 2>&1 && \
   ncu --set full --clock-control none -k regex:"rx_sync_search_(td8|os|tdg)" -c 40 -o $O/prof_sync -f \
       python tools/bench_sync.py n64_utsa_stride1 lte_stride1 n64_m2_stride1 lte_bank3_stride1 --no-cpu > $O/prof_sync_ncu.log 2>&1
+fi
 # gpurun brings back at most 64 MiB: keep the raw pages (what tools/publish_evidence.py reads) and drop the reports
 for rep in prof_final prof_sync; do
   if [ -f $O/$rep.ncu-rep ]; then
