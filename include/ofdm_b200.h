@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OFDM_B200_ABI_VERSION 4
+#define OFDM_B200_ABI_VERSION 5
 
 enum {
     OFDM_OK = 0,
@@ -224,7 +224,8 @@ int ofdm_tx_modulate_host(ofdm_plan *plan, const uint8_t *h_bits, float *h_time,
  *   mode 1 = gr-RXOFDM synch_and_chan_est: stride cp_len-1, every acceptable lock (up to 100), the first data symbol
  *            after each lock with that lock's row.
  * The counter reset at the end of work() (:261 / :265) is applied; what the block writes to its output stream (and
- * the "nothing on the first call" rule, :257) stays with the caller, which owns the output buffer. */
+ * the "nothing on the first call" rule, :257) stays with the caller, which owns the output buffer -- for HOST buffers;
+ * ofdm_rx_block_work_device below writes the stream too. */
 typedef struct ofdm_rx_block ofdm_rx_block;
 typedef struct {
     int32_t n_new_locks;            /* locks accepted by this call */
@@ -241,6 +242,32 @@ typedef struct {
 int ofdm_rx_block_create(ofdm_plan *plan, int32_t mode, int32_t rows, ofdm_rx_block **block_out);
 int ofdm_rx_block_destroy(ofdm_rx_block *block);
 int ofdm_rx_block_work(ofdm_rx_block *block, const float *h_in, int64_t n_samples, ofdm_rx_block_result *result);
+/* The same call for a block whose scheduler buffers already live in DEVICE memory -- what a GNU Radio 3.10 block built on
+ * custom (device) buffers is handed by the scheduler instead of host views (the boundary of
+ * GRR/gr-RXOFDM/python/synch_and_chan_est.py:121-124,:140-142 and GRR/gr-utsa_ofdm/python/SynchAndChanEst.py:135-137).
+ * d_in (n_samples complex64, n_samples >= 1, 8-byte aligned) is read in place: no staging copy, no host-to-device copy.
+ * Work queued on `stream` before the call (the upstream block's kernel, the previous reader of the output buffers) is
+ * ordered before the block's own stream; the call returns after its one synchronisation, so d_in may be reused and the
+ * outputs read on any stream afterwards.
+ *   d_rows (nullable, 16-byte aligned, ofdm_rx_block_max_rows() x num_data_bins complex64): receives the equalised data
+ *     rows of this call's list, in list order; without it they go to a device buffer of the block's.  Either way
+ *     result->data_freq is a DEVICE pointer after this call.  Everything else in `result` is host memory as above.
+ *   est_data_freq (SynchAndChanEst.py:93 / synch_and_chan_est.py:97), from which the reference packs its output stream
+ *     and whose rows persist from call to call, is kept in device memory by this entry point (rows listed by
+ *     ofdm_rx_block_work calls go to the caller's host mirror instead and are not seen by it).
+ *   d_stream_out (nullable, 8-byte aligned, out_capacity complex64): the block's output stream, out[0:m] of
+ *     SynchAndChanEst.py:249-259 (mode 0: the rows np.delete(est_data_freq, range(3, rows, M0+D)) keeps, laid end to end)
+ *     and synch_and_chan_est.py:252-263 (mode 1: est_data_freq[0:corr_size]).  pack_rows = how many packed rows the
+ *     stream has: n_data_symb of SynchAndChanEst.py:138 in mode 0, corr_size of synch_and_chan_est.py:253 in mode 1 --
+ *     one line of arithmetic on the caller's constructor arguments; it is clamped to the rows that exist.
+ *     *n_written (nullable) = m = min(out_capacity, packed rows x num_data_bins).  The reference writes nothing on its
+ *     first call (:257 / :261): the caller passes d_stream_out = NULL then.
+ * State (lock counter, time_synch_ref, est_chan_freq_P) is shared with ofdm_rx_block_work: the two calls may be mixed. */
+int ofdm_rx_block_work_device(ofdm_rx_block *block, const float *d_in, int64_t n_samples, float *d_rows,
+                              float *d_stream_out, int64_t pack_rows, int64_t out_capacity, void *stream,
+                              ofdm_rx_block_result *result, int64_t *n_written);
+/* rows a call can list at most: `rows` in mode 0, 100 in mode 1 (the size of d_rows above and of result->demod_rows) */
+int ofdm_rx_block_max_rows(const ofdm_rx_block *block);
 /* est_chan_freq_P: copies the first `rows` channel rows (nfft complex64 each) to h_H. */
 int ofdm_rx_block_chan_freq(ofdm_rx_block *block, float *h_H, int32_t rows);
 

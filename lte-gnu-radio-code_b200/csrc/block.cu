@@ -183,6 +183,42 @@ block_control_kernel(const BlockGeom g, const CtlLayout lay, const float *__rest
     }
 }
 
+// ---- the block's output stream on device buffers -------------------------------------------------------------------
+// est_data_freq (SynchAndChanEst.py:93 / synch_and_chan_est.py:97) is block state: rows a call does not list keep what
+// an earlier call left there, and the output stream is packed from the whole array.  For device buffers the array
+// lives in device memory: this call's rows (list order) are scattered to their rows ...
+__global__ void __launch_bounds__(64)
+block_scatter_kernel(const unsigned char *__restrict__ ctl, const CtlLayout lay, const float2 *__restrict__ rows,
+                     float2 *__restrict__ edf, int ndb) {
+    const int i = blockIdx.x;
+    if (i >= reinterpret_cast<const CtlHeader *>(ctl)->n_demod) return;
+    const int r = reinterpret_cast<const int *>(ctl + lay.dm_row)[i];
+    for (int b = threadIdx.x; b < ndb; b += blockDim.x) edf[(size_t)r * ndb + b] = rows[(size_t)i * ndb + b];
+}
+
+// ... and the stream is the first n_elems values of the kept rows laid end to end: every row in mode 1
+// (est_data_freq[0:corr_size], synch_and_chan_est.py:252-254), the rows np.delete(.., range(3, rows, M0+D)) leaves in
+// mode 0 (SynchAndChanEst.py:249-250 -- the deleted rows start at 3 whatever M0 is; reproduced).
+__device__ __forceinline__ long long kept_row(long long k, int mode, int fsyms) {
+    if (mode == 1 || k < 3) return k;
+    const long long q = (k - 3) / (fsyms - 1), rem = (k - 3) - q * (fsyms - 1);       // fsyms >= 2 here (checked on the host)
+    return 3 + q * fsyms + 1 + rem;
+}
+__global__ void __launch_bounds__(256)
+block_pack_kernel(const float2 *__restrict__ edf, float2 *__restrict__ out, long long n_elems, int ndb, int mode, int fsyms) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += (long long)gridDim.x * blockDim.x) {
+        const long long k = e / ndb;
+        out[e] = edf[kept_row(k, mode, fsyms) * ndb + (e - k * ndb)];
+    }
+}
+
+// rows the packed stream can have at most
+long long kept_rows_total(const BlockGeom &g, int h_rows) {
+    if (g.mode == 1) return h_rows;
+    const long long deleted = g.rows > 3 ? (g.rows - 3 + g.fsyms - 1) / g.fsyms : 0;   // len(range(3, rows, M0+D))
+    return g.rows - deleted;
+}
+
 }  // namespace
 
 struct ofdm_rx_block {
@@ -190,13 +226,16 @@ struct ofdm_rx_block {
     BlockGeom g;
     CtlLayout lay;
     cudaStream_t st;
+    cudaEvent_t ev;            // orders a caller's stream before the block's (device-buffer entry point)
     unsigned char *d_ctl;      // control block, device copy (persistent state + this call's lists)
     float2 *d_H;               // est_chan_freq_P: max_lock rows of nfft (utsa: `rows` rows)
     int h_rows;
     float2 *d_x;               // the call's samples
     float *d_peak;
     int *d_delay;
-    long long cap_samples, cap_trials;
+    float2 *d_eq;              // device-buffer calls: this call's equalised rows in list order (when the caller gives none)
+    float2 *d_edf;             // device-buffer calls: est_data_freq, h_rows x num_data_bins, persistent
+    long long cap_samples, cap_trial_samples;
     // pinned (mapped) host memory
     float2 *p_in;              // staging for the samples
     unsigned char *p_ctl;      // host copy of the control block
@@ -207,11 +246,14 @@ struct ofdm_rx_block {
 static void block_free(ofdm_rx_block *b) {
     if (!b) return;
     if (b->st) cudaStreamDestroy(b->st);
+    if (b->ev) cudaEventDestroy(b->ev);
     cudaFree(b->d_ctl);
     cudaFree(b->d_H);
     cudaFree(b->d_x);
     cudaFree(b->d_peak);
     cudaFree(b->d_delay);
+    cudaFree(b->d_eq);
+    cudaFree(b->d_edf);
     cudaFreeHost(b->p_in);
     cudaFreeHost(b->p_ctl);
     cudaFreeHost(b->p_aux);
@@ -219,23 +261,31 @@ static void block_free(ofdm_rx_block *b) {
     delete b;
 }
 
-static int block_reserve(ofdm_rx_block *b, long long n) {
-    if (n <= b->cap_samples) return OFDM_OK;
-    long long cap = b->cap_samples ? b->cap_samples : 8192;
-    while (cap < n) cap *= 2;
-    const long long trials = cap / b->g.stride + 2;
-    cudaFree(b->d_x);
-    cudaFree(b->d_peak);
-    cudaFree(b->d_delay);
-    cudaFreeHost(b->p_in);
-    b->d_x = nullptr, b->d_peak = nullptr, b->d_delay = nullptr, b->p_in = nullptr;
-    b->cap_samples = b->cap_trials = 0;
-    CU(cudaMalloc(&b->d_x, (size_t)cap * sizeof(float2)), "ofdm_rx_block(cudaMalloc)");
-    CU(cudaMalloc(&b->d_peak, (size_t)trials * sizeof(float)), "ofdm_rx_block(cudaMalloc)");
-    CU(cudaMalloc(&b->d_delay, (size_t)trials * sizeof(int)), "ofdm_rx_block(cudaMalloc)");
-    CU(cudaHostAlloc(&b->p_in, (size_t)cap * sizeof(float2), cudaHostAllocDefault), "ofdm_rx_block(cudaHostAlloc)");
-    b->cap_samples = cap;
-    b->cap_trials = trials;
+// Buffers sized by the call: the search's per-trial results (always) and, for host input only, the sample staging pair.
+static int block_reserve(ofdm_rx_block *b, long long n, bool staging) {
+    if (n > b->cap_trial_samples) {
+        long long cap = b->cap_trial_samples ? b->cap_trial_samples : 8192;
+        while (cap < n) cap *= 2;
+        const long long trials = cap / b->g.stride + 2;
+        cudaFree(b->d_peak);
+        cudaFree(b->d_delay);
+        b->d_peak = nullptr, b->d_delay = nullptr;
+        b->cap_trial_samples = 0;
+        CU(cudaMalloc(&b->d_peak, (size_t)trials * sizeof(float)), "ofdm_rx_block(cudaMalloc)");
+        CU(cudaMalloc(&b->d_delay, (size_t)trials * sizeof(int)), "ofdm_rx_block(cudaMalloc)");
+        b->cap_trial_samples = cap;
+    }
+    if (staging && n > b->cap_samples) {
+        long long cap = b->cap_samples ? b->cap_samples : 8192;
+        while (cap < n) cap *= 2;
+        cudaFree(b->d_x);
+        cudaFreeHost(b->p_in);
+        b->d_x = nullptr, b->p_in = nullptr;
+        b->cap_samples = 0;
+        CU(cudaMalloc(&b->d_x, (size_t)cap * sizeof(float2)), "ofdm_rx_block(cudaMalloc)");
+        CU(cudaHostAlloc(&b->p_in, (size_t)cap * sizeof(float2), cudaHostAllocDefault), "ofdm_rx_block(cudaHostAlloc)");
+        b->cap_samples = cap;
+    }
     return OFDM_OK;
 }
 
@@ -291,13 +341,36 @@ int ofdm_rx_block_destroy(ofdm_rx_block *b) {
     return OFDM_OK;
 }
 
-int ofdm_rx_block_work(ofdm_rx_block *b, const float *h_in, int64_t n, ofdm_rx_block_result *res) {
-    if (!b || !res || n < 0 || (n > 0 && !h_in)) return fail(OFDM_EINVAL, "ofdm_rx_block_work: bad argument%s");
+// The body both entry points share.  h_in: host samples, staged and uploaded (d_in == nullptr; the equalised rows go
+// to the block's mapped pinned rows), or d_in: samples that already live in device memory and are read in place; then
+// the rows stay in device memory (d_rows, or a buffer of the block's), est_data_freq is kept there as well, and
+// d_stream (nullable) receives the block's output stream.
+static int block_work(ofdm_rx_block *b, const float *h_in, const float *d_in, int64_t n, float *d_rows, float *d_stream,
+                      int64_t pack_rows, int64_t out_capacity, void *caller_stream, ofdm_rx_block_result *res,
+                      int64_t *n_written) {
     ofdm_plan *pl = b->pl;
     DevGuard dev_guard(pl);
     const BlockGeom &g = b->g;
-    int rc = block_reserve(b, n > 0 ? n : 1);
+    const int ndb = pl->dev.ndd;
+    int rc = block_reserve(b, n > 0 ? n : 1, d_in == nullptr);
     if (rc) return rc;
+    const float2 *x = d_in ? reinterpret_cast<const float2 *>(d_in) : b->d_x;
+    float2 *eq_rows = b->p_eq;
+    if (d_in) {
+        if (!b->d_edf) {
+            const size_t bytes = (size_t)b->h_rows * ndb * sizeof(float2);
+            CU(cudaMalloc(&b->d_edf, bytes), "ofdm_rx_block_work_device(cudaMalloc)");
+            CU(cudaMemsetAsync(b->d_edf, 0, bytes, b->st), "ofdm_rx_block_work_device(memset)");   // np.zeros, :93 / :97
+        }
+        if (!d_rows && !b->d_eq)
+            CU(cudaMalloc(&b->d_eq, (size_t)g.max_sym * ndb * sizeof(float2)), "ofdm_rx_block_work_device(cudaMalloc)");
+        eq_rows = d_rows ? reinterpret_cast<float2 *>(d_rows) : b->d_eq;
+        // whatever the caller queued on its stream (the upstream block's kernel writing d_in, the previous consumer of
+        // d_out) comes first
+        if (!b->ev) CU(cudaEventCreateWithFlags(&b->ev, cudaEventDisableTiming), "ofdm_rx_block_work_device(event)");
+        CU(cudaEventRecord(b->ev, (cudaStream_t)caller_stream), "ofdm_rx_block_work_device(record)");
+        CU(cudaStreamWaitEvent(b->st, b->ev, 0), "ofdm_rx_block_work_device(wait)");
+    }
     // trials P = 0.. that pass the window guard M0*L + P*stride + N + CP < n  (SynchAndChanEst.py:139,:144)
     long long nv = 0;
     {
@@ -308,12 +381,12 @@ int ofdm_rx_block_work(ofdm_rx_block *b, const float *h_in, int64_t n, ofdm_rx_b
             if (nv > n_trials) nv = n_trials;
         }
     }
-    if (n > 0) {
+    if (n > 0 && !d_in) {
         memcpy(b->p_in, h_in, (size_t)n * sizeof(float2));
         CU(cudaMemcpyAsync(b->d_x, b->p_in, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, b->st), "ofdm_rx_block_work(H2D)");
     }
     if (nv > 0) {
-        rc = ofdm_rx_sync_search(pl, (const float *)b->d_x, n, g.CP, g.stride, nv, b->d_peak, b->d_delay, b->st);
+        rc = ofdm_rx_sync_search(pl, (const float *)x, n, g.CP, g.stride, nv, b->d_peak, b->d_delay, b->st);
         if (rc) return rc;
     }
     block_control_kernel<<<1, 256, 0, b->st>>>(g, b->lay, b->d_peak, b->d_delay, (int)nv, (long long)n, b->d_ctl);
@@ -322,17 +395,39 @@ int ofdm_rx_block_work(ofdm_rx_block *b, const float *h_in, int64_t n, ofdm_rx_b
     const int *d_n_new = &reinterpret_cast<const CtlHeader *>(b->d_ctl)->n_new;
     const int *d_n_dm = &reinterpret_cast<const CtlHeader *>(b->d_ctl)->n_demod;
     float2 *aux = b->p_aux;                                  // mapped: the device writes host memory directly (UVA)
-    CU(pl->ks->chanest(pl->dev, b->d_x, n, reinterpret_cast<const long long *>(b->d_ctl + b->lay.new_pos),
+    CU(pl->ks->chanest(pl->dev, x, n, reinterpret_cast<const long long *>(b->d_ctl + b->lay.new_pos),
                        reinterpret_cast<const int *>(b->d_ctl + b->lay.new_delay), nullptr, g.max_lock, b->d_H, aux,
                        aux + (size_t)g.max_lock * g.N, b->st, pl->sms,
                        reinterpret_cast<const int *>(b->d_ctl + b->lay.new_row), d_n_new),
        "ofdm_rx_block_work(chanest)");
-    CU(pl->ks->rx_demod(pl->dev, b->d_x, n, reinterpret_cast<const long long *>(b->d_ctl + b->lay.dm_start),
+    CU(pl->ks->rx_demod(pl->dev, x, n, reinterpret_cast<const long long *>(b->d_ctl + b->lay.dm_start),
                         reinterpret_cast<const int *>(b->d_ctl + b->lay.dm_delay),
-                        reinterpret_cast<const int *>(b->d_ctl + b->lay.dm_hrow), nullptr, b->d_H, g.max_sym, b->p_eq, nullptr,
+                        reinterpret_cast<const int *>(b->d_ctl + b->lay.dm_hrow), nullptr, b->d_H, g.max_sym, eq_rows, nullptr,
                         nullptr, b->st, pl->sms, d_n_dm),
        "ofdm_rx_block_work(demod)");
     CU(cudaMemcpyAsync(b->p_ctl, b->d_ctl, b->lay.bytes, cudaMemcpyDeviceToHost, b->st), "ofdm_rx_block_work(D2H)");
+    if (d_in) {
+        block_scatter_kernel<<<g.max_sym, 64, 0, b->st>>>(b->d_ctl, b->lay, eq_rows, b->d_edf, ndb);
+        count_launch();
+        CU(cudaGetLastError(), "ofdm_rx_block_work_device(scatter)");
+        long long n_elems = 0;
+        if (d_stream) {
+            // data_out[0:m], m = min(len(out), data_out.size): SynchAndChanEst.py:250-259 / synch_and_chan_est.py:253-263
+            long long k = pack_rows < 0 ? 0 : pack_rows;
+            const long long have = kept_rows_total(g, b->h_rows);
+            if (k > have) k = have;
+            n_elems = k * ndb;
+            if (n_elems > out_capacity) n_elems = out_capacity;
+            if (n_elems > 0) {
+                const int grid = (int)((n_elems + 255) / 256 < 4 * pl->sms ? (n_elems + 255) / 256 : 4 * pl->sms);
+                block_pack_kernel<<<grid, 256, 0, b->st>>>(b->d_edf, reinterpret_cast<float2 *>(d_stream), n_elems, ndb,
+                                                           g.mode, g.fsyms);
+                count_launch();
+                CU(cudaGetLastError(), "ofdm_rx_block_work_device(pack)");
+            }
+        }
+        if (n_written) *n_written = n_elems;
+    }
     CU(cudaStreamSynchronize(b->st), "ofdm_rx_block_work(sync)");
     const CtlHeader *hd = reinterpret_cast<const CtlHeader *>(b->p_ctl);
     res->n_new_locks = hd->n_new;
@@ -344,9 +439,25 @@ int ofdm_rx_block_work(ofdm_rx_block *b, const float *h_in, int64_t n, ofdm_rx_b
     res->chan_time = reinterpret_cast<const float *>(b->p_aux);
     res->synch_freq = reinterpret_cast<const float *>(b->p_aux + (size_t)g.max_lock * g.N);
     res->demod_rows = reinterpret_cast<const int32_t *>(b->p_ctl + b->lay.dm_row);
-    res->data_freq = reinterpret_cast<const float *>(b->p_eq);
+    res->data_freq = reinterpret_cast<const float *>(eq_rows);
     return OFDM_OK;
 }
+
+int ofdm_rx_block_work(ofdm_rx_block *b, const float *h_in, int64_t n, ofdm_rx_block_result *res) {
+    if (!b || !res || n < 0 || (n > 0 && !h_in)) return fail(OFDM_EINVAL, "ofdm_rx_block_work: bad argument%s");
+    return block_work(b, h_in, nullptr, n, nullptr, nullptr, 0, 0, nullptr, res, nullptr);
+}
+
+int ofdm_rx_block_work_device(ofdm_rx_block *b, const float *d_in, int64_t n, float *d_rows, float *d_stream_out,
+                              int64_t pack_rows, int64_t out_capacity, void *stream, ofdm_rx_block_result *res,
+                              int64_t *n_written) {
+    if (!b || !res || n < 1 || !d_in || (d_stream_out && (pack_rows < 0 || out_capacity < 0)))
+        return fail(OFDM_EINVAL, "ofdm_rx_block_work_device: bad argument%s");
+    if (n_written) *n_written = 0;
+    return block_work(b, nullptr, d_in, n, d_rows, d_stream_out, pack_rows, out_capacity, stream, res, n_written);
+}
+
+int ofdm_rx_block_max_rows(const ofdm_rx_block *b) { return b ? b->g.max_sym : OFDM_EINVAL; }
 
 int ofdm_rx_block_chan_freq(ofdm_rx_block *b, float *h_H, int32_t rows) {
     if (!b || !h_H || rows < 0 || rows > b->h_rows) return fail(OFDM_EINVAL, "ofdm_rx_block_chan_freq: bad argument%s");

@@ -62,6 +62,9 @@ SIGNATURES = {
     "ofdm_rx_block_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "ofdm_rx_block_destroy": (C.c_int, [_P]),
     "ofdm_rx_block_work": (C.c_int, [_P, _P, _I64, C.POINTER(RxBlockResult)]),
+    "ofdm_rx_block_work_device": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _I64, _P, C.POINTER(RxBlockResult),
+                                           C.POINTER(_I64)]),
+    "ofdm_rx_block_max_rows": (C.c_int, [_P]),
     "ofdm_rx_block_chan_freq": (C.c_int, [_P, _P, C.c_int32]),
 }
 
@@ -85,7 +88,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.ofdm_abi_version() != 4:
+        if l.ofdm_abi_version() != 5:
             raise OfdmError("libofdm_b200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -114,6 +114,81 @@ class RxBlockBase(gr.sync_block):
             self.est_data_freq[dm_rows[:k]] = eq[:k]
         return r
 
+    # ---- device-buffer form of work() (additive) --------------------------------------------
+    def work_device(self, rx, out=None):
+        """work() for a block whose scheduler buffers already live in device memory -- what a GNU Radio 3.10 block
+        built on custom (device) buffers is handed instead of the host views of
+        GRR/gr-RXOFDM/python/synch_and_chan_est.py:121-124,:140-142.  One C-ABI call (ofdm_rx_block_work_device): the
+        samples are read in place, nothing is staged or uploaded, the equalised data rows and est_data_freq stay in
+        device memory, and the output stream is packed there.
+
+        rx: complex64 CUDA tensor [n] on the block's device.  Loops A and B, the lock rule and the block's state
+        (lock counter, time_synch_ref, est_chan_freq_P, est_chan_time, est_synch_freq) behave exactly as in work(),
+        with which it may be mixed.  out (optional): complex64 CUDA tensor [m], the output buffer of work(): receives
+        out[0:last_written] exactly as work() would write it -- nothing on the block's first call, then the packed rows
+        of est_data_freq (SynchAndChanEst.py:249-259 / synch_and_chan_est.py:252-263), where est_data_freq is the
+        device-resident copy that work_device calls maintain.  Returns (rows, eq): eq is a CUDA tensor
+        [n_demod, num_data_bins] -- a view of a buffer the block owns, valid until its next call -- and rows (NumPy
+        int32 [n_demod]) names the est_data_freq row each one is.  The HOST mirror est_data_freq is not refreshed (that
+        copy is what this entry point saves)."""
+        torch = self._torch
+        if not self._blk:
+            raise _lib.OfdmError("work_device needs the one-call block path (fused=True)")
+        if not (torch.is_tensor(rx) and rx.is_cuda and rx.dtype == torch.complex64 and rx.dim() == 1 and rx.is_contiguous()):
+            raise ValueError("work_device expects a contiguous 1-D complex64 CUDA tensor")
+        if rx.device != self.modem.device:
+            raise ValueError("input lives on %s, the block on %s" % (rx.device, self.modem.device))
+        c = self.cfg
+        if rx.numel() == 0:
+            return np.zeros(0, np.int32), torch.empty((0, c.num_data_bins), dtype=torch.complex64, device=rx.device)
+        if getattr(self, "_d_eq", None) is None:
+            max_rows = _lib.lib().ofdm_rx_block_max_rows(self._blk)
+            self._d_eq = torch.empty((max_rows, c.num_data_bins), dtype=torch.complex64, device=self.modem.device)
+        r = self._res
+        d_stream, cap, pack_rows = None, 0, 0
+        if out is not None:
+            if not (torch.is_tensor(out) and out.is_cuda and out.dtype == torch.complex64 and out.dim() == 1
+                    and out.is_contiguous() and out.device == self.modem.device):
+                raise ValueError("work_device expects `out` as a contiguous 1-D complex64 CUDA tensor on the block's device")
+            self.last_written = 0
+            if self.count > 0 and out.numel() > 0:           # nothing on the first call (:257 / :261)
+                d_stream, cap = out.data_ptr(), out.numel()
+                if self.compat == "utsa":                    # n_data_symb, SynchAndChanEst.py:136-138
+                    pack_rows = int((rx.numel() // c.sym_len) * (c.d / c.frame_syms))
+                else:                                        # corr_size, synch_and_chan_est.py:253 (made integral)
+                    pack_rows = min(int(self.num_ofdm_symb / c.frame_syms), self.rows)
+        n_written = C.c_int64(0)
+        with torch.cuda.device(self.modem.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().ofdm_rx_block_work_device(self._blk, rx.data_ptr(), rx.numel(), self._d_eq.data_ptr(),
+                                                            d_stream, pack_rows, cap, st, self._res_ref,
+                                                            C.byref(n_written)))
+        if out is not None:
+            self.last_written = int(n_written.value)
+        ml, ms = (1, self.rows) if self.compat == "utsa" else (100, 100)
+        as_arr = np.ctypeslib.as_array
+        if getattr(self, "_views_dev", None) is None:
+            # host-side result pointers address pinned memory owned by the block object and never move
+            self._views_dev = (as_arr(r.new_rows, (ml,)), as_arr(r.chan_time, (ml, 2 * c.nfft)).view(np.complex64),
+                               as_arr(r.synch_freq, (ml, 2 * c.mm)).view(np.complex64), as_arr(r.demod_rows, (ms,)),
+                               as_arr(r.time_synch_ref, (r.n_state_rows, 3)))
+        new_rows, ht, se, dm_rows, self._tsr_view = self._views_dev
+        k = r.n_new_locks
+        if k:
+            self.est_chan_time[new_rows[:k]] = ht[:k]
+            self.est_synch_freq[new_rows[:k]] = se[:k]
+            self._last_chan_time = ht[:k]
+        if self.compat == "utsa":
+            self.time_synch_ref[:] = self._tsr_view[0]
+            self.corr_obs = 0                                # SynchAndChanEst.py:261
+        else:
+            k = r.obs_after_search + 1
+            if k > 0:
+                self.time_synch_ref[:k] = self._tsr_view[:k]
+            self.cor_obs = 0                                 # synch_and_chan_est.py:265
+        self.count += 1
+        return dm_rows[:r.n_demod].copy(), self._d_eq[:r.n_demod]
+
     def _upload(self, in0):
         torch = self._torch
         a = np.ascontiguousarray(in0, dtype=np.complex64)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.SIGNATURES) == set(names)
     lib.ofdm_abi_version.restype = ctypes.c_int
     want = int(re.search(r"#define\s+OFDM_B200_ABI_VERSION\s+(\d+)", open(HEADER).read()).group(1))
-    assert lib.ofdm_abi_version() == want == 4
+    assert lib.ofdm_abi_version() == want == 5
 
 
 def test_block_result_struct_matches_header():

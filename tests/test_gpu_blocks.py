@@ -337,3 +337,77 @@ def test_carry_over_streaming_is_chunk_invariant(variant):
         blk.work([rx[at:at + 1000]], [out])
         seen += blk.last_written // 60
     assert seen < nf * 3
+
+
+@pytest.mark.parametrize("variant", ["utsa", "rxofdm"])
+def test_device_buffer_work_equals_host_work(golden, variant):
+    """SURVEY.md 8f rank 3, the device-buffer half: ofdm_rx_block_work_device reads the scheduler's samples where they
+    already are (a GNU Radio custom buffer in device memory) and leaves the equalised rows in device memory.  Same
+    capture through work() on one instance and through work_device() on another: lock record, state rows, channel
+    estimates and every equalised row identical bit for bit over two calls (cross-call state included); then both
+    instances take a host call -- the two entry points share their state and may be mixed.  The device copy starts one
+    sample into its allocation (8-byte alignment is all the entry point asks for) and is produced by a kernel still in
+    flight on the caller's stream, which the call has to order before its own."""
+    import RXOFDM
+    import utsa_ofdm
+    from oracle.blocks_oracle import UtsaBlockOracle as UO, RxofdmBlockOracle as RO
+    rx = golden["rx_offline"][0].astype(np.complex64)
+
+    def make_block():
+        if variant == "utsa":
+            return utsa_ofdm.SynchAndChanEst(240, 64, 16, 62, [1, 3], 60, 100, 0.7, "/tmp/", "cest.pckl", 0, 0)
+        return RXOFDM.synch_and_chan_est(24, 64, 16, 62, [1, 3], 60, 100, "/tmp/", "o", 0, 0, zc_root=23)
+    host, dev = make_block(), make_block()
+    ora = UO(240, 64, 16, 62, [1, 3], 60, 100, 0.7) if variant == "utsa" else RO(24, 64, 16, 62, [1, 3], 60, 100, zc_root=23)
+    out_h, out_d, out_o = (np.zeros(len(rx), np.complex64) for _ in range(3))
+    store = torch.empty(len(rx) + 1, dtype=torch.complex64, device="cuda")
+    store[1:] = torch.from_numpy(rx).cuda()
+    for call in range(2):
+        host.work([rx], [out_h])
+        ora.work(rx, out_o)
+        d_in = torch.empty(len(rx) + 1, dtype=torch.complex64, device="cuda")[1:]
+        d_in.copy_(store[1:])                                        # a device-side copy queued right before the call
+        d_stream = torch.full((len(rx),), 7 + 7j, dtype=torch.complex64, device="cuda")
+        rows, eq = dev.work_device(d_in, out=d_stream)
+        assert eq.is_cuda and eq.shape == (len(rows), 60)
+        # the output stream, packed on the device from the device-resident est_data_freq: what work() wrote, bit for bit,
+        # nothing on the first call, nothing past last_written
+        lw = host.last_written
+        assert dev.last_written == lw and (lw > 0) == (call > 0)
+        got_stream = d_stream.cpu().numpy()
+        assert np.array_equal(got_stream[:lw], out_h[:lw]) and np.all(got_stream[lw:] == 7 + 7j)
+        if lw:                                               # a short output buffer cuts the stream mid-row (m = len(out))
+            d_short = torch.zeros(lw - 61, dtype=torch.complex64, device="cuda")
+            probe = make_block()
+            probe.work_device(d_in)
+            probe.work_device(d_in, out=d_short)
+            assert probe.last_written == lw - 61 and np.array_equal(d_short.cpu().numpy(), out_h[:lw - 61])
+            probe.close()
+        assert np.array_equal(np.asarray(host.time_synch_ref), np.asarray(dev.time_synch_ref)), call
+        assert np.array_equal(np.asarray(dev.time_synch_ref), np.asarray(ora.time_synch_ref)), call
+        assert np.array_equal(rows, host._views[3][:host._res.n_demod])
+        assert len(rows) > 0 and len(rows) % 3 == 0                 # whole frames of D = 3 data symbols
+        assert np.array_equal(eq.cpu().numpy(), host.est_data_freq[rows].astype(np.complex64))
+        assert rel_err(eq.cpu().numpy(), ora.est_data_freq[rows]) < 1e-4
+        assert np.array_equal(host.est_chan_freq_P, dev.est_chan_freq_P)
+        assert np.array_equal(host.est_chan_time, dev.est_chan_time)
+        assert np.array_equal(host.est_synch_freq, dev.est_synch_freq)
+    host.work([rx], [out_h])
+    dev.work([rx], [out_d])
+    assert host.last_written == dev.last_written > 0
+    assert np.array_equal(np.asarray(host.time_synch_ref), np.asarray(dev.time_synch_ref))
+    rows3 = host._views[3][:host._res.n_demod]
+    assert np.array_equal(rows3, dev._views[3][:dev._res.n_demod])
+    assert np.array_equal(host.est_data_freq[rows3], dev.est_data_freq[rows3])     # work_device leaves the host mirror alone
+    if variant == "utsa":               # the listed rows are the first rows of the packed stream there; the rows after
+        m = len(rows3) * 60             # them are leftovers of call 1 in the HOST mirror, which work_device does not keep
+        assert m > 0 and np.array_equal(out_h[:m], out_d[:m])
+    # argument checks: host arrays and tensors of another type are refused, an empty buffer is a no-op
+    with pytest.raises(ValueError):
+        dev.work_device(rx)
+    with pytest.raises(ValueError):
+        dev.work_device(store.real)
+    rows, eq = dev.work_device(store[:0])
+    assert len(rows) == 0 and eq.shape == (0, 60)
+    host.close()
+    dev.close()
