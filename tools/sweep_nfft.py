@@ -1,5 +1,6 @@
 """BASELINE config 5: NFFT sweep 64..4096 x QPSK/16-QAM/64-QAM, soft-LLR demap on, throughput vs the
-HBM roofline.  CP = N/4 (reference convention, SDRScript.py:96-97), ndb = 0.9375*N rounded to a multiple
+HBM roofline.  CP = N/4 (reference convention, SDRScript.py:96-97) or, with the argument `lte`, the LTE normal-CP
+ratio 9N/128 rounded to the nearest sample (SURVEY.md 8d config 5 names both); ndb = 0.9375*N rounded to a multiple
 of 4 (SDRScript.py:57-58), frames of 1 synch + 3 data symbols, ~1 GiB of input samples per point."""
 import json
 import os
@@ -20,11 +21,12 @@ PEAK = 6542.7
 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 
+CP_LTE = len(sys.argv) > 1 and sys.argv[1] == "lte"
 rows = []
 for n in (64, 128, 256, 512, 1024, 2048, 4096):
     for bps in (2, 4, 6):
         ndb = int(0.9375 * n) // 4 * 4
-        cfg = ModemConfig(nfft=n, cp_len=n // 4, num_synch_bins=n - 2, num_data_bins=ndb, m0=1, d=3, bps=bps, snr=100,
+        cfg = ModemConfig(nfft=n, cp_len=(9 * n + 64) // 128 if CP_LTE else n // 4, num_synch_bins=n - 2, num_data_bins=ndb, m0=1, d=3, bps=bps, snr=100,
                           gate=0.5, noise_var=0.01)
         nf = (1 << 27) // cfg.frame_len                      # 2^27 samples = 1 GiB of complex64
         m = Modem(cfg)
@@ -42,7 +44,7 @@ for n in (64, 128, 256, 512, 1024, 2048, 4096):
         nsym = nf * cfg.d
         rx_b = nf * cfg.frame_len * 8 + nsym * ndb * (8 + 4 * bps) + nsym * cfg.hard_stride + nf * 9
         tx_b = nsym * cfg.hard_stride + nf * cfg.frame_len * 8
-        r = dict(nfft=n, bps=bps, ndb=ndb, frames=nf, rx_ms=t_rx, rx_GBs=rx_b / t_rx / 1e6, rx_frac=rx_b / t_rx / 1e6 / PEAK,
+        r = dict(nfft=n, cp_len=cfg.cp_len, bps=bps, ndb=ndb, frames=nf, rx_ms=t_rx, rx_GBs=rx_b / t_rx / 1e6, rx_frac=rx_b / t_rx / 1e6 / PEAK,
                  rx_Msym_s=nsym / t_rx / 1e3, tx_ms=t_tx, tx_GBs=tx_b / t_tx / 1e6, tx_frac=tx_b / t_tx / 1e6 / PEAK,
                  tx_Msym_s=nf * cfg.frame_syms / t_tx / 1e3, ber=cnt[0] / cnt[1], locked=cnt[4] / cnt[5], peak_GBs=PEAK,
                  clocks=clocks)
