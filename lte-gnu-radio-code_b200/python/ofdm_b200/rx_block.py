@@ -140,6 +140,8 @@ class RxBlockBase(gr.sync_block):
             raise ValueError("input lives on %s, the block on %s" % (rx.device, self.modem.device))
         c = self.cfg
         if rx.numel() == 0:
+            if out is not None:
+                self.last_written = 0
             return np.zeros(0, np.int32), torch.empty((0, c.num_data_bins), dtype=torch.complex64, device=rx.device)
         if getattr(self, "_d_eq", None) is None:
             max_rows = _lib.lib().ofdm_rx_block_max_rows(self._blk)
