@@ -109,6 +109,13 @@ def test_block_names_and_signatures_match_the_reference():
         ["pickle_directory", "pickle_file"]
     assert [p for p in inspect.signature(OFDMReceiver.BitRecovery.__init__).parameters][1:4] == \
         ["modulation", "directory_name", "diagnostics"]
+    # the additive vector-item blocks keep the reference's argument names and order where they still apply
+    pos = [p.name for p in inspect.signature(utsa_ofdm.SynchAndChanEstVec.__init__).parameters.values()
+           if p.kind == p.POSITIONAL_OR_KEYWORD][1:]
+    assert pos == ["nfft", "cp_len", "num_synch_bins", "synch_dat", "num_data_bins", "snr", "scale_factor_gate"]
+    pos = [p.name for p in inspect.signature(RXOFDM.synch_and_chan_est_vec.__init__).parameters.values()
+           if p.kind == p.POSITIONAL_OR_KEYWORD][1:]
+    assert pos == ["nfft", "cp_len", "num_synch_bins", "synch_dat", "num_data_bins", "snr"]
 
 
 def test_grc_descriptors_keep_ids_and_make_templates():
@@ -125,6 +132,9 @@ def test_grc_descriptors_keep_ids_and_make_templates():
         "OFDMReceiver_SynchEstFOAndDSSS.block.yml": ("OFDMReceiver_SynchEstFOAndDSSS", "OFDMReceiver.SynchEstFOAndDSSS(", 5),
         "OFDMReceiver_SynchronizeAndEstimate.block.yml": ("OFDMReceiver_SynchronizeAndEstimate",
                                                           "OFDMReceiver.SynchronizeAndEstimate(", 1),
+        # additive: one frame per item ("vector I/O with vlen = frame")
+        "utsa_ofdm_SynchAndChanEstVec.block.yml": ("utsa_ofdm_SynchAndChanEstVec", "utsa_ofdm.SynchAndChanEstVec(", 7),
+        "RXOFDM_synch_and_chan_est_vec.block.yml": ("RXOFDM_synch_and_chan_est_vec", "RXOFDM.synch_and_chan_est_vec(", 6),
     }
     for fn, (bid, make, nargs) in want.items():
         d = yaml.safe_load(open(os.path.join(grc, fn)))

@@ -411,3 +411,59 @@ def test_device_buffer_work_equals_host_work(golden, variant):
     assert len(rows) == 0 and eq.shape == (0, 60)
     host.close()
     dev.close()
+
+
+@pytest.mark.parametrize("variant,bps,soft", [("utsa", 2, False), ("utsa", 4, True), ("rxofdm", 2, False)])
+def test_vector_item_block_matches_oracle_frames(variant, bps, soft):
+    """SURVEY.md 8f rank 3, "vector I/O with vlen = frame": one frame per scheduler item in, its equalised data symbols
+    (and LLRs) per item out, written straight into the scheduler's output buffers.  Per frame it is the arithmetic of
+    one accepted lock of the reference's work() (SynchAndChanEst.py:145-248) -- checked against oo.rx_frames on the same
+    samples -- and identical to the framed receiver called directly.  Two calls of different item counts (no state
+    crosses calls), a frame of noise that must come back unlocked, and output buffers that are not directly usable
+    (wrong dtype) taking the copy path."""
+    import RXOFDM
+    import utsa_ofdm
+    from ofdm_b200 import Modem, ModemConfig
+    nf = 11
+    if variant == "utsa":
+        blk = utsa_ofdm.SynchAndChanEstVec(64, 16, 62, [1, 3], 60, 100, 0.7, modulation=bps, soft=soft, noise_var=0.02)
+        prm = oo.ModemParams(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=bps, snr=100, gate=0.7)
+    else:
+        blk = RXOFDM.synch_and_chan_est_vec(64, 16, 62, [1, 3], 60, 50, modulation=bps, zc_root=23, soft=soft)
+        prm = oo.ModemParams(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=bps, snr=50,
+                             compat="rxofdm", zc_root=23)
+    assert blk.in_sig == [(np.complex64, 320)]
+    assert blk.out_sig == [(np.complex64, 180)] + ([(np.float32, 180 * bps)] if soft else [])
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 2, nf * 3 * 60 * bps)
+    tx = oo.tx_modulate(bits, prm, nf)
+    rx = oo.add_awgn(oo.apply_channel(tx, oo.reference_channel(64))[:len(tx)], 1e-3, rng).astype(np.complex64)
+    items = rx.reshape(nf, 320).copy()
+    items[7] = (rng.standard_normal(320) + 1j * rng.standard_normal(320)).astype(np.complex64) * 0.5   # not a frame
+    ref = oo.rx_frames(items.reshape(-1), nf, prm)
+    assert ref["locked"].sum() == nf - 1 and not ref["locked"][7]
+    outs = [np.full((nf, 180), 9 + 9j, np.complex64)] + ([np.full((nf, 180 * bps), 9, np.float32)] if soft else [])
+    # first call: 4 items, second call: the other 7
+    assert blk.work([items[:4]], [o[:4] for o in outs]) == 4
+    assert np.array_equal(blk.locked, ref["locked"][:4]) and np.array_equal(blk.delay, ref["delay"][:4])
+    assert blk.work([items[4:]], [o[4:] for o in outs]) == 7
+    assert np.array_equal(blk.locked, ref["locked"][4:]) and np.array_equal(blk.delay, ref["delay"][4:])
+    assert rel_err(blk.peak, ref["peak"][4:]) < 1e-4
+    good = ref["locked"].astype(bool)
+    assert rel_err(outs[0].reshape(nf, 3, 60)[good], ref["eq"][good]) < 1e-4
+    got_bits = oo.hard_bits(outs[0][good].reshape(-1), bps)
+    want_bits = bits.reshape(nf, -1)[good].reshape(-1)
+    assert np.array_equal(got_bits, want_bits)
+    # the same frames through the framed receiver directly: bit-identical (the block adds no arithmetic)
+    direct = Modem(blk.cfg).rx_frames_host(np.ascontiguousarray(items.reshape(-1)), nf, want_llr=soft, want_hard=False)
+    assert np.array_equal(direct["eq"].reshape(nf, 180), outs[0])
+    if soft:
+        assert np.array_equal(direct["llr"].reshape(nf, -1), outs[1])
+    # an output buffer of another dtype (complex128) takes the copy path and receives the same values
+    wide = [np.zeros((nf, 180), np.complex128)] + ([np.zeros((nf, 180 * bps), np.float64)] if soft else [])
+    assert blk.work([items], wide) == nf
+    assert np.array_equal(wide[0].astype(np.complex64), outs[0])
+    # fewer output items than input items: a sync block produces what fits
+    assert blk.work([items], [o[:3] for o in outs]) == 3
+    assert blk.work([items[:0]], [o[:0] for o in outs]) == 0
+    blk.close()

@@ -95,8 +95,40 @@ def run(name, n_samples):
                           clocks=clocks)), flush=True)
 
 
+def run_vec(n_items):
+    """The vector-item block (one frame per item): work() on n_items frames in host buffers."""
+    import utsa_ofdm
+    prm = oo.ModemParams(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=2, snr=100, gate=0.7)
+    rng = np.random.default_rng(11)
+    base = 64
+    tx = oo.tx_modulate(rng.integers(0, 2, base * 3 * 120), prm, base)
+    rx = oo.add_awgn(oo.apply_channel(tx, oo.reference_channel(64))[:len(tx)], 1e-3, rng).astype(np.complex64)
+    items = np.ascontiguousarray(np.tile(rx.reshape(base, 320), (n_items // base, 1)))
+    out = np.zeros((n_items, 180), np.complex64)
+    blk = utsa_ofdm.SynchAndChanEstVec(64, 16, 62, [1, 3], 60, 100, 0.7)
+    for _ in range(3):
+        blk.work([items], [out])
+    sampler = ClockSampler(0)
+    sampler.start()
+    ts = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        blk.work([items], [out])
+        ts.append(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    t = float(np.mean(ts))
+    ref = oo.rx_frames(items[:base].reshape(-1), base, prm)
+    err = float(np.max(np.abs(out[:base].reshape(base, 3, 60) - ref["eq"])) / np.sqrt(np.mean(np.abs(ref["eq"]) ** 2)))
+    print(json.dumps(dict(block="utsa_vec", items_per_call=n_items, samples_per_call=n_items * 320, ms_per_call_b200=1e3 * t,
+                          msamples_per_s_b200=n_items * 320 / t / 1e6, frames_locked=int(blk.locked.sum()),
+                          rel_err_vs_oracle=err, clocks=clocks)), flush=True)
+    blk.close()
+
+
 if __name__ == "__main__":
     # whole frames (the reference packing needs num_ofdm_symb % (M0+D) == 0); gr-RXOFDM keeps at most 100 locks
     for name, sizes in (("utsa", (4160, 32000)), ("rxofdm", (4160, 16000))):
         for n in sizes:
             run(name, n)
+    for n in (64, 1024, 16384):
+        run_vec(n)
