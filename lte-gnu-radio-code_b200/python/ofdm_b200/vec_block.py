@@ -86,3 +86,47 @@ class RxVecBlockBase(gr.sync_block):
         m = getattr(self, "modem", None)
         if m is not None and hasattr(m, "close"):
             m.close()
+
+
+class TxVecBlockBase(gr.sync_block):
+    """The transmit side of the same idea: one frame's packed payload per input item, one frame of samples per output
+    item.  The reference modulates OFFLINE (SDRScript.py:128-134 -> MultiAntennaSystem.multi_ant_binary_map /
+    multi_ant_symb_gen, :113-219) and its live blocks replay the stored waveform (tx_signal_transmitter.py:24-27); this
+    block runs that arithmetic -- bits -> points / Zadoff-Chu symbols -> IFFT -> prefix -> the two normalisations -- in
+    the flowgraph, one ofdm_tx_modulate_host call per work().
+
+        in_sig  = [(np.uint8, D * hard_stride)]      D payload rows, num_data_bins * bps bits each, MSB first, each row
+                                                     padded to whole bytes (np.packbits of the reference's bit rows)
+        out_sig = [(np.complex64, frame_len)]        M0 synch + D data symbols with their prefixes"""
+
+    def _setup_vec(self, name, nfft, cp_len, num_synch_bins, synch_dat, num_data_bins, modulation, zc_root, compat, device):
+        self.cfg = ModemConfig(nfft=int(nfft), cp_len=int(cp_len), num_synch_bins=int(num_synch_bins),
+                               num_data_bins=int(num_data_bins), m0=int(synch_dat[0]), d=int(synch_dat[1]),
+                               bps=modulation, compat=compat, zc_root=zc_root)
+        c = self.cfg
+        self.frame_len = c.frame_len
+        self.in_len = c.d * c.hard_stride
+        gr.sync_block.__init__(self, name=name, in_sig=[(np.uint8, self.in_len)], out_sig=[(np.complex64, self.frame_len)])
+        self.modem = Modem(c, device=device)
+
+    def work(self, input_items, output_items):
+        in0, out0 = input_items[0], output_items[0]
+        n = min(len(in0), len(out0))
+        if n == 0:
+            return 0
+        bits = in0[:n]
+        if not (isinstance(bits, np.ndarray) and bits.dtype == np.uint8 and bits.flags.c_contiguous):
+            bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        if bits.size != n * self.in_len:
+            raise ValueError("items of %d bytes expected, got %d" % (self.in_len, bits.size // n))
+        v = out0[:n]
+        if isinstance(v, np.ndarray) and v.dtype == np.complex64 and v.flags.c_contiguous:
+            self.modem.tx_modulate_host(bits.reshape(-1), n, out=v.reshape(-1))
+        else:
+            out0[:n] = self.modem.tx_modulate_host(bits.reshape(-1), n).reshape(np.shape(v))
+        return n
+
+    def close(self):
+        m = getattr(self, "modem", None)
+        if m is not None:
+            m.close()

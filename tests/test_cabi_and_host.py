@@ -135,6 +135,7 @@ def test_grc_descriptors_keep_ids_and_make_templates():
         # additive: one frame per item ("vector I/O with vlen = frame")
         "utsa_ofdm_SynchAndChanEstVec.block.yml": ("utsa_ofdm_SynchAndChanEstVec", "utsa_ofdm.SynchAndChanEstVec(", 7),
         "RXOFDM_synch_and_chan_est_vec.block.yml": ("RXOFDM_synch_and_chan_est_vec", "RXOFDM.synch_and_chan_est_vec(", 6),
+        "TXOFDM_tx_modulator_vec.block.yml": ("TXOFDM_tx_modulator_vec", "TXOFDM.tx_modulator_vec(", 6),
     }
     for fn, (bid, make, nargs) in want.items():
         d = yaml.safe_load(open(os.path.join(grc, fn)))

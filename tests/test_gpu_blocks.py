@@ -467,3 +467,32 @@ def test_vector_item_block_matches_oracle_frames(variant, bps, soft):
     assert blk.work([items], [o[:3] for o in outs]) == 3
     assert blk.work([items[:0]], [o[:0] for o in outs]) == 0
     blk.close()
+
+
+@pytest.mark.parametrize("bps", [2, 6])
+def test_vector_item_modulator_and_loopback(bps):
+    """The live modulator with one frame per item (TXOFDM.tx_modulator_vec): packed payload rows in, frames out --
+    the arithmetic of MultiAntennaSystem.py:113-219, checked against oo.tx_modulate -- and a loopback through the
+    vector-item receiver: tx items straight into rx items, the payload comes back without error."""
+    import TXOFDM
+    import utsa_ofdm
+    nf = 9
+    prm = oo.ModemParams(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=1, d=3, bps=bps, snr=100, gate=0.7)
+    txb = TXOFDM.tx_modulator_vec(64, 16, 62, [1, 3], 60, modulation=bps)
+    hs = (60 * bps + 7) // 8
+    assert txb.in_sig == [(np.uint8, 3 * hs)] and txb.out_sig == [(np.complex64, 320)]
+    rng = np.random.default_rng(21)
+    bits = rng.integers(0, 2, nf * 3 * 60 * bps)
+    packed = np.packbits(bits.reshape(nf * 3, 60 * bps).astype(np.uint8), axis=1).reshape(nf, 3 * hs)
+    frames = np.zeros((nf, 320), np.complex64)
+    assert txb.work([packed[:5]], [frames[:5]]) == 5 and txb.work([packed[5:]], [frames[5:]]) == 4
+    ref = oo.tx_modulate(bits, prm, nf)
+    assert rel_err(frames.reshape(-1), ref) < 1e-4
+    wide = np.zeros((nf, 320), np.complex128)                                   # copy path
+    assert txb.work([packed], [wide]) == nf and np.array_equal(wide.astype(np.complex64), frames)
+    rxb = utsa_ofdm.SynchAndChanEstVec(64, 16, 62, [1, 3], 60, 100, 0.7, modulation=bps)
+    eq = np.zeros((nf, 180), np.complex64)
+    assert rxb.work([frames], [eq]) == nf and rxb.locked.all() and not rxb.delay.any()
+    assert np.array_equal(oo.hard_bits(eq.reshape(-1), bps), bits)
+    txb.close()
+    rxb.close()
