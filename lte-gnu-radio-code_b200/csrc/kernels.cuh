@@ -446,6 +446,11 @@ __device__ __forceinline__ void pack_bits(const uint8_t *hb, unsigned *pk, uint8
 #ifndef OFDM_SPLIT_MIN_LOG2N
 #define OFDM_SPLIT_MIN_LOG2N 13
 #endif
+// ... and the same for the kernels below 64-QAM only.  B200, N=4096, same box, two alternating runs
+// (profiles/r2_ab_split_phase_n4096_final.txt): QPSK 0.602 -> 0.594 ms, 16-QAM 0.674 -> 0.670 ms, 64-QAM 0.805 -> 0.810 ms.
+#ifndef OFDM_SPLIT_LOWBPS_MIN_LOG2N
+#define OFDM_SPLIT_LOWBPS_MIN_LOG2N 12
+#endif
 // ... and for the bulk-row variant (64-QAM, N >= 1024), whose 2 CTAs x 8 warps per SM leave DRAM latency exposed: three
 // symbols ahead.  B200, LTE 20 MHz 64-QAM, one box, ms per launch (depth 1 / 2 / 3): 0.672 / 0.677 / 0.648 with the
 // power-table twiddles, 0.697 / 0.652 / -- with chained rows; the per-lane kernels lose 2-3 % at depth 2 and stay at 1.
@@ -631,6 +636,31 @@ __device__ __forceinline__ void chan_core(const DevParams &P, const float2 (&ys)
     }
 }
 
+// 64-QAM: a bin's six LLRs are 24 bytes at a 24-byte pitch, so three 8-byte stores per lane leave every 32-byte sector
+// written by three instructions.  WIDE form: two stores per bin instead -- one 8-byte and one 16-byte, ordered by the
+// parity of the bin's 8-byte slot so that the 16-byte one is aligned (even slot: {L0..L3} at q, {L4,L5} at q+4; odd
+// slot: {L0,L1} at q, {L2..L5} at q+2); neighbouring lanes' 8-byte halves then share a sector.  Six selects per bin buy
+// one store instruction less: B200, 64-QAM, same box (profiles/r2_ab_llr6_wide.txt): N=4096 0.470 -> 0.416 ms (one CTA
+// of 192-register threads per SM, whose registers wait in the store queue), but N=64..1024 +4..9 % slower, N=2048
+// +0.6 %, LTE grid 0.636 -> 0.667 ms -- so from N = 2^OFDM_LLR6_WIDE_MIN_LOG2N only.
+#ifndef OFDM_LLR6_WIDE_MIN_LOG2N
+#define OFDM_LLR6_WIDE_MIN_LOG2N 12
+#endif
+template <bool CS> __device__ __forceinline__ void store_llr6(float *q, const float (&L)[6], bool odd) {
+    const float2 a = odd ? make_float2(L[0], L[1]) : make_float2(L[4], L[5]);
+    const float4 b = odd ? make_float4(L[2], L[3], L[4], L[5]) : make_float4(L[0], L[1], L[2], L[3]);
+    st_out<CS>(reinterpret_cast<float2 *>(q + (odd ? 0 : 4)), a);
+    st_out<CS>(reinterpret_cast<float4 *>(q + (odd ? 2 : 0)), b);
+}
+template <bool CS, int BPS, bool WIDE> __device__ __forceinline__ void store_llr_pairs(float *q, const float (&L)[BPS], bool odd) {
+    if constexpr (BPS == 6 && WIDE) {
+        store_llr6<CS>(q, L, odd);
+    } else {
+#pragma unroll
+        for (int b = 0; b + 1 < BPS; b += 2) st_out<CS>(reinterpret_cast<float2 *>(q + b), make_float2(L[b], L[b + 1]));
+    }
+}
+
 // Everything a data symbol's epilogue needs that does not change from symbol to symbol.
 template <class C, int BPS> struct DataCtx {
     BinMap map;
@@ -671,6 +701,10 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
     float *lp = (staged ? ls : llr_out + row * P.ndb * BPS) + D.map.base_p * BPS;
     float *ln = (staged ? ls : llr_out + row * P.ndb * BPS) + (D.map.base_n - (PPT / 2) * T) * BPS;
     uint8_t *hp = hb + D.map.base_p, *hn = hb + (D.map.base_n - (PPT / 2) * T);
+    // parity of the 8-byte slot of this thread's LLRs in each spectrum half (a bin's pitch is m*T*BPS floats, T even)
+    static_assert(T % 2 == 0, "LLR slot parity is per thread");
+    const bool odd_p = (reinterpret_cast<unsigned long long>(lp) & 8ull) != 0, odd_n = (reinterpret_cast<unsigned long long>(ln) & 8ull) != 0;
+    (void)odd_p; (void)odd_n;
     // CH bins at a time: the chunk is skipped when no lane of the warp uses any of its bins (a warp-uniform vote, so no
     // divergence), otherwise all CH bins are computed branch-free and only the stores are predicated.  CH = PPT is the
     // fully dense form; CH = 0 keeps the per-lane branches of the loop further down.
@@ -705,9 +739,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
 #pragma unroll
                             for (int b = 0; b + 1 < BPS; b += 2) *reinterpret_cast<float2 *>(q + b) = make_float2(Lb[b], Lb[b + 1]);
                         } else {
-#pragma unroll
-                            for (int b = 0; b + 1 < BPS; b += 2)
-                                st_out<CS>(reinterpret_cast<float2 *>(q + b), make_float2(Lb[b], Lb[b + 1]));
+                            store_llr_pairs<CS, BPS, (C::LOG2N >= OFDM_LLR6_WIDE_MIN_LOG2N)>(q, Lb, m < PPT / 2 ? odd_p : odd_n);
                         }
                     }
                     if ((OFDM_EPI_MASKS >= 3 && !EQC) ? (hmask & (1u << m)) != 0 : (used && hard)) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
@@ -734,9 +766,7 @@ __device__ __forceinline__ void data_epilogue(const DevParams &P, const DataCtx<
 #pragma unroll
                         for (int b = 0; b + 1 < BPS; b += 2) *reinterpret_cast<float2 *>(q + b) = make_float2(Lb[b], Lb[b + 1]);
                     } else {
-#pragma unroll
-                        for (int b = 0; b + 1 < BPS; b += 2)
-                            st_out<CS>(reinterpret_cast<float2 *>(q + b), make_float2(Lb[b], Lb[b + 1]));
+                        store_llr_pairs<CS, BPS, (C::LOG2N >= OFDM_LLR6_WIDE_MIN_LOG2N)>(q, Lb, m < PPT / 2 ? odd_p : odd_n);
                     }
                 }
                 if (hard) (m < PPT / 2 ? hp : hn)[m * T] = (uint8_t)bits;
@@ -1000,7 +1030,7 @@ rx_frames_kernel(const DevParams P, const float2 *__restrict__ x, long long n_sa
                  uint8_t *__restrict__ hard_out) {
     constexpr int DEPTH = EPI == EPI_BULK ? OFDM_PF_DEPTH_BULK : OFDM_PF_DEPTH;
     // exchanges that wait on an mbarrier after preparing the next pass' twiddles instead of bar.sync (fft_core.cuh)
-    constexpr bool SPLIT = C::LOG2N >= OFDM_SPLIT_MIN_LOG2N && !SB;
+    constexpr bool SPLIT = (C::LOG2N >= OFDM_SPLIT_MIN_LOG2N || (BPS <= 4 && C::LOG2N >= OFDM_SPLIT_LOWBPS_MIN_LOG2N)) && !SB;
     OFDM_KERNEL_PROLOGUE_(GROUPS, false, PIL, GSM, SB, DEPTH)
     constexpr int N = C::N;
     const int L = N + P.cp, fs = P.m0 + P.d;
