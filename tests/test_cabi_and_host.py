@@ -144,6 +144,27 @@ def test_grc_descriptors_keep_ids_and_make_templates():
         assert d["templates"]["make"].count("${") == nargs
 
 
+def test_vector_item_descriptors_size_their_ports_like_the_blocks():
+    """The additive one-frame-per-item blocks: the vlen expressions GRC evaluates for the ports must be the item sizes
+    the classes announce (frame_len in, D * num_data_bins out; packed payload rows in for the modulator)."""
+    import yaml
+    from ofdm_b200 import ModemConfig
+    grc = os.path.join(ROOT, "lte-gnu-radio-code_b200", "grc")
+    for nfft, cp, sd, ndb, bps in ((64, 16, [1, 3], 60, 2), (2048, 144, [1, 13], 1200, 6), (128, 9, [2, 5], 100, 4)):
+        cfg = ModemConfig(nfft=nfft, cp_len=cp, num_synch_bins=nfft - 2, num_data_bins=ndb, m0=sd[0], d=sd[1], bps=bps)
+        env = dict(nfft=nfft, cp_len=cp, synch_dat=sd, num_data_bins=ndb, modulation=bps)
+
+        def vlen(port):
+            return eval(str(port["vlen"]).strip()[2:-1], {}, dict(env))
+        for fn in ("utsa_ofdm_SynchAndChanEstVec.block.yml", "RXOFDM_synch_and_chan_est_vec.block.yml"):
+            d = yaml.safe_load(open(os.path.join(grc, fn)))
+            assert vlen(d["inputs"][0]) == cfg.frame_len
+            assert vlen(d["outputs"][0]) == cfg.d * cfg.num_data_bins
+        d = yaml.safe_load(open(os.path.join(grc, "TXOFDM_tx_modulator_vec.block.yml")))
+        assert vlen(d["inputs"][0]) == cfg.d * cfg.hard_stride
+        assert vlen(d["outputs"][0]) == cfg.frame_len
+
+
 def test_sharding_helpers():
     from ofdm_b200 import shard
     assert shard.my_streams(10, 1, 4) == [1, 5, 9]
