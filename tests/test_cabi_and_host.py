@@ -165,6 +165,41 @@ def test_vector_item_descriptors_size_their_ports_like_the_blocks():
         assert vlen(d["outputs"][0]) == cfg.frame_len
 
 
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/ofdm_b200.h compiles as C99 (-pedantic) and as C++, and a C program linked
+    against libofdm_b200.so resolves every declared entry point and can call the ones that need no device."""
+    import shutil
+    import subprocess
+    from ofdm_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    names = declared_symbols()
+    src = tmp_path / "link.c"
+    refs = "\n".join("    (fn)%s," % n for n in names)
+    src.write_text('#include <stdio.h>\n#include "ofdm_b200.h"\n'
+                   "typedef void (*fn)(void);\nstatic const fn entry[] = {\n%s\n};\n"
+                   "int main(void) {\n"
+                   "    ofdm_plan *p = NULL;\n"
+                   "    if (ofdm_abi_version() != OFDM_B200_ABI_VERSION) return 2;\n"
+                   "    if (ofdm_plan_create(NULL, &p) == OFDM_OK || p != NULL) return 3;   /* bad argument: refused */\n"
+                   '    printf("%%d %%zu %%s\\n", ofdm_abi_version(), sizeof(entry) / sizeof(entry[0]), ofdm_last_error());\n'
+                   "    return 0;\n}\n" % refs)
+    inc = os.path.dirname(HEADER)
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-pedantic", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    if shutil.which("g++"):
+        subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-x", "c++", "-I", inc, HEADER], check=True)
+    exe = tmp_path / "link"
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lofdm_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 2)
+    assert int(out[0]) == 5 and int(out[1]) == len(names) == len(_lib.SIGNATURES)
+    assert out[2].strip()                                   # the refusal left a message in ofdm_last_error()
+
+
 def test_sharding_helpers():
     from ofdm_b200 import shard
     assert shard.my_streams(10, 1, 4) == [1, 5, 9]
