@@ -30,6 +30,8 @@ CASES = {
                           gate=0.5, noise_var=0.01), 13107),
     "n4096": (ModemConfig(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=3, bps=4, snr=100,
                           gate=0.5, noise_var=0.01), 3276),
+    "n4096_64qam": (ModemConfig(nfft=4096, cp_len=1024, num_synch_bins=4094, num_data_bins=3840, m0=1, d=3, bps=6, snr=100,
+                                gate=0.5, noise_var=0.01), 3276),
 }
 
 if __name__ == "__main__":
