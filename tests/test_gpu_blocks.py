@@ -496,3 +496,38 @@ def test_vector_item_modulator_and_loopback(bps):
     assert np.array_equal(oo.hard_bits(eq.reshape(-1), bps), bits)
     txb.close()
     rxb.close()
+
+
+@pytest.mark.parametrize("synch_dat,nsym", [([2, 3], 60), ([1, 6], 49), ([1, 1], 30)])
+def test_device_stream_packing_for_other_frame_shapes(synch_dat, nsym):
+    """The device-side packing rule (block_pack_kernel: the rows np.delete(est_data_freq, range(3, rows, M0+D)) keeps,
+    SynchAndChanEst.py:249-250 -- the deleted rows start at 3 whatever M0 is) for frame shapes other than the
+    reference's [1, 3]: the stream work_device() packs on the device equals the one work() packs on the host, bit for
+    bit, over three calls on a synthetic capture."""
+    import utsa_ofdm
+    m0, d = synch_dat
+    prm = oo.ModemParams(nfft=64, cp_len=16, num_synch_bins=62, num_data_bins=60, m0=m0, d=d, bps=2, snr=100, gate=0.7)
+    nf = nsym // (m0 + d) + 2
+    rng = np.random.default_rng(31)
+    bits = rng.integers(0, 2, nf * d * 120)
+    tx = oo.tx_modulate(bits, prm, nf)
+    rx = oo.add_awgn(oo.apply_channel(tx, oo.reference_channel(64))[:len(tx)], 1e-4, rng).astype(np.complex64)
+    rx = np.concatenate((np.zeros(37, np.complex64), rx))[:nsym * 80 + 50]
+
+    def make_block():
+        return utsa_ofdm.SynchAndChanEst(nsym, 64, 16, 62, synch_dat, 60, 100, 0.7, "/tmp/", "cest.pckl", 0, 0)
+    host, dev = make_block(), make_block()
+    d_rx = torch.from_numpy(rx).cuda()
+    out_h = np.zeros(len(rx), np.complex64)
+    for call in range(3):
+        host.work([rx], [out_h])
+        d_out = torch.full((len(rx),), 5 - 5j, dtype=torch.complex64, device="cuda")
+        dev.work_device(d_rx, out=d_out)
+        lw = host.last_written
+        assert dev.last_written == lw and (lw > 0) == (call > 0)
+        got = d_out.cpu().numpy()
+        assert np.array_equal(got[:lw], out_h[:lw]) and np.all(got[lw:] == 5 - 5j)
+        assert tuple(host.time_synch_ref) == tuple(dev.time_synch_ref)
+    assert host.time_synch_ref[2] > 0 and np.any(out_h[:lw] != 0)
+    host.close()
+    dev.close()
